@@ -1,0 +1,167 @@
+// CUDA runtime side of backend.h: allocation, streams, error handling, launch
+// accounting and optional per-kernel CUDA-event timing (product build only).
+#include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "backend.h"
+#include "pipeline.h"
+
+namespace gb200 {
+
+void cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", static_cast<int>(e), cudaGetErrorString(e),
+           file, line, what);
+  throw std::runtime_error(buf);
+}
+
+void* dev_alloc(size_t bytes) {
+  void* p = nullptr;
+  GB_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+  return p;
+}
+
+void dev_free(void* p) {
+  if (p) cudaFree(p);
+}
+
+void h2d(void* dst, const void* src, size_t n, Stream s) {
+  GB_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s));
+}
+void d2h(void* dst, const void* src, size_t n, Stream s) {
+  GB_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaStreamSynchronize(s));
+}
+void d2d(void* dst, const void* src, size_t n, Stream s) {
+  GB_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s));
+}
+void dev_zero(void* dst, size_t n, Stream s) { GB_CUDA(cudaMemsetAsync(dst, 0, n, s)); }
+void stream_sync(Stream s) { GB_CUDA(cudaStreamSynchronize(s)); }
+
+int cuda_device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void select_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    throw std::runtime_error(
+        "guetzli_b200: no CUDA device visible. This library has no CPU fallback; it needs a B200 (sm_100a).");
+  }
+  GB_CUDA(cudaSetDevice(device));
+}
+
+Stream make_stream() {
+  cudaStream_t s;
+  GB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  return s;
+}
+
+void destroy_stream(Stream s) { cudaStreamDestroy(s); }
+
+namespace {
+struct Prof {
+  std::mutex mu;
+  bool on = false;
+  long launches = 0;
+  struct Entry {
+    long launches = 0;
+    double ms = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t> > pending;
+  };
+  std::map<std::string, Entry> by_name;
+  cudaEvent_t cur_start = nullptr;
+};
+Prof& prof() {
+  static Prof p;
+  return p;
+}
+
+void drain(Prof::Entry& e) {
+  for (size_t i = 0; i < e.pending.size(); ++i) {
+    float ms = 0;
+    cudaEventSynchronize(e.pending[i].second);
+    cudaEventElapsedTime(&ms, e.pending[i].first, e.pending[i].second);
+    e.ms += ms;
+    cudaEventDestroy(e.pending[i].first);
+    cudaEventDestroy(e.pending[i].second);
+  }
+  e.pending.clear();
+}
+}  // namespace
+
+void note_launch(const char* name, Stream s) {
+  Prof& p = prof();
+  std::lock_guard<std::mutex> lock(p.mu);
+  ++p.launches;
+  Prof::Entry& e = p.by_name[name];
+  ++e.launches;
+  if (p.on) {
+    cudaEvent_t a;
+    cudaEventCreate(&a);
+    cudaEventRecord(a, s);
+    p.cur_start = a;
+  }
+}
+
+void note_launch_end(const char* name, Stream s) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) cuda_fail(err, name, __FILE__, __LINE__);
+  Prof& p = prof();
+  std::lock_guard<std::mutex> lock(p.mu);
+  if (p.on && p.cur_start) {
+    cudaEvent_t b;
+    cudaEventCreate(&b);
+    cudaEventRecord(b, s);
+    Prof::Entry& e = p.by_name[name];
+    e.pending.push_back(std::make_pair(p.cur_start, b));
+    p.cur_start = nullptr;
+    if (e.pending.size() > 256) drain(e);
+  }
+}
+
+long total_launches() {
+  Prof& p = prof();
+  std::lock_guard<std::mutex> lock(p.mu);
+  return p.launches;
+}
+
+void profiling_enable(bool on) {
+  Prof& p = prof();
+  std::lock_guard<std::mutex> lock(p.mu);
+  p.on = on;
+}
+
+std::vector<KernelStat> profiling_snapshot() {
+  Prof& p = prof();
+  std::lock_guard<std::mutex> lock(p.mu);
+  std::vector<KernelStat> out;
+  for (std::map<std::string, Prof::Entry>::iterator it = p.by_name.begin(); it != p.by_name.end(); ++it) {
+    drain(it->second);
+    KernelStat k;
+    k.name = it->first;
+    k.launches = it->second.launches;
+    k.ms = it->second.ms;
+    out.push_back(k);
+  }
+  return out;
+}
+
+void profiling_reset() {
+  Prof& p = prof();
+  std::lock_guard<std::mutex> lock(p.mu);
+  for (std::map<std::string, Prof::Entry>::iterator it = p.by_name.begin(); it != p.by_name.end(); ++it)
+    drain(it->second);
+  p.by_name.clear();
+  p.launches = 0;
+}
+
+}  // namespace gb200

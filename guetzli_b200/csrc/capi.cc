@@ -1,0 +1,230 @@
+// C ABI (include/guetzli_b200.h) over the C++ implementation.
+#include "guetzli_b200.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <exception>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "jpeg_out.h"
+#include "pipeline.h"
+#include "search.h"
+#include "tables.h"
+
+namespace gb200 {
+long total_launches();
+void profiling_enable(bool on);
+std::vector<KernelStat> profiling_snapshot();
+void profiling_reset();
+#if !defined(GB200_HOSTSIM)
+int cuda_device_count();
+#endif
+}  // namespace gb200
+
+namespace {
+thread_local std::string g_err;
+
+template <class F>
+int guarded(F f) {
+  try {
+    f();
+    return 1;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+  } catch (...) {
+    g_err = "unknown error";
+  }
+  return 0;
+}
+}  // namespace
+
+struct gb200_image {
+  gb200::ImageContext* ctx;
+};
+
+extern "C" {
+
+void gb200_params_default(gb200_params* p) {
+  p->butteraugli_target = 1.0f;
+  p->clear_metadata = 1;
+  p->try_420 = 0;
+  p->force_420 = 0;
+  p->use_silver_screen = 0;
+  p->zeroing_greedy_lookahead = 3;
+  p->new_zeroing_model = 1;
+}
+
+double gb200_butteraugli_score_for_quality(double quality) { return gb200::distance_for_quality(quality); }
+
+int gb200_process_rgb(const gb200_params* params, const uint8_t* rgb, int w, int h, int device,
+                      gb200_log_fn log, void* log_user, uint8_t** out, size_t* out_len,
+                      gb200_stats* stats) {
+  *out = nullptr;
+  *out_len = 0;
+  bool ok = false;
+  int guarded_ok = guarded([&]() {
+    gb200::SearchParams sp;
+    if (params) {
+      sp.butteraugli_target = params->butteraugli_target;
+      sp.clear_metadata = params->clear_metadata != 0;
+      sp.try_420 = params->try_420 != 0;
+      sp.force_420 = params->force_420 != 0;
+      sp.use_silver_screen = params->use_silver_screen != 0;
+      sp.zeroing_greedy_lookahead = params->zeroing_greedy_lookahead;
+      sp.new_zeroing_model = params->new_zeroing_model != 0;
+    }
+    gb200::SearchStats st;
+    std::string jpeg, err;
+    ok = gb200::process_rgb(sp, rgb, w, h, device, log, log_user, &jpeg, &st, &err);
+    if (!ok) g_err = err;
+    if (!jpeg.empty()) {
+      *out = static_cast<uint8_t*>(malloc(jpeg.size()));
+      memcpy(*out, jpeg.data(), jpeg.size());
+      *out_len = jpeg.size();
+    }
+    if (stats) {
+      stats->iterations = st.iterations;
+      stats->iterations_up = st.iterations_up;
+      stats->iterations_down = st.iterations_down;
+      stats->compares = st.compares;
+      stats->gpu_launches = st.gpu_launches;
+      stats->ms_total = st.ms_total;
+      stats->ms_device_setup = st.ms_device_setup;
+      stats->ms_compare = st.ms_compare;
+      stats->ms_zeroing = st.ms_zeroing;
+      stats->ms_jpeg = st.ms_jpeg;
+      stats->ms_sort = st.ms_sort;
+      stats->ms_walk = st.ms_walk;
+    }
+  });
+  return (guarded_ok && ok) ? 1 : 0;
+}
+
+void gb200_free(void* p) { free(p); }
+const char* gb200_last_error(void) { return g_err.c_str(); }
+const char* gb200_backend_name(void) { return gb200::backend_name(); }
+
+int gb200_device_count(void) {
+#if defined(GB200_HOSTSIM)
+  return 1;
+#else
+  return gb200::cuda_device_count();
+#endif
+}
+
+gb200_image* gb200_image_create(const uint8_t* rgb, int w, int h, int device) {
+  gb200_image* img = nullptr;
+  guarded([&]() {
+    if (!rgb || w <= 0 || h <= 0 || w >= 65536 || h >= 65536) throw std::runtime_error("bad image size");
+    gb200::ImageContext* ctx = new gb200::ImageContext(rgb, w, h, device);
+    img = new gb200_image;
+    img->ctx = ctx;
+  });
+  return img;
+}
+
+void gb200_image_destroy(gb200_image* img) {
+  if (!img) return;
+  guarded([&]() { delete img->ctx; });
+  delete img;
+}
+
+int gb200_image_num_blocks(const gb200_image* img) { return img->ctx->geom().nblocks; }
+
+int gb200_image_orig_coeffs(gb200_image* img, int16_t* out) {
+  return guarded([&]() {
+    const std::vector<int16_t>& c = img->ctx->orig_coeffs();
+    memcpy(out, c.data(), c.size() * sizeof(int16_t));
+  });
+}
+
+int gb200_image_apply_global_quant(gb200_image* img, const int* q) {
+  return guarded([&]() { img->ctx->apply_global_quant(q); });
+}
+int gb200_image_upload_candidate(gb200_image* img, const int16_t* coeffs) {
+  return guarded([&]() { img->ctx->upload_candidate(coeffs); });
+}
+int gb200_image_download_candidate(gb200_image* img, int16_t* coeffs) {
+  return guarded([&]() { img->ctx->download_candidate(coeffs); });
+}
+int gb200_image_scatter(gb200_image* img, const int* index, const int16_t* value, int n) {
+  return guarded([&]() {
+    img->ctx->scatter_coeffs(std::vector<int>(index, index + n), std::vector<int16_t>(value, value + n));
+  });
+}
+int gb200_image_compare(gb200_image* img, float* distance) {
+  return guarded([&]() { *distance = img->ctx->compare(); });
+}
+int gb200_image_distmap(gb200_image* img, float* out) {
+  return guarded([&]() { img->ctx->download_distmap(out); });
+}
+int gb200_image_block_weights(gb200_image* img, int direction, int radius, double target_distance,
+                              int zero_distmap, float* out) {
+  return guarded([&]() { img->ctx->block_weights(direction, radius, target_distance, zero_distmap != 0, out); });
+}
+int gb200_image_zeroing_orders(gb200_image* img, float block_error_limit, int lookahead, uint8_t* idx,
+                               float* err, int* count) {
+  return guarded([&]() {
+    std::vector<uint8_t> vi;
+    std::vector<float> ve;
+    std::vector<int> vc;
+    img->ctx->zeroing_orders(block_error_limit, lookahead, &vi, &ve, &vc);
+    memcpy(idx, vi.data(), vi.size());
+    memcpy(err, ve.data(), ve.size() * sizeof(float));
+    memcpy(count, vc.data(), vc.size() * sizeof(int));
+  });
+}
+int gb200_image_debug_blur(gb200_image* img, const float* in, float* out, int blur_id) {
+  return guarded([&]() { img->ctx->debug_blur(in, out, blur_id); });
+}
+int gb200_image_debug_opsin(gb200_image* img, const float* rgb_linear, float* xyb) {
+  return guarded([&]() { img->ctx->debug_opsin(rgb_linear, xyb); });
+}
+int gb200_image_debug_separate(gb200_image* img, const float* xyb, float* psycho10) {
+  return guarded([&]() { img->ctx->debug_separate(xyb, psycho10); });
+}
+int gb200_image_debug_render(gb200_image* img, float* linear_rgb) {
+  return guarded([&]() { img->ctx->debug_render(linear_rgb); });
+}
+int gb200_image_debug_psycho0(gb200_image* img, float* psycho10) {
+  return guarded([&]() { img->ctx->debug_psycho0(psycho10); });
+}
+int gb200_image_debug_corner_mask(gb200_image* img, float* out) {
+  return guarded([&]() { img->ctx->debug_corner_mask(out); });
+}
+
+int gb200_write_jpeg(const int16_t* coeffs, int w, int h, const int* q, uint8_t** out, size_t* out_len) {
+  return guarded([&]() {
+    gb200::CoeffImage ci;
+    ci.w = w;
+    ci.h = h;
+    ci.bw = (w + 7) / 8;
+    ci.bh = (h + 7) / 8;
+    ci.nblocks = ci.bw * ci.bh;
+    ci.coeffs = coeffs;
+    memcpy(ci.q, q, sizeof(ci.q));
+    std::string s = gb200::write_jpeg(ci);
+    *out = static_cast<uint8_t*>(malloc(s.size() + 1));
+    memcpy(*out, s.data(), s.size());
+    *out_len = s.size();
+  });
+}
+
+void gb200_profile_enable(int on) { gb200::profiling_enable(on != 0); }
+void gb200_profile_reset(void) { gb200::profiling_reset(); }
+int gb200_profile_get(char (*names)[48], long* launches, double* ms, int cap) {
+  std::vector<gb200::KernelStat> s = gb200::profiling_snapshot();
+  const int n = static_cast<int>(s.size());
+  for (int i = 0; i < n && i < cap; ++i) {
+    strncpy(names[i], s[i].name.c_str(), 47);
+    names[i][47] = 0;
+    launches[i] = s[i].launches;
+    ms[i] = s[i].ms;
+  }
+  return n;
+}
+
+}  // extern "C"

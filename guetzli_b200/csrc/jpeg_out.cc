@@ -1,0 +1,474 @@
+// See jpeg_out.h.
+#include "jpeg_out.h"
+
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "tables.h"
+
+namespace gb200 {
+
+namespace {
+
+inline int floor_log2_nz(uint32_t n) { return 31 ^ __builtin_clz(n); }
+inline int floor_log2(uint32_t n) { return n == 0 ? -1 : floor_log2_nz(n); }
+
+struct TreeNode {
+  uint32_t count;
+  int16_t left;            // -1 for leaves
+  int16_t right_or_value;  // symbol for leaves
+};
+
+// Depth of every leaf below root; false if any leaf is deeper than limit.
+bool assign_depths(const TreeNode* pool, int root, int limit, uint8_t* depth) {
+  int stack_node[64], stack_level[64];
+  int sp = 0;
+  stack_node[sp] = root;
+  stack_level[sp] = 0;
+  ++sp;
+  while (sp > 0) {
+    --sp;
+    const int p = stack_node[sp], level = stack_level[sp];
+    if (pool[p].left >= 0) {
+      if (level + 1 > limit) return false;
+      stack_node[sp] = pool[p].right_or_value;
+      stack_level[sp] = level + 1;
+      ++sp;
+      stack_node[sp] = pool[p].left;
+      stack_level[sp] = level + 1;
+      ++sp;
+    } else {
+      depth[pool[p].right_or_value] = static_cast<uint8_t>(level);
+    }
+  }
+  return true;
+}
+
+}  // namespace
+
+void huffman_code_lengths(const uint32_t* counts, int n, int limit, uint8_t* depth) {
+  std::vector<TreeNode> tree(2 * n + 2);
+  for (uint32_t floor_count = 1;; floor_count *= 2) {
+    int leaves = 0;
+    for (int i = n - 1; i >= 0; --i) {
+      if (counts[i]) {
+        TreeNode t = {std::max<uint32_t>(counts[i], floor_count), -1, static_cast<int16_t>(i)};
+        tree[leaves++] = t;
+      }
+    }
+    if (leaves == 1) {
+      depth[tree[0].right_or_value] = 1;
+      return;
+    }
+    // least frequent first; equal counts: larger symbol first
+    std::sort(tree.begin(), tree.begin() + leaves, [](const TreeNode& a, const TreeNode& b) {
+      if (a.count != b.count) return a.count < b.count;
+      return a.right_or_value > b.right_or_value;
+    });
+    // two-queue merge: leaves in [0,leaves), parents appended from leaves+1
+    const TreeNode sentinel = {~static_cast<uint32_t>(0), -1, -1};
+    tree[leaves] = sentinel;
+    tree[leaves + 1] = sentinel;
+    int i = 0, j = leaves + 1;
+    for (int k = leaves - 1; k != 0; --k) {
+      int left, right;
+      if (tree[i].count <= tree[j].count) left = i++; else left = j++;
+      if (tree[i].count <= tree[j].count) right = i++; else right = j++;
+      const int parent = 2 * leaves - k;
+      tree[parent].count = tree[left].count + tree[right].count;
+      tree[parent].left = static_cast<int16_t>(left);
+      tree[parent].right_or_value = static_cast<int16_t>(right);
+      tree[parent + 1] = sentinel;
+    }
+    if (assign_depths(tree.data(), 2 * leaves - 1, limit, depth)) return;
+  }
+}
+
+size_t histogram_header_bits(const SymbolHistogram& h) {
+  size_t bits = 17 * 8;
+  for (int i = 0; i + 1 < SymbolHistogram::kSize; ++i)
+    if (h.counts[i] > 0) bits += 8;
+  return bits;
+}
+
+size_t histogram_data_bits(const SymbolHistogram& h, const uint8_t* depth) {
+  size_t bits = 0;
+  for (int i = 0; i + 1 < SymbolHistogram::kSize; ++i) bits += (h.counts[i] / 2) * (depth[i] + (i & 0xf));
+  bits += (bits * 3 + 512) >> 10;  // 0xff stuffing estimate
+  return bits;
+}
+
+size_t cluster_histograms(SymbolHistogram* h, size_t* num, int* index, uint8_t* depth) {
+  const int K = SymbolHistogram::kSize;
+  memset(depth, 0, *num * K);
+  size_t costs[4];
+  for (size_t i = 0; i < *num; ++i) {
+    index[i] = static_cast<int>(i);
+    huffman_code_lengths(h[i].counts, K, 16, &depth[i * K]);
+    costs[i] = histogram_header_bits(h[i]) + histogram_data_bits(h[i], &depth[i * K]);
+  }
+  const size_t orig_num = *num;
+  while (*num > 1) {
+    const size_t last = *num - 1, prev = *num - 2;
+    SymbolHistogram both(h[last]);
+    both.merge(h[prev]);
+    uint8_t depth_both[SymbolHistogram::kSize] = {0};
+    huffman_code_lengths(both.counts, K, 16, depth_both);
+    const size_t cost_both = histogram_header_bits(both) + histogram_data_bits(both, depth_both);
+    if (cost_both < costs[last] + costs[prev]) {
+      h[prev] = both;
+      h[last] = SymbolHistogram();
+      costs[prev] = cost_both;
+      memcpy(&depth[prev * K], depth_both, sizeof(depth_both));
+      for (size_t i = 0; i < orig_num; ++i)
+        if (index[i] == static_cast<int>(last)) index[i] = static_cast<int>(prev);
+      --(*num);
+    } else {
+      break;
+    }
+  }
+  size_t total = 0;
+  for (size_t i = 0; i < *num; ++i) total += costs[i];
+  return (total + 7) / 8;
+}
+
+int num_output_components(const CoeffImage& img) {
+  if (img.as_encoded) return 3;
+  const size_t n = static_cast<size_t>(img.nblocks) * 64;
+  const int16_t* p = img.coeffs + n;
+  for (size_t i = 0; i < 2 * n; ++i)
+    if (p[i] != 0) return 3;
+  return 1;
+}
+
+void ac_symbols_of_block(const int16_t* dq, const int* q, int weight, SymbolHistogram* h) {
+  const int* zz = zigzag_to_natural();
+  int run = 0;
+  for (int k = 1; k < 64; ++k) {
+    const int nat = zz[k];
+    const int16_t coeff = dq[nat];
+    if (coeff == 0) {
+      ++run;
+      continue;
+    }
+    while (run > 15) {
+      h->add(0xf0, weight);
+      run -= 16;
+    }
+    const int nbits = floor_log2_nz(abs(coeff / q[nat])) + 1;
+    h->add((run << 4) + nbits, weight);
+    run = 0;
+  }
+  if (run > 0) h->add(0, weight);
+}
+
+void build_ac_histograms(const CoeffImage& img, SymbolHistogram* h3) {
+  const int ncomp = num_output_components(img);
+  for (int c = 0; c < ncomp; ++c)
+    for (int b = 0; b < img.nblocks; ++b) ac_symbols_of_block(img.block(c, b), img.q[c], 1, &h3[c]);
+}
+
+namespace {
+void build_dc_histograms(const CoeffImage& img, int ncomp, SymbolHistogram* h) {
+  for (int c = 0; c < ncomp; ++c) {
+    int last = 0;
+    const int q0 = img.q[c][0];
+    for (int b = 0; b < img.nblocks; ++b) {
+      const int dc = img.block(c, b)[0] / q0;
+      const int diff = abs(static_cast<int16_t>(dc) - static_cast<int16_t>(last));
+      h[c].add(floor_log2(diff) + 1);
+      last = dc;
+    }
+  }
+}
+
+// Distinct quant tables in component order (g/jpeg_data.cc:70).
+struct QuantSet {
+  int num;
+  int table[3][64];
+  int precision[3];
+  int comp_idx[3];
+};
+QuantSet dedup_quant(const CoeffImage& img, int ncomp) {
+  QuantSet qs;
+  qs.num = 0;
+  if (img.as_encoded) {
+    qs.num = 3;
+    for (int c = 0; c < 3; ++c) {
+      memcpy(qs.table[c], img.q[c], sizeof(qs.table[c]));
+      qs.precision[c] = 0;
+      qs.comp_idx[c] = c;
+    }
+    return qs;
+  }
+  for (int c = 0; c < ncomp; ++c) {
+    int found = -1;
+    for (int j = 0; j < qs.num; ++j)
+      if (memcmp(img.q[c], qs.table[j], sizeof(qs.table[j])) == 0) {
+        found = j;
+        break;
+      }
+    if (found < 0) {
+      memcpy(qs.table[qs.num], img.q[c], sizeof(qs.table[0]));
+      qs.precision[qs.num] = 0;
+      for (int k = 0; k < 64; ++k)
+        if (img.q[c][k] > 0xff) qs.precision[qs.num] = 1;
+      found = qs.num++;
+    }
+    qs.comp_idx[c] = found;
+  }
+  return qs;
+}
+
+struct CodeTable {
+  uint8_t depth[256];
+  int code[256];
+};
+
+// Canonical JPEG code from code lengths; the phantom symbol 256 sorts last
+// within the longest length and is dropped, which reserves the all-ones code
+// (g/jpeg_data_writer.cc:130-183,401-427).
+void canonical_code(const uint8_t* depth, int* counts /*[17]*/, int* values /*[257]*/, CodeTable* table) {
+  const int K = SymbolHistogram::kSize;
+  for (int i = 0; i <= 16; ++i) counts[i] = 0;
+  for (int i = 0; i < K; ++i)
+    if (depth[i] > 0) ++counts[depth[i]];
+  int offset[17] = {0};
+  for (int i = 1; i <= 16; ++i) offset[i] = offset[i - 1] + counts[i - 1];
+  for (int i = 0; i < K; ++i)
+    if (depth[i] > 0) values[offset[depth[i]]++] = i;
+  for (int i = 0; i < 256; ++i) table->depth[i] = 255;
+  int total = 0;
+  for (int l = 1; l <= 16; ++l) total += counts[l];
+  if (total == 0) return;
+  int code = 0, p = 0;
+  for (int l = 1; l <= 16; ++l) {
+    for (int i = 0; i < counts[l]; ++i, ++p) {
+      if (p < total - 1) {  // all but the phantom
+        table->depth[values[p]] = static_cast<uint8_t>(l);
+        table->code[values[p]] = code;
+      }
+      ++code;
+    }
+    code <<= 1;
+  }
+}
+
+struct BitSink {
+  std::string* out;
+  uint64_t acc;
+  int nbits;  // bits currently held in acc (low end)
+  explicit BitSink(std::string* o) : out(o), acc(0), nbits(0) {}
+  inline void put_byte(int b) {
+    out->push_back(static_cast<char>(b));
+    if (b == 0xff) out->push_back(0);
+  }
+  inline void put(int n, uint32_t bits) {
+    acc = (acc << n) | bits;
+    nbits += n;
+    while (nbits >= 8) {
+      nbits -= 8;
+      put_byte(static_cast<int>((acc >> nbits) & 0xff));
+    }
+  }
+  void finish() {
+    if (nbits > 0) {
+      const int pad = 8 - nbits;
+      put_byte(static_cast<int>(((acc << pad) | ((1u << pad) - 1)) & 0xff));
+      nbits = 0;
+    }
+  }
+};
+
+}  // namespace
+
+size_t estimate_dc_bytes(const CoeffImage& img) {
+  // EstimateDCSize builds ncomp histograms (of the saved JPEG) and clusters them.
+  const int ncomp = num_output_components(img);
+  SymbolHistogram h[3];
+  build_dc_histograms(img, ncomp, h);
+  size_t num = ncomp;
+  int index[4];
+  uint8_t depth[3 * SymbolHistogram::kSize];
+  return cluster_histograms(h, &num, index, depth);
+}
+
+size_t jpeg_header_bytes(const CoeffImage& img) {
+  const int ncomp = num_output_components(img);
+  const QuantSet qs = dedup_quant(img, ncomp);
+  size_t n = 2 + 18;  // SOI, APP0
+  n += 4;             // DQT marker + length
+  for (int i = 0; i < qs.num; ++i) n += 1 + (qs.precision[i] ? 2 : 1) * 64;
+  n += 10 + 3 * ncomp;  // SOF
+  n += 4;               // DHT marker + length
+  n += 8 + 2 * ncomp;   // SOS
+  n += 2;               // EOI
+  return n;
+}
+
+size_t compute_entropy_codes(const SymbolHistogram* h3, uint8_t* depths) {
+  const int K = SymbolHistogram::kSize;
+  SymbolHistogram clustered[3] = {h3[0], h3[1], h3[2]};
+  size_t num = 3;
+  int index[4];
+  uint8_t cdepth[3 * SymbolHistogram::kSize];
+  cluster_histograms(clustered, &num, index, cdepth);
+  for (int i = 0; i < 3; ++i) memcpy(&depths[i * K], &cdepth[index[i] * K], K);
+  size_t bytes = 0;
+  for (size_t i = 0; i < num; ++i) bytes += histogram_header_bits(clustered[i]) / 8;
+  return bytes;
+}
+
+size_t entropy_coded_bytes(const SymbolHistogram* h3, const uint8_t* depths) {
+  size_t bits = 0;
+  for (int i = 0; i < 3; ++i) bits += histogram_data_bits(h3[i], &depths[i * SymbolHistogram::kSize]);
+  return (bits + 7) / 8;
+}
+
+std::string write_jpeg(const CoeffImage& img) {
+  const int K = SymbolHistogram::kSize;
+  const int ncomp = num_output_components(img);
+  const QuantSet qs = dedup_quant(img, ncomp);
+  const int* zz = zigzag_to_natural();
+  std::string out;
+  out.reserve(static_cast<size_t>(img.nblocks) * 48 + 1024);
+  auto byte = [&out](int b) { out.push_back(static_cast<char>(b)); };
+
+  // SOI + JFIF APP0 (g/jpeg_data_writer.cc:52-63)
+  static const uint8_t kHead[] = {0xff, 0xd8, 0xff, 0xe0, 0x00, 0x10, 0x4a, 0x46, 0x49, 0x46,
+                                  0x00, 0x01, 0x01, 0x00, 0x00, 0x01, 0x00, 0x01, 0x00, 0x00};
+  out.append(reinterpret_cast<const char*>(kHead), sizeof(kHead));
+  // DQT
+  {
+    int len = 2;
+    for (int i = 0; i < qs.num; ++i) len += 1 + (qs.precision[i] ? 2 : 1) * 64;
+    byte(0xff); byte(0xdb); byte(len >> 8); byte(len & 0xff);
+    for (int i = 0; i < qs.num; ++i) {
+      byte((qs.precision[i] << 4) + (img.as_encoded ? 0 : i));
+      for (int k = 0; k < 64; ++k) {
+        const int v = qs.table[i][zz[k]];
+        if (qs.precision[i]) byte(v >> 8);
+        byte(v & 0xff);
+      }
+    }
+  }
+  // SOF1 (extended sequential, 0xc1)
+  {
+    const int len = 8 + 3 * ncomp;
+    byte(0xff); byte(0xc1); byte(len >> 8); byte(len & 0xff);
+    byte(8);
+    byte(img.h >> 8); byte(img.h & 0xff);
+    byte(img.w >> 8); byte(img.w & 0xff);
+    byte(ncomp);
+    for (int c = 0; c < ncomp; ++c) {
+      byte(c);
+      byte(0x11);
+      byte(img.as_encoded ? 0 : qs.comp_idx[c]);
+    }
+  }
+  // Huffman codes: cluster DC then AC histograms
+  SymbolHistogram dc_h[3], ac_h[3];
+  build_dc_histograms(img, ncomp, dc_h);
+  size_t num_dc = ncomp, num_ac = ncomp;
+  int dc_index[4], ac_index[4];
+  std::vector<uint8_t> dc_depth(3 * K), ac_depth(3 * K);
+  cluster_histograms(dc_h, &num_dc, dc_index, dc_depth.data());
+  for (int c = 0; c < ncomp; ++c)
+    for (int b = 0; b < img.nblocks; ++b) ac_symbols_of_block(img.block(c, b), img.q[c], 1, &ac_h[c]);
+  cluster_histograms(ac_h, &num_ac, ac_index, ac_depth.data());
+  CodeTable dc_table[3], ac_table[3];
+  {
+    int total_symbols = 0;
+    for (size_t i = 0; i < num_dc; ++i) total_symbols += dc_h[i].num_symbols();
+    for (size_t i = 0; i < num_ac; ++i) total_symbols += ac_h[i].num_symbols();
+    const int num_histo = static_cast<int>(num_dc + num_ac);
+    const int dht_len = 2 + num_histo * 17 + total_symbols;
+    byte(0xff); byte(0xc4); byte(dht_len >> 8); byte(dht_len & 0xff);
+    for (int i = 0; i < num_histo; ++i) {
+      const bool is_dc = i < static_cast<int>(num_dc);
+      const int idx = is_dc ? i : i - static_cast<int>(num_dc);
+      int counts[17], values[SymbolHistogram::kSize] = {0};
+      CodeTable table;
+      canonical_code(is_dc ? &dc_depth[idx * K] : &ac_depth[idx * K], counts, values, &table);
+      for (int c = 0; c < ncomp; ++c) {
+        if (is_dc && dc_index[c] == idx) dc_table[c] = table;
+        if (!is_dc && ac_index[c] == idx) ac_table[c] = table;
+      }
+      int max_len = 16;
+      while (max_len > 0 && counts[max_len] == 0) --max_len;
+      --counts[max_len];  // drop the phantom symbol
+      int total = 0;
+      for (int j = 0; j <= max_len; ++j) total += counts[j];
+      byte(is_dc ? i : idx + 0x10);
+      for (int j = 1; j <= 16; ++j) byte(counts[j]);
+      for (int j = 0; j < total; ++j) byte(values[j]);
+    }
+  }
+  // SOS
+  {
+    const int len = 6 + 2 * ncomp;
+    byte(0xff); byte(0xda); byte(len >> 8); byte(len & 0xff);
+    byte(ncomp);
+    for (int c = 0; c < ncomp; ++c) {
+      byte(c);
+      byte((dc_index[c] << 4) | ac_index[c]);
+    }
+    byte(0); byte(63); byte(0);
+  }
+  // entropy-coded scan, one block of each component per MCU (444)
+  {
+    BitSink bw(&out);
+    int last_dc[3] = {0, 0, 0};
+    for (int b = 0; b < img.nblocks; ++b) {
+      for (int c = 0; c < ncomp; ++c) {
+        const int16_t* dq = img.block(c, b);
+        const int* q = img.q[c];
+        const CodeTable& dct = dc_table[c];
+        const CodeTable& act = ac_table[c];
+        // DC difference (g/jpeg_data_writer.cc:460-474), int16 arithmetic
+        const int16_t dc = static_cast<int16_t>(dq[0] / q[0]);
+        int16_t diff = static_cast<int16_t>(dc - last_dc[c]);
+        last_dc[c] = dc;
+        int16_t bits = diff;
+        if (diff < 0) {
+          diff = static_cast<int16_t>(-diff);
+          --bits;
+        }
+        int nbits = floor_log2(static_cast<uint32_t>(static_cast<int>(diff))) + 1;
+        bw.put(dct.depth[nbits], dct.code[nbits]);
+        if (nbits > 0) bw.put(nbits, bits & ((1 << nbits) - 1));
+        int run = 0;
+        for (int k = 1; k < 64; ++k) {
+          const int nat = zz[k];
+          int v = dq[nat];
+          if (v == 0) {
+            ++run;
+            continue;
+          }
+          v /= q[nat];
+          int mag = v, low = v;
+          if (v < 0) {
+            mag = -v;
+            low = ~mag;
+          }
+          while (run > 15) {
+            bw.put(act.depth[0xf0], act.code[0xf0]);
+            run -= 16;
+          }
+          nbits = floor_log2_nz(mag) + 1;
+          const int symbol = (run << 4) + nbits;
+          bw.put(act.depth[symbol], act.code[symbol]);
+          bw.put(nbits, low & ((1 << nbits) - 1));
+          run = 0;
+        }
+        if (run > 0) bw.put(act.depth[0], act.code[0]);
+      }
+    }
+    bw.finish();
+  }
+  byte(0xff); byte(0xd9);
+  return out;
+}
+
+}  // namespace gb200

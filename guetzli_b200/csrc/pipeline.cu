@@ -1,0 +1,313 @@
+// Kernel sequences of the hot path (see pipeline.h).  Compiled by nvcc for
+// sm_100a in the product, and by g++ -DGB200_HOSTSIM for the CPU port.
+#include "pipeline.h"
+
+#include <string.h>
+
+#include <algorithm>
+
+#include "block_math.h"
+
+namespace gb200 {
+
+#if defined(GB200_HOSTSIM)
+static void select_device(int) {}
+static Stream make_stream() { return 0; }
+static void destroy_stream(Stream) {}
+long total_launches() { return 0; }
+void profiling_enable(bool) {}
+std::vector<KernelStat> profiling_snapshot() { return std::vector<KernelStat>(); }
+void profiling_reset() {}
+#else
+void select_device(int device);
+Stream make_stream();
+void destroy_stream(Stream s);
+long total_launches();
+void profiling_enable(bool on);
+std::vector<KernelStat> profiling_snapshot();
+void profiling_reset();
+#endif
+
+float* ImageContext::planes(int n) {
+  void* p = dev_alloc(sizeof(float) * g_.plane * n);
+  dev_zero(p, sizeof(float) * g_.plane * n, s_);
+  owned_.push_back(p);
+  return static_cast<float*>(p);
+}
+
+ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device)
+    : g_(make_geom(w, h)), device_(device) {
+  select_device(device);
+  s_ = make_stream();
+  t_ = build_tables(w, h, s_, &owned_, &ht_);
+  malta_call_params(malta_);
+  l2_asym_weights(&asym_w0_, &asym_w1_);
+
+  const size_t ncoef = static_cast<size_t>(3) * g_.nblocks * 64;
+  d_rgb_ = static_cast<uint8_t*>(dev_alloc(static_cast<size_t>(3) * w * h));
+  owned_.push_back(d_rgb_);
+  d_orig_ = static_cast<int16_t*>(dev_alloc(ncoef * 2));
+  owned_.push_back(d_orig_);
+  d_cand_ = static_cast<int16_t*>(dev_alloc(ncoef * 2));
+  owned_.push_back(d_cand_);
+  d_q_ = static_cast<int*>(dev_alloc(192 * sizeof(int)));
+  owned_.push_back(d_q_);
+  corner_mask_ = static_cast<float*>(dev_alloc(sizeof(float) * 3 * g_.nblocks));
+  owned_.push_back(corner_mask_);
+  block_max_ = static_cast<float*>(dev_alloc(sizeof(float) * g_.nblocks));
+  owned_.push_back(block_max_);
+  zero_block_max_ = static_cast<float*>(dev_alloc(sizeof(float) * g_.nblocks));
+  owned_.push_back(zero_block_max_);
+  dev_zero(zero_block_max_, sizeof(float) * g_.nblocks, s_);
+  weights_ = static_cast<float*>(dev_alloc(sizeof(float) * g_.nblocks));
+  owned_.push_back(weights_);
+  partial_ = static_cast<float*>(dev_alloc(sizeof(float) * 1024));
+  owned_.push_back(partial_);
+
+  ps0_ = planes(kPsychoPlanes);
+  lin_ = planes(3);
+  tmp_ = planes(3);
+  blr_ = planes(3);
+  xyb_ = planes(3);
+  lf_ = planes(3);
+  mf_in_ = planes(3);
+  mf_blr_ = planes(3);
+  hf_raw_ = planes(2);
+  hf_blr_ = planes(2);
+  ps1_ = planes(kPsychoPlanes);
+  diffs_ = planes(1);
+  ac_ = planes(2);
+  noise_ = planes(2);
+  mpre_ = planes(2);
+  sact_ = planes(3);
+  dm_ = planes(2);
+
+  metric_ = (w >= 32 && h >= 32);  // g/processor.cc:940: no Butteraugli below 32x32
+  h2d(d_rgb_, rgb, static_cast<size_t>(3) * w * h, s_);
+
+  // a2: one-time forward DCT; the host search keeps a copy of the coefficients.
+  launch_1d(s_, FdctBlocks{d_rgb_, d_orig_, g_}, g_.nblocks, "fdct_blocks");
+  d2d(d_cand_, d_orig_, ncoef * 2, s_);
+  orig_host_.resize(ncoef);
+  d2h(orig_host_.data(), d_orig_, ncoef * 2, s_);
+
+  if (!metric_) {
+    stream_sync(s_);
+    return;
+  }
+  // a3: PsychoImage of the original (pi0_), resident for the whole search.
+  launch_2d(s_, LinearizeRgb{d_rgb_, lin_, g_, t_.srgb_lin}, g_.w, g_.h, "linearize_rgb");
+  opsin(lin_, xyb_);
+  separate(xyb_, ps0_);
+
+  // a13: mask_xyz_ = Mask(xyb0, xyb0), only its block-corner samples are ever read.
+  launch_2d(s_, MaskDiffPreSelf{xyb_, mpre_, g_}, g_.w, g_.h, "mask_diff_pre_self");
+  blur(mpre_, sact_, 1, kBlurMaskX);
+  blur(mpre_ + g_.plane, sact_ + g_.plane, 1, kBlurMaskY0);
+  blur(mpre_ + g_.plane, sact_ + 2 * g_.plane, 1, kBlurMaskY1);
+  launch_1d(s_, BlockCornerMask{sact_, sact_ + g_.plane, sact_ + 2 * g_.plane, corner_mask_, g_, t_.mask_lut},
+            g_.nblocks, "block_corner_mask");
+  stream_sync(s_);
+}
+
+ImageContext::~ImageContext() {
+  stream_sync(s_);
+  for (size_t i = 0; i < owned_.size(); ++i) dev_free(owned_[i]);
+  destroy_stream(s_);
+}
+
+void ImageContext::blur(const float* in, float* out, int nplanes, int id) {
+  launch_2d(s_, BlurX{in, tmp_, t_.blur[id], g_}, g_.w, g_.h * nplanes, "blur_x");
+  launch_2d(s_, BlurY{tmp_, out, t_.blur[id], g_}, g_.w, g_.h * nplanes, "blur_y");
+}
+
+void ImageContext::opsin(const float* lin, float* xyb) {
+  blur(lin, blr_, 3, kBlurOpsin);
+  launch_2d(s_, OpsinPx{lin, blr_, xyb, g_}, g_.w, g_.h, "opsin_px");
+}
+
+void ImageContext::separate(const float* xyb, float* ps) {
+  blur(xyb, lf_, 3, kBlurLf);
+  launch_2d(s_, SubPlanes{xyb, lf_, mf_in_, g_}, g_.w, 3 * g_.h, "sub_planes");
+  blur(mf_in_, mf_blr_, 3, kBlurMf);
+  launch_2d(s_, SplitMfHf{mf_in_, mf_blr_, ps, hf_raw_, g_}, g_.w, g_.h, "split_mf_hf");
+  blur(hf_raw_, hf_blr_, 2, kBlurHf);
+  launch_2d(s_, SplitHfUhf{hf_raw_, hf_blr_, lf_, ps, g_}, g_.w, g_.h, "split_hf_uhf");
+}
+
+void ImageContext::apply_global_quant(const int q[192]) {
+  h2d(d_q_, q, 192 * sizeof(int), s_);
+  launch_1d(s_, QuantizeCoeffs{d_orig_, d_cand_, d_q_, g_.nblocks}, 3 * g_.nblocks * 64,
+            "quantize_coeffs");
+}
+
+void ImageContext::scatter_coeffs(const std::vector<int>& index, const std::vector<int16_t>& value) {
+  const int n = static_cast<int>(index.size());
+  if (n == 0) return;
+  int* d_i = static_cast<int*>(dev_alloc(n * sizeof(int)));
+  int16_t* d_v = static_cast<int16_t*>(dev_alloc(n * sizeof(int16_t)));
+  h2d(d_i, index.data(), n * sizeof(int), s_);
+  h2d(d_v, value.data(), n * sizeof(int16_t), s_);
+  launch_1d(s_, ScatterCoeffs{d_i, d_v, d_cand_}, n, "scatter_coeffs");
+  stream_sync(s_);
+  dev_free(d_i);
+  dev_free(d_v);
+}
+
+void ImageContext::upload_candidate(const int16_t* coeffs) {
+  h2d(d_cand_, coeffs, static_cast<size_t>(3) * g_.nblocks * 64 * 2, s_);
+  stream_sync(s_);
+}
+
+void ImageContext::download_candidate(int16_t* coeffs) {
+  d2h(coeffs, d_cand_, static_cast<size_t>(3) * g_.nblocks * 64 * 2, s_);
+}
+
+float ImageContext::compare() {
+  const size_t P = g_.plane;
+  // S0 render, S1 opsin, S2-S6 frequency split
+  launch_1d(s_, RenderBlocks{d_cand_, lin_, g_, t_}, g_.nblocks, "render_blocks");
+  opsin(lin_, xyb_);
+  separate(xyb_, ps1_);
+  // S7 Malta: uhf[Y], uhf[X] with 9-tap lines; hf[Y], hf[X], mf[Y], mf[X] with 5-tap lines
+  static const int kMaltaPlane[6] = {kUhfY, kUhfX, kHfY, kHfX, kMfY, kMfX};
+  static const int kMaltaAcc[6] = {1, 0, 1, 0, 1, 0};
+  for (int i = 0; i < 6; ++i) {
+    const int pl = kMaltaPlane[i];
+    launch_2d(s_, MaltaPre{ps0_ + pl * P, ps1_ + pl * P, diffs_, malta_[i], g_}, g_.w, g_.h, "malta_pre");
+    MaltaAcc acc;
+    acc.diffs = diffs_;
+    acc.acc = ac_ + kMaltaAcc[i] * P;
+    acc.pat = i < 2 ? t_.malta_hf : t_.malta_lf;
+    acc.pat_len = i < 2 ? t_.malta_hf_len : nullptr;
+    acc.stride = i < 2 ? 9 : 5;
+    acc.first = i < 2 ? 1 : 0;
+    acc.g = g_;
+    launch_2d(s_, acc, g_.w, g_.h, i < 2 ? "malta_acc_hf" : "malta_acc_lf");
+  }
+  // S8 + S9 on block_diff_ac[Y]
+  launch_2d(s_, NoisePre{ps0_ + kHfY * P, ps1_ + kHfY * P, noise_, g_}, g_.w, g_.h, "noise_pre");
+  blur(noise_, noise_ + P, 1, kBlurNoise);
+  launch_2d(s_, NoiseAndAsymAcc{noise_ + P, ps0_ + kHfY * P, ps1_ + kHfY * P, ac_ + P, asym_w0_, asym_w1_, g_},
+            g_.w, g_.h, "noise_asym_acc");
+  // S10 mask
+  launch_2d(s_, MaskDiffPre{ps0_, ps1_, mpre_, g_}, g_.w, g_.h, "mask_diff_pre");
+  blur(mpre_, sact_, 1, kBlurMaskX);
+  blur(mpre_ + P, sact_ + P, 1, kBlurMaskY0);
+  blur(mpre_ + P, sact_ + 2 * P, 1, kBlurMaskY1);
+  // S11 + S12
+  launch_2d(s_, CombineAndSqrt{ps0_, ps1_, ac_, sact_, sact_ + P, sact_ + 2 * P, dm_, g_, t_.mask_lut}, g_.w,
+            g_.h, "combine_sqrt");
+  blur(dm_, dm_ + P, 1, kBlurFinal);
+  launch_2d(s_, DiffmapMix{dm_ + P, dm_, g_}, g_.w, g_.h, "diffmap_mix");
+  // S13 + a15 first half
+  launch_1d(s_, BlockMax{dm_, block_max_, g_}, g_.nblocks, "block_max");
+  const int lanes = 1024;
+  launch_1d(s_, PartialMax{block_max_, partial_, g_.nblocks, lanes}, lanes, "partial_max");
+  float part[1024];
+  d2h(part, partial_, sizeof(part), s_);
+  float m = 0.0f;
+  for (int i = 0; i < lanes; ++i) m = std::max(m, part[i]);
+  return m;
+}
+
+void ImageContext::download_planes(const float* src, float* packed, int n) {
+  std::vector<float> buf(g_.plane * n);
+  d2h(buf.data(), src, sizeof(float) * g_.plane * n, s_);
+  for (int c = 0; c < n; ++c)
+    for (int y = 0; y < g_.h; ++y)
+      memcpy(packed + (static_cast<size_t>(c) * g_.h + y) * g_.w, &buf[c * g_.plane + static_cast<size_t>(y) * g_.pitch],
+             sizeof(float) * g_.w);
+}
+
+void ImageContext::upload_planes(const float* packed, float* dst, int n) {
+  std::vector<float> buf(g_.plane * n, 0.0f);
+  for (int c = 0; c < n; ++c)
+    for (int y = 0; y < g_.h; ++y)
+      memcpy(&buf[c * g_.plane + static_cast<size_t>(y) * g_.pitch], packed + (static_cast<size_t>(c) * g_.h + y) * g_.w,
+             sizeof(float) * g_.w);
+  h2d(dst, buf.data(), sizeof(float) * g_.plane * n, s_);
+  stream_sync(s_);
+}
+
+void ImageContext::download_distmap(float* out) { download_planes(dm_, out, 1); }
+
+void ImageContext::download_block_max(float* out) { d2h(out, block_max_, sizeof(float) * g_.nblocks, s_); }
+
+void ImageContext::block_weights(int direction, int radius, double target_distance, bool zero_distmap,
+                                 float* out) {
+  BlockWeights bw;
+  bw.block_max = zero_distmap ? zero_block_max_ : block_max_;
+  bw.weight = weights_;
+  bw.g = g_;
+  bw.direction = direction;
+  bw.radius = radius;
+  bw.target_distance = target_distance;
+  launch_1d(s_, bw, g_.nblocks, "block_weights");
+  d2h(out, weights_, sizeof(float) * g_.nblocks, s_);
+}
+
+void ImageContext::zeroing_orders(float block_error_limit, int lookahead, std::vector<uint8_t>* idx,
+                                  std::vector<float>* err, std::vector<int>* count) {
+  const size_t slots = static_cast<size_t>(g_.nblocks) * 192;
+  uint8_t* d_idx = static_cast<uint8_t*>(dev_alloc(slots));
+  float* d_err = static_cast<float*>(dev_alloc(slots * sizeof(float)));
+  int* d_cnt = static_cast<int*>(dev_alloc(sizeof(int) * g_.nblocks));
+  ZeroingOrders z;
+  z.cand = d_cand_;
+  z.orig = d_orig_;
+  z.rgb = d_rgb_;
+  z.corner_mask = corner_mask_;
+  z.out_idx = d_idx;
+  z.out_err = d_err;
+  z.out_count = d_cnt;
+  z.g = g_;
+  z.t = t_;
+  z.scale8 = t_.opsin_scale8;
+  z.lookahead = lookahead;
+  z.block_error_limit = block_error_limit;
+  launch_1d(s_, z, g_.nblocks, "zeroing_orders");
+  idx->resize(slots);
+  err->resize(slots);
+  count->resize(g_.nblocks);
+  d2h(idx->data(), d_idx, slots, s_);
+  d2h(err->data(), d_err, slots * sizeof(float), s_);
+  d2h(count->data(), d_cnt, sizeof(int) * g_.nblocks, s_);
+  dev_free(d_idx);
+  dev_free(d_err);
+  dev_free(d_cnt);
+}
+
+void ImageContext::debug_blur(const float* in, float* out, int id) {
+  upload_planes(in, xyb_, 1);
+  blur(xyb_, lf_, 1, id);
+  download_planes(lf_, out, 1);
+}
+
+void ImageContext::debug_opsin(const float* rgb_lin, float* xyb) {
+  upload_planes(rgb_lin, lin_, 3);
+  opsin(lin_, xyb_);
+  download_planes(xyb_, xyb, 3);
+}
+
+void ImageContext::debug_separate(const float* xyb, float* ps10) {
+  upload_planes(xyb, xyb_, 3);
+  separate(xyb_, ps1_);
+  download_planes(ps1_, ps10, kPsychoPlanes);
+}
+
+void ImageContext::debug_render(float* lin3) {
+  launch_1d(s_, RenderBlocks{d_cand_, lin_, g_, t_}, g_.nblocks, "render_blocks");
+  download_planes(lin_, lin3, 3);
+}
+
+void ImageContext::debug_psycho0(float* ps10) { download_planes(ps0_, ps10, kPsychoPlanes); }
+
+void ImageContext::debug_corner_mask(float* out) { d2h(out, corner_mask_, sizeof(float) * 3 * g_.nblocks, s_); }
+
+long ImageContext::launches() const { return total_launches(); }
+void ImageContext::set_profiling(bool on) { profiling_enable(on); }
+std::vector<KernelStat> ImageContext::kernel_stats() const { return profiling_snapshot(); }
+void ImageContext::reset_stats() { profiling_reset(); }
+
+}  // namespace gb200

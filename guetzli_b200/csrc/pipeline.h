@@ -1,0 +1,121 @@
+// Device-resident state of one image and the kernel sequences of the hot path.
+// One ImageContext = one image on one GPU, driven by one host thread on one
+// stream.  See DESIGN.md for the HBM layout and the kernel list.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "tables.h"
+
+namespace gb200 {
+
+struct KernelStat {
+  std::string name;
+  long launches;
+  double ms;  // CUDA-event time accumulated when profiling is on
+};
+
+class ImageContext {
+ public:
+  // Uploads the image, runs the one-time kernels (a2 FDCT, a3 PsychoImage of the
+  // original, a13 block-corner masks).  rgb: interleaved sRGB u8, w*h*3.
+  ImageContext(const uint8_t* rgb, int w, int h, int device);
+  ~ImageContext();
+
+  int width() const { return g_.w; }
+  int height() const { return g_.h; }
+  const Geom& geom() const { return g_; }
+
+  // a2 result on the host: [3][nblocks][64] int16 (q = 1 coefficients).
+  const std::vector<int16_t>& orig_coeffs() const { return orig_host_; }
+
+  // a8: candidate := Quantize(original, q) for all coefficients. q: [3][64].
+  void apply_global_quant(const int q[192]);
+  // Sparse edits of the candidate: flat indices into [3][nblocks][64].
+  void scatter_coeffs(const std::vector<int>& index, const std::vector<int16_t>& value);
+  // Whole candidate from the host (tests).
+  void upload_candidate(const int16_t* coeffs);
+  void download_candidate(int16_t* coeffs);
+
+  // a7+a9+a10: renders the candidate and scores it against the original.
+  // Leaves the distmap and per-block maxima on the device; returns distance_.
+  float compare();
+  void download_distmap(float* out);      // [h][w] packed
+  void download_block_max(float* out);    // [nblocks]
+
+  // a15: block weights for the current distmap (or an all-zero distmap when
+  // zero_distmap is set, the reference's first "up" iteration).
+  void block_weights(int direction, int radius, double target_distance, bool zero_distmap,
+                     float* out);
+
+  // a13+a14: greedy zeroing order of every block of the current candidate.
+  // idx/err are [nblocks][192] slots, count[nblocks] valid entries each.
+  void zeroing_orders(float block_error_limit, int lookahead, std::vector<uint8_t>* idx,
+                      std::vector<float>* err, std::vector<int>* count);
+
+  // test hooks: run single stages on caller-provided planes (packed [n][h][w]).
+  void debug_blur(const float* in, float* out, int id);
+  void debug_opsin(const float* rgb_lin, float* xyb);
+  void debug_separate(const float* xyb, float* ps10);
+  void debug_render(float* lin3);
+  void debug_psycho0(float* ps10);
+  void debug_corner_mask(float* out);  // [nblocks][3]
+
+  long launches() const;
+  void set_profiling(bool on);
+  std::vector<KernelStat> kernel_stats() const;
+  void reset_stats();
+  Stream stream() const { return s_; }
+
+ private:
+  void blur(const float* in, float* out, int nplanes, int id);
+  void opsin(const float* lin, float* xyb);
+  void separate(const float* xyb, float* ps);
+  void upload_planes(const float* packed, float* dst, int n);
+  void download_planes(const float* src, float* packed, int n);
+  float* planes(int n);
+
+  Geom g_;
+  int device_;
+  bool metric_;
+  Stream s_;
+  Tables t_;
+  HostTables ht_;
+  std::vector<void*> owned_;
+  std::vector<int16_t> orig_host_;
+
+  uint8_t* d_rgb_;
+  int16_t* d_orig_;
+  int16_t* d_cand_;
+  int* d_q_;
+  float* ps0_;        // [10]
+  float* corner_mask_;  // [nblocks][3]
+  // work planes
+  float* lin_;     // [3]
+  float* tmp_;     // [3] blur x-pass output
+  float* blr_;     // [3]
+  float* xyb_;     // [3]
+  float* lf_;      // [3]
+  float* mf_in_;   // [3]
+  float* mf_blr_;  // [3]
+  float* hf_raw_;  // [2]
+  float* hf_blr_;  // [2]
+  float* ps1_;     // [10]
+  float* diffs_;   // [1]
+  float* ac_;      // [2]
+  float* noise_;   // [2] pre, blurred
+  float* mpre_;    // [2]
+  float* sact_;    // [3] sx, sy1, sy2
+  float* dm_;      // [2] diffmap, blurred
+  float* block_max_;  // [nblocks]
+  float* weights_;    // [nblocks]
+  float* partial_;    // [1024]
+  float* zero_block_max_;
+  MaltaParams malta_[6];
+  double asym_w0_, asym_w1_;
+};
+
+}  // namespace gb200

@@ -1,0 +1,44 @@
+// Host search driver: the control flow of guetzli::Process(RGB)
+// (g/processor.cc:926) -- global quant-matrix bisection (a5/a6) and the
+// per-block frequency masking iterations (a12, a16) -- over device-resident
+// image state (pipeline.h).  g/ = /root/reference/guetzli/.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+
+namespace gb200 {
+
+// Mirrors guetzli::Params (g/processor.h:29-37).
+struct SearchParams {
+  float butteraugli_target = 1.0f;
+  bool clear_metadata = true;
+  bool try_420 = false;
+  bool force_420 = false;
+  bool use_silver_screen = false;
+  int zeroing_greedy_lookahead = 3;
+  bool new_zeroing_model = true;
+};
+
+typedef void (*LogSink)(void* user, const char* text);
+
+struct SearchStats {
+  int iterations = 0;       // "number of iterations"
+  int iterations_up = 0;    // "number of iterations up"
+  int iterations_down = 0;  // "number of iterations down"
+  // device-side accounting of this call
+  long gpu_launches = 0;
+  double ms_total = 0, ms_device_setup = 0, ms_compare = 0, ms_zeroing = 0, ms_jpeg = 0, ms_sort = 0,
+         ms_walk = 0;
+  int compares = 0;
+};
+
+// Returns true on success; *jpeg_out receives the best JPEG found (possibly
+// empty on failure), error text goes to err (and stderr, like the reference).
+bool process_rgb(const SearchParams& params, const uint8_t* rgb, int w, int h, int device, LogSink log,
+                 void* log_user, std::string* jpeg_out, SearchStats* stats, std::string* err);
+
+// ScoreJPEG (g/score.cc:23).
+double score_jpeg(double distance, int size, double target);
+
+}  // namespace gb200
