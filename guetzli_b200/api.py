@@ -25,6 +25,7 @@ class _CParams(C.Structure):
 class _CStats(C.Structure):
     _fields_ = [("iterations", C.c_int), ("iterations_up", C.c_int), ("iterations_down", C.c_int),
                 ("compares", C.c_int), ("gpu_launches", C.c_long),
+                ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
                 ("ms_total", C.c_double), ("ms_device_setup", C.c_double), ("ms_compare", C.c_double),
                 ("ms_zeroing", C.c_double), ("ms_jpeg", C.c_double), ("ms_sort", C.c_double),
                 ("ms_walk", C.c_double)]
@@ -59,6 +60,10 @@ def load_library(path=None):
     lib.gb200_free.argtypes = [C.c_void_p]
     lib.gb200_image_create.restype = C.c_void_p
     lib.gb200_image_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.gb200_image_create2.restype = C.c_void_p
+    lib.gb200_image_create2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.gb200_image_process.argtypes = [C.c_void_p, P(_CParams), _LOG_FN, C.c_void_p,
+                                        P(P(C.c_uint8)), P(C.c_size_t), P(_CStats)]
     lib.gb200_image_destroy.argtypes = [C.c_void_p]
     for name in ("num_blocks", "orig_coeffs", "apply_global_quant", "upload_candidate",
                  "download_candidate", "compare", "distmap", "debug_render", "debug_psycho0",
@@ -173,11 +178,11 @@ class DeviceImage:
     """One image resident on one GPU (gb200_image_*): the reference's Comparator /
     OutputImage pair moved onto device memory.  Used by the parity tests."""
 
-    def __init__(self, rgb, device=0, lib=None):
+    def __init__(self, rgb, device=0, lib=None, prepare=True):
         self.lib = lib or load_library()
         rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
         self.h, self.w, _ = rgb.shape
-        self._h = self.lib.gb200_image_create(rgb.ctypes.data, self.w, self.h, device)
+        self._h = self.lib.gb200_image_create2(rgb.ctypes.data, self.w, self.h, device, int(prepare))
         if not self._h:
             raise RuntimeError("gb200_image_create failed: " + _err(self.lib))
         self.nblocks = self.lib.gb200_image_num_blocks(self._h)
@@ -193,6 +198,26 @@ class DeviceImage:
     def _ck(self, ok):
         if not ok:
             raise RuntimeError(_err(self.lib))
+
+    def process(self, params, stats=None):
+        """guetzli::Process on the resident image -> (ok, jpeg bytes)."""
+        cp = _CParams(params.butteraugli_target, int(params.clear_metadata), int(params.try_420),
+                      int(params.force_420), int(params.use_silver_screen),
+                      int(params.zeroing_greedy_lookahead), int(params.new_zeroing_model))
+        cs = _CStats()
+        out = C.POINTER(C.c_uint8)()
+        out_len = C.c_size_t()
+        ok = self.lib.gb200_image_process(self._h, C.byref(cp), C.cast(None, _LOG_FN), None,
+                                          C.byref(out), C.byref(out_len), C.byref(cs))
+        data = C.string_at(out, out_len.value) if out_len.value else b""
+        if out:
+            self.lib.gb200_free(out)
+        if stats is not None:
+            stats.counters["number of iterations"] = cs.iterations
+            stats.counters["number of iterations up"] = cs.iterations_up
+            stats.counters["number of iterations down"] = cs.iterations_down
+            stats.device = {k: getattr(cs, k) for k, _ in _CStats._fields_}
+        return bool(ok), data
 
     def orig_coeffs(self):
         out = np.zeros((3, self.nblocks, 64), dtype=np.int16)

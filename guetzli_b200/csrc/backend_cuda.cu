@@ -2,6 +2,7 @@
 // accounting and optional per-kernel CUDA-event timing (product build only).
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -30,10 +31,16 @@ void dev_free(void* p) {
   if (p) cudaFree(p);
 }
 
+static std::atomic<long long> g_h2d_bytes(0), g_d2h_bytes(0);
+long long h2d_bytes_total() { return g_h2d_bytes.load(); }
+long long d2h_bytes_total() { return g_d2h_bytes.load(); }
+
 void h2d(void* dst, const void* src, size_t n, Stream s) {
+  g_h2d_bytes += static_cast<long long>(n);
   GB_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s));
 }
 void d2h(void* dst, const void* src, size_t n, Stream s) {
+  g_d2h_bytes += static_cast<long long>(n);
   GB_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, s));
   GB_CUDA(cudaStreamSynchronize(s));
 }

@@ -45,6 +45,39 @@ struct gb200_image {
   gb200::ImageContext* ctx;
 };
 
+namespace {
+gb200::SearchParams to_search_params(const gb200_params* params) {
+  gb200::SearchParams sp;
+  if (params) {
+    sp.butteraugli_target = params->butteraugli_target;
+    sp.clear_metadata = params->clear_metadata != 0;
+    sp.try_420 = params->try_420 != 0;
+    sp.force_420 = params->force_420 != 0;
+    sp.use_silver_screen = params->use_silver_screen != 0;
+    sp.zeroing_greedy_lookahead = params->zeroing_greedy_lookahead;
+    sp.new_zeroing_model = params->new_zeroing_model != 0;
+  }
+  return sp;
+}
+void fill_stats(const gb200::SearchStats& st, gb200_stats* stats) {
+  if (!stats) return;
+  stats->iterations = st.iterations;
+  stats->iterations_up = st.iterations_up;
+  stats->iterations_down = st.iterations_down;
+  stats->compares = st.compares;
+  stats->gpu_launches = st.gpu_launches;
+  stats->h2d_bytes = st.h2d_bytes;
+  stats->d2h_bytes = st.d2h_bytes;
+  stats->ms_total = st.ms_total;
+  stats->ms_device_setup = st.ms_device_setup;
+  stats->ms_compare = st.ms_compare;
+  stats->ms_zeroing = st.ms_zeroing;
+  stats->ms_jpeg = st.ms_jpeg;
+  stats->ms_sort = st.ms_sort;
+  stats->ms_walk = st.ms_walk;
+}
+}  // namespace
+
 extern "C" {
 
 void gb200_params_default(gb200_params* p) {
@@ -66,16 +99,7 @@ int gb200_process_rgb(const gb200_params* params, const uint8_t* rgb, int w, int
   *out_len = 0;
   bool ok = false;
   int guarded_ok = guarded([&]() {
-    gb200::SearchParams sp;
-    if (params) {
-      sp.butteraugli_target = params->butteraugli_target;
-      sp.clear_metadata = params->clear_metadata != 0;
-      sp.try_420 = params->try_420 != 0;
-      sp.force_420 = params->force_420 != 0;
-      sp.use_silver_screen = params->use_silver_screen != 0;
-      sp.zeroing_greedy_lookahead = params->zeroing_greedy_lookahead;
-      sp.new_zeroing_model = params->new_zeroing_model != 0;
-    }
+    gb200::SearchParams sp = to_search_params(params);
     gb200::SearchStats st;
     std::string jpeg, err;
     ok = gb200::process_rgb(sp, rgb, w, h, device, log, log_user, &jpeg, &st, &err);
@@ -85,20 +109,28 @@ int gb200_process_rgb(const gb200_params* params, const uint8_t* rgb, int w, int
       memcpy(*out, jpeg.data(), jpeg.size());
       *out_len = jpeg.size();
     }
-    if (stats) {
-      stats->iterations = st.iterations;
-      stats->iterations_up = st.iterations_up;
-      stats->iterations_down = st.iterations_down;
-      stats->compares = st.compares;
-      stats->gpu_launches = st.gpu_launches;
-      stats->ms_total = st.ms_total;
-      stats->ms_device_setup = st.ms_device_setup;
-      stats->ms_compare = st.ms_compare;
-      stats->ms_zeroing = st.ms_zeroing;
-      stats->ms_jpeg = st.ms_jpeg;
-      stats->ms_sort = st.ms_sort;
-      stats->ms_walk = st.ms_walk;
+    fill_stats(st, stats);
+  });
+  return (guarded_ok && ok) ? 1 : 0;
+}
+
+int gb200_image_process(gb200_image* img, const gb200_params* params, gb200_log_fn log, void* log_user,
+                        uint8_t** out, size_t* out_len, gb200_stats* stats) {
+  *out = nullptr;
+  *out_len = 0;
+  bool ok = false;
+  int guarded_ok = guarded([&]() {
+    gb200::SearchParams sp = to_search_params(params);
+    gb200::SearchStats st;
+    std::string jpeg, err;
+    ok = gb200::process_resident(sp, img->ctx, log, log_user, &jpeg, &st, &err);
+    if (!ok) g_err = err;
+    if (!jpeg.empty()) {
+      *out = static_cast<uint8_t*>(malloc(jpeg.size()));
+      memcpy(*out, jpeg.data(), jpeg.size());
+      *out_len = jpeg.size();
     }
+    fill_stats(st, stats);
   });
   return (guarded_ok && ok) ? 1 : 0;
 }
@@ -116,10 +148,14 @@ int gb200_device_count(void) {
 }
 
 gb200_image* gb200_image_create(const uint8_t* rgb, int w, int h, int device) {
+  return gb200_image_create2(rgb, w, h, device, 1);
+}
+
+gb200_image* gb200_image_create2(const uint8_t* rgb, int w, int h, int device, int prepare) {
   gb200_image* img = nullptr;
   guarded([&]() {
     if (!rgb || w <= 0 || h <= 0 || w >= 65536 || h >= 65536) throw std::runtime_error("bad image size");
-    gb200::ImageContext* ctx = new gb200::ImageContext(rgb, w, h, device);
+    gb200::ImageContext* ctx = new gb200::ImageContext(rgb, w, h, device, prepare != 0);
     img = new gb200_image;
     img->ctx = ctx;
   });

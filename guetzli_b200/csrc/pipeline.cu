@@ -15,6 +15,8 @@ static void select_device(int) {}
 static Stream make_stream() { return 0; }
 static void destroy_stream(Stream) {}
 long total_launches() { return 0; }
+long long h2d_bytes_total() { return 0; }
+long long d2h_bytes_total() { return 0; }
 void profiling_enable(bool) {}
 std::vector<KernelStat> profiling_snapshot() { return std::vector<KernelStat>(); }
 void profiling_reset() {}
@@ -23,6 +25,8 @@ void select_device(int device);
 Stream make_stream();
 void destroy_stream(Stream s);
 long total_launches();
+long long h2d_bytes_total();
+long long d2h_bytes_total();
 void profiling_enable(bool on);
 std::vector<KernelStat> profiling_snapshot();
 void profiling_reset();
@@ -35,7 +39,7 @@ float* ImageContext::planes(int n) {
   return static_cast<float*>(p);
 }
 
-ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device)
+ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device, bool prepare_now)
     : g_(make_geom(w, h)), device_(device) {
   select_device(device);
   s_ = make_stream();
@@ -83,8 +87,16 @@ ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device)
   dm_ = planes(2);
 
   metric_ = (w >= 32 && h >= 32);  // g/processor.cc:940: no Butteraugli below 32x32
+  prepared_ = false;
   h2d(d_rgb_, rgb, static_cast<size_t>(3) * w * h, s_);
+  stream_sync(s_);
+  if (prepare_now) prepare();
+}
 
+void ImageContext::prepare() {
+  if (prepared_) return;
+  prepared_ = true;
+  const size_t ncoef = static_cast<size_t>(3) * g_.nblocks * 64;
   // a2: one-time forward DCT; the host search keeps a copy of the coefficients.
   launch_1d(s_, FdctBlocks{d_rgb_, d_orig_, g_}, g_.nblocks, "fdct_blocks");
   d2d(d_cand_, d_orig_, ncoef * 2, s_);

@@ -22,7 +22,10 @@ class ImageContext {
  public:
   // Uploads the image, runs the one-time kernels (a2 FDCT, a3 PsychoImage of the
   // original, a13 block-corner masks).  rgb: interleaved sRGB u8, w*h*3.
-  ImageContext(const uint8_t* rgb, int w, int h, int device);
+  ImageContext(const uint8_t* rgb, int w, int h, int device, bool prepare_now = true);
+  // the one-time kernels (idempotent); split from the upload so that a caller can
+  // time the job with the image already resident in HBM
+  void prepare();
   ~ImageContext();
 
   int width() const { return g_.w; }
@@ -81,6 +84,7 @@ class ImageContext {
   Geom g_;
   int device_;
   bool metric_;
+  bool prepared_;
   Stream s_;
   Tables t_;
   HostTables ht_;

@@ -21,6 +21,8 @@
 namespace gb200 {
 
 long total_launches();
+long long h2d_bytes_total();
+long long d2h_bytes_total();
 
 double score_jpeg(double distance, int size, double target) {
   const double kScale = 50, kMaxExponent = 10, kLargeSize = 1e30;
@@ -466,18 +468,7 @@ class Search {
 
 }  // namespace
 
-bool process_rgb(const SearchParams& params, const uint8_t* rgb, int w, int h, int device, LogSink log,
-                 void* log_user, std::string* jpeg_out, SearchStats* stats, std::string* err) {
-  SearchStats local;
-  SearchStats* st = stats ? stats : &local;
-  *st = SearchStats();
-  jpeg_out->clear();
-  Clock::time_point t_all = Clock::now();
-  if (rgb == nullptr || w < 0 || w >= 1 << 16 || h < 0 || h >= 1 << 16) {
-    *err = "Could not create jpg data from rgb pixels\n";
-    fputs(err->c_str(), stderr);
-    return false;
-  }
+static bool check_params(const SearchParams& params, std::string* err) {
   if (params.butteraugli_target > 2.0f) {
     *err =
         "Guetzli should be called with quality >= 84, otherwise the\n"
@@ -491,24 +482,32 @@ bool process_rgb(const SearchParams& params, const uint8_t* rgb, int w, int h, i
     fputs(err->c_str(), stderr);
     return false;
   }
-  if (w == 0 || h == 0) {
-    *err = "guetzli_b200: empty image\n";
-    fputs(err->c_str(), stderr);
-    return false;
-  }
-  Clock::time_point t0 = Clock::now();
+  return true;
+}
+
+bool process_resident(const SearchParams& params, ImageContext* ctx, LogSink log, void* log_user,
+                      std::string* jpeg_out, SearchStats* stats, std::string* err) {
+  SearchStats local;
+  SearchStats* st = stats ? stats : &local;
+  const double setup_ms = st->ms_device_setup;
+  *st = SearchStats();
+  st->ms_device_setup = setup_ms;
+  jpeg_out->clear();
+  Clock::time_point t_all = Clock::now();
+  if (!check_params(params, err)) return false;
   const long launches0 = total_launches();
-  ImageContext ctx(rgb, w, h, device);
-  st->ms_device_setup = ms_since(t0);
+  const long long h2d0 = h2d_bytes_total(), d2h0 = d2h_bytes_total();
+  ctx->prepare();
+  const int w = ctx->width(), h = ctx->height();
   if (w < 32 || h < 32) {
     // Butteraugli is skipped for tiny images (g/processor.cc:832-838,940)
     CoeffImage img;
     img.w = w;
     img.h = h;
-    img.bw = ctx.geom().bw;
-    img.bh = ctx.geom().bh;
-    img.nblocks = ctx.geom().nblocks;
-    img.coeffs = ctx.orig_coeffs().data();
+    img.bw = ctx->geom().bw;
+    img.bh = ctx->geom().bh;
+    img.nblocks = ctx->geom().nblocks;
+    img.coeffs = ctx->orig_coeffs().data();
     for (int c = 0; c < 3; ++c)
       for (int k = 0; k < 64; ++k) img.q[c][k] = 1;
     img.as_encoded = true;
@@ -519,12 +518,41 @@ bool process_rgb(const SearchParams& params, const uint8_t* rgb, int w, int h, i
       log(log_user, buf);
     }
   } else {
-    Search search(params, &ctx, log, log_user, st);
+    Search search(params, ctx, log, log_user, st);
     search.run(jpeg_out);
   }
-  st->gpu_launches = ctx.launches() - launches0;
+  st->gpu_launches = total_launches() - launches0;
+  st->h2d_bytes = h2d_bytes_total() - h2d0;
+  st->d2h_bytes = d2h_bytes_total() - d2h0;
   st->ms_total = ms_since(t_all);
   return true;
+}
+
+bool process_rgb(const SearchParams& params, const uint8_t* rgb, int w, int h, int device, LogSink log,
+                 void* log_user, std::string* jpeg_out, SearchStats* stats, std::string* err) {
+  SearchStats local;
+  SearchStats* st = stats ? stats : &local;
+  *st = SearchStats();
+  jpeg_out->clear();
+  if (rgb == nullptr || w < 0 || w >= 1 << 16 || h < 0 || h >= 1 << 16) {
+    *err = "Could not create jpg data from rgb pixels\n";
+    fputs(err->c_str(), stderr);
+    return false;
+  }
+  if (!check_params(params, err)) return false;
+  if (w == 0 || h == 0) {
+    *err = "guetzli_b200: empty image\n";
+    fputs(err->c_str(), stderr);
+    return false;
+  }
+  Clock::time_point t0 = Clock::now();
+  const long long h2d0 = h2d_bytes_total();
+  ImageContext ctx(rgb, w, h, device, false);
+  st->ms_device_setup = ms_since(t0);
+  const bool ok = process_resident(params, &ctx, log, log_user, jpeg_out, st, err);
+  st->h2d_bytes = h2d_bytes_total() - h2d0;
+  st->ms_total = ms_since(t0);
+  return ok;
 }
 
 }  // namespace gb200

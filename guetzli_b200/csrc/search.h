@@ -31,7 +31,14 @@ struct SearchStats {
   double ms_total = 0, ms_device_setup = 0, ms_compare = 0, ms_zeroing = 0, ms_jpeg = 0, ms_sort = 0,
          ms_walk = 0;
   int compares = 0;
+  long long h2d_bytes = 0, d2h_bytes = 0;
 };
+
+class ImageContext;
+// Same job on an image that is already resident on the device (upload done by
+// the ImageContext constructor with prepare_now=false).
+bool process_resident(const SearchParams& params, ImageContext* ctx, LogSink log, void* log_user,
+                      std::string* jpeg_out, SearchStats* stats, std::string* err);
 
 // Returns true on success; *jpeg_out receives the best JPEG found (possibly
 // empty on failure), error text goes to err (and stderr, like the reference).

@@ -48,6 +48,8 @@ typedef struct gb200_stats {
   int iterations_down; /* "number of iterations down" */
   int compares;        /* full-image Compare calls */
   long gpu_launches;   /* CUDA kernels launched by this call */
+  long long h2d_bytes; /* host->device bytes copied by this call */
+  long long d2h_bytes; /* device->host bytes copied by this call */
   double ms_total, ms_device_setup, ms_compare, ms_zeroing, ms_jpeg, ms_sort, ms_walk;
 } gb200_stats;
 
@@ -77,7 +79,13 @@ typedef struct gb200_image gb200_image;
  * PsychoImage of the original (butteraugli.cc:784), block masks
  * (guetzli/butteraugli_comparator.cc:415). */
 gb200_image* gb200_image_create(const uint8_t* rgb, int w, int h, int device);
+/* prepare=0: upload only; the one-time kernels then run inside gb200_image_process */
+gb200_image* gb200_image_create2(const uint8_t* rgb, int w, int h, int device, int prepare);
 void gb200_image_destroy(gb200_image* img);
+/* guetzli::Process on an image that is already resident in HBM (same result as
+ * gb200_process_rgb; used to time the job without the host->device upload) */
+int gb200_image_process(gb200_image* img, const gb200_params* params, gb200_log_fn log, void* log_user,
+                        uint8_t** out, size_t* out_len, gb200_stats* stats);
 int gb200_image_num_blocks(const gb200_image* img);
 /* coefficients: int16 [3][num_blocks][64], block-major (JPEGComponent::coeffs) */
 int gb200_image_orig_coeffs(gb200_image* img, int16_t* out);

@@ -1,0 +1,83 @@
+"""GPU suite (-m gpu): the CUDA product, through its C ABI, against the oracle
+(the real reference build oracle/_ref, prebuilt and shipped with the snapshot)
+and the committed golden answers.  Bit-exact everywhere: integers, float bit
+patterns of every butteraugli stage, JPEG bytes and the verbose trace."""
+import numpy as np
+import pytest
+
+import parity
+from guetzli_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(64, 96, 7), (70, 51, 3), (136, 200, 4)]
+
+
+@pytest.mark.parametrize("h,w,seed", SIZES)
+def test_integer_stages(cuda_lib, ref, h, w, seed):
+    parity.check_integer_stages(cuda_lib, ref, synth.gradnoise(h, w, seed))
+
+
+@pytest.mark.parametrize("h,w,seed", SIZES)
+def test_butteraugli_stages(cuda_lib, ref, h, w, seed):
+    parity.check_butteraugli_stages(cuda_lib, ref, synth.gradnoise(h, w, seed))
+
+
+@pytest.mark.parametrize("h,w,seed", SIZES + [(40, 33, 2)])
+def test_compare_and_block_kernels(cuda_lib, ref, h, w, seed):
+    parity.check_compare_and_blocks(cuda_lib, ref, synth.noise(h, w, seed))
+
+
+@pytest.mark.parametrize("name", sorted(parity.GOLDEN))
+def test_process_matches_golden(cuda_lib, name):
+    st = parity.check_golden(cuda_lib, name)
+    if not name.startswith("tiny"):
+        assert st.device["gpu_launches"] > 0
+
+
+def test_process_matches_reference_256(cuda_lib, ref):
+    st = parity.check_process_vs_ref(cuda_lib, ref, synth.gradnoise(256, 256, 21), 92)
+    assert st.device["gpu_launches"] > 0
+
+
+def test_product_equals_port_on_512(cuda_lib, port_lib):
+    """A larger case where the reference takes too long for a test: the CUDA
+    product against the CPU restatement (itself pinned to the reference)."""
+    rgb = synth.gradnoise(384, 512, 33)
+    ok, jpeg, trace, _ = parity.run_process(cuda_lib, rgb, 90)
+    ok2, jpeg2, trace2, _ = parity.run_process(port_lib, rgb, 90)
+    assert ok and ok2 and trace == trace2 and jpeg == jpeg2
+
+
+def test_full_size_properties_1080p(cuda_lib):
+    """BASELINE config sizes, size-independent properties: (1) Compare of the
+    unquantised image is deterministic across two contexts, (2) the distance is
+    monotone under coarser quantisation, (3) scatter(restore) returns the exact
+    distmap, (4) quantise is idempotent."""
+    import guetzli_b200 as gb
+    rgb = synth.gradnoise(1080, 1920, 4321)
+    a = gb.DeviceImage(rgb, lib=cuda_lib)
+    d0 = a.compare()
+    dm0 = a.distmap()
+    b = gb.DeviceImage(rgb, lib=cuda_lib)
+    assert b.compare() == d0 and parity.bits_equal(b.distmap(), dm0)
+    b.close()
+    q2 = np.full((3, 64), 2, dtype=np.int32)
+    q8 = np.full((3, 64), 8, dtype=np.int32)
+    a.apply_global_quant(q2)
+    c2 = a.download_candidate()
+    d2 = a.compare()
+    a.apply_global_quant(q8)
+    d8 = a.compare()
+    assert d0 <= d2 <= d8
+    a.apply_global_quant(q2)
+    assert np.array_equal(a.download_candidate(), c2)
+    # zero a few coefficients then restore them: distmap must come back bit for bit
+    dm2 = (a.compare(), a.distmap())
+    flat = c2.reshape(-1)
+    nz = np.flatnonzero(flat)[::5000][:200].astype(np.int32)
+    a.scatter(nz, np.zeros(len(nz), dtype=np.int16))
+    assert a.compare() >= 0
+    a.scatter(nz, flat[nz])
+    assert a.compare() == dm2[0] and parity.bits_equal(a.distmap(), dm2[1])
+    a.close()

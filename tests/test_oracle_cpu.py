@@ -1,0 +1,72 @@
+"""CPU suite (-m "not gpu"): pins the oracle.  The CPU restatement of the hot
+path (oracle/_build/libguetzli_port.so, same kernel bodies as the CUDA product)
+is checked against the unmodified reference (oracle/_ref) stage by stage and
+end to end, and against the committed golden answers."""
+import numpy as np
+import pytest
+
+import parity
+from guetzli_b200 import synth
+
+SIZES = [(64, 96, 7), (70, 51, 3)]
+
+
+@pytest.mark.parametrize("h,w,seed", SIZES)
+def test_port_integer_stages_match_reference(port_lib, ref, h, w, seed):
+    parity.check_integer_stages(port_lib, ref, synth.gradnoise(h, w, seed))
+
+
+@pytest.mark.parametrize("h,w,seed", SIZES)
+def test_port_butteraugli_stages_match_reference(port_lib, ref, h, w, seed):
+    parity.check_butteraugli_stages(port_lib, ref, synth.gradnoise(h, w, seed))
+
+
+@pytest.mark.parametrize("h,w,seed", SIZES + [(40, 33, 2)])
+def test_port_compare_and_block_kernels_match_reference(port_lib, ref, h, w, seed):
+    parity.check_compare_and_blocks(port_lib, ref, synth.noise(h, w, seed))
+
+
+@pytest.mark.parametrize("name", [n for n in parity.GOLDEN if not n.startswith("bees")])
+def test_port_process_matches_golden(port_lib, name):
+    parity.check_golden(port_lib, name)
+
+
+def test_port_process_bees_matches_golden(port_lib):
+    """BASELINE.json configs[0]: tests/bees.png --quality 95."""
+    parity.check_golden(port_lib, "bees_444x258_q95")
+
+
+def test_reference_reproduces_golden(ref):
+    """The committed golden answers are what oracle/_ref produces here."""
+    import hashlib
+    for name in ("gradnoise_64x96_s7_q90", "gray_64x64_s9_q90"):
+        g = parity.GOLDEN[name]
+        ok, jpeg, trace, cnt, _ = ref.process_rgb(parity.golden_input(name), g["quality"])
+        assert hashlib.sha256(jpeg).hexdigest() == g["jpeg_sha256"]
+        assert cnt == g["iterations"]
+
+
+def test_tables_match_reference(port_lib, ref):
+    """Generated / formula tables equal the reference's literal tables."""
+    import ctypes as C
+    cr_r, cb_b, cr_g, cb_g, rl = ref.color_tables()
+    x = np.arange(256) - 128
+    assert np.array_equal(cr_r, (91881 * x + 32768) >> 16)
+    assert np.array_equal(cb_b, (116130 * x + 32768) >> 16)
+    assert np.array_equal(cr_g, -46802 * x)
+    assert np.array_equal(cb_g, -22554 * x + 32768)
+    assert np.array_equal(rl, np.clip(np.arange(1024) - 384, 0, 255).astype(np.uint8))
+    for q in (84, 90, 95, 97.5, 100, 110, 60):
+        assert port_lib.gb200_butteraugli_score_for_quality(float(q)) == ref.lib().gref_target_for_quality(float(q))
+
+
+def test_rejects_low_quality_and_bad_sizes(port_lib):
+    import guetzli_b200 as gb
+    rgb = synth.gradnoise(40, 40, 1)
+    p = gb.Params(butteraugli_target=gb.butteraugli_score_for_quality(80, lib=port_lib))
+    ok, jpeg = gb.process(p, None, rgb, 40, 40, lib=port_lib)
+    assert not ok and jpeg == b""            # quality < 84 (processor.cc:800)
+    ok, jpeg = gb.process(gb.Params(), None, rgb, 41, 40, lib=port_lib)
+    assert not ok and jpeg == b""            # rgb.size() != 3*w*h (jpeg_data_encoder.cc:68)
+    ok, jpeg = gb.process(gb.Params(force_420=True), None, rgb, 40, 40, lib=port_lib)
+    assert not ok                            # YUV420 is out of scope
