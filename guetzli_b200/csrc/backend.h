@@ -64,7 +64,7 @@ void stream_sync(Stream s);
 inline const char* backend_name() { return "cuda-sm_100a"; }
 
 // launch accounting (gpu_launches in bench.py; per-kernel-name CUDA-event timing)
-void note_launch(const char* name, Stream s);
+void note_launch(const char* name, Stream s, double elements);
 void note_launch_end(const char* name, Stream s);
 
 }  // namespace gb200
@@ -99,7 +99,7 @@ template <class F>
 inline void launch_2d(Stream s, const F& f, int w, int h, const char* name = "px2d") {
   if (w <= 0 || h <= 0) return;
   dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
-  note_launch(name, s);
+  note_launch(name, s, static_cast<double>(w) * h);
   k_launch_2d<F><<<grid, block, 0, s>>>(f, w, h);
   note_launch_end(name, s);
 }
@@ -107,7 +107,7 @@ inline void launch_2d(Stream s, const F& f, int w, int h, const char* name = "px
 template <class F>
 inline void launch_1d(Stream s, const F& f, int n, const char* name = "px1d") {
   if (n <= 0) return;
-  note_launch(name, s);
+  note_launch(name, s, n);
   k_launch_1d<F><<<(n + 127) / 128, 128, 0, s>>>(f, n);
   note_launch_end(name, s);
 }

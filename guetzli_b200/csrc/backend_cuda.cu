@@ -82,6 +82,7 @@ struct Prof {
   struct Entry {
     long launches = 0;
     double ms = 0;
+    double elements = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t> > pending;
   };
   std::map<std::string, Entry> by_name;
@@ -105,12 +106,13 @@ void drain(Prof::Entry& e) {
 }
 }  // namespace
 
-void note_launch(const char* name, Stream s) {
+void note_launch(const char* name, Stream s, double elements) {
   Prof& p = prof();
   std::lock_guard<std::mutex> lock(p.mu);
   ++p.launches;
   Prof::Entry& e = p.by_name[name];
   ++e.launches;
+  e.elements += elements;
   if (p.on) {
     cudaEvent_t a;
     cudaEventCreate(&a);
@@ -157,6 +159,7 @@ std::vector<KernelStat> profiling_snapshot() {
     k.name = it->first;
     k.launches = it->second.launches;
     k.ms = it->second.ms;
+    k.elements = it->second.elements;
     out.push_back(k);
   }
   return out;

@@ -251,7 +251,7 @@ int gb200_write_jpeg(const int16_t* coeffs, int w, int h, const int* q, uint8_t*
 
 void gb200_profile_enable(int on) { gb200::profiling_enable(on != 0); }
 void gb200_profile_reset(void) { gb200::profiling_reset(); }
-int gb200_profile_get(char (*names)[48], long* launches, double* ms, int cap) {
+int gb200_profile_get(char (*names)[48], long* launches, double* ms, double* elements, int cap) {
   std::vector<gb200::KernelStat> s = gb200::profiling_snapshot();
   const int n = static_cast<int>(s.size());
   for (int i = 0; i < n && i < cap; ++i) {
@@ -259,6 +259,7 @@ int gb200_profile_get(char (*names)[48], long* launches, double* ms, int cap) {
     names[i][47] = 0;
     launches[i] = s[i].launches;
     ms[i] = s[i].ms;
+    elements[i] = s[i].elements;
   }
   return n;
 }

@@ -33,4 +33,34 @@ GB_HD T hd_max(T a, T b) { return (a < b) ? b : a; }
 GB_HD float hd_fabsf(float x) { return ::fabsf(x); }
 GB_HD double hd_fabs(double x) { return ::fabs(x); }
 
+// Relaxed atomics usable from kernel bodies on both backends.
+GB_HD unsigned int hd_atomic_add(unsigned int* p, unsigned int v) {
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(p, v);
+#else
+  return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+#endif
+}
+GB_HD unsigned int hd_atomic_or(unsigned int* p, unsigned int v) {
+#if defined(__CUDA_ARCH__)
+  return atomicOr(p, v);
+#else
+  return __atomic_fetch_or(p, v, __ATOMIC_RELAXED);
+#endif
+}
+GB_HD unsigned int hd_float_bits(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  unsigned int u;
+  __builtin_memcpy(&u, &f, 4);
+  return u;
+#endif
+}
+// Monotone map float -> uint32 (total order; -0 sorts just below +0).
+GB_HD unsigned int hd_float_sortable(float f) {
+  const unsigned int u = hd_float_bits(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
 }  // namespace gb200

@@ -584,4 +584,63 @@ struct BlockWeights {
   }
 };
 
+// ---------------------------------------------------------------------------
+// a16 ordering: keys of the selection walk, g/processor.cc:636-663.  Entry
+// (block b, candidate slot i) has key (err_i - max_err_b)/w_b ("up", slots
+// >= last_index) or (max_err_b - err_i)/w_b ("down", slots < last_index).
+// Launched over (slot 0..191, block).  Pass 1 histograms the upper 16 bits of
+// the order-preserving integer image of the key; pass 2 compacts every entry
+// whose bin is <= threshold_bin (a superset of the K smallest keys).
+struct OrderKeyCommon {
+  const float* err;        // [nblocks][192]
+  const int* count;        // [nblocks]
+  const int* last_index;   // [nblocks]
+  const float* max_err;    // [nblocks]
+  const float* weight;     // [nblocks]
+  int direction;
+  GB_HD bool key(int slot, int b, float* val) const {
+    const float w = weight[b];
+    if (w == 0) return false;
+    const int li = last_index[b];
+    const float e = err[static_cast<size_t>(b) * 192 + slot];
+    if (direction > 0) {
+      if (slot < li || slot >= count[b]) return false;
+      *val = (e - max_err[b]) / w;
+    } else {
+      if (slot >= li) return false;
+      *val = (max_err[b] - e) / w;
+    }
+    return true;
+  }
+};
+
+struct OrderKeyHist {
+  OrderKeyCommon c;
+  unsigned int* hist;  // [65536]
+  GB_HD void operator()(int slot, int b) const {
+    float v;
+    if (!c.key(slot, b, &v)) return;
+    hd_atomic_add(&hist[hd_float_sortable(v) >> 16], 1u);
+  }
+};
+
+struct OrderKeyCompact {
+  OrderKeyCommon c;
+  unsigned int threshold_bin;
+  unsigned int* counter;
+  float* out_val;
+  int* out_block;
+  unsigned int cap;
+  GB_HD void operator()(int slot, int b) const {
+    float v;
+    if (!c.key(slot, b, &v)) return;
+    if ((hd_float_sortable(v) >> 16) > threshold_bin) return;
+    const unsigned int at = hd_atomic_add(counter, 1u);
+    if (at < cap) {
+      out_val[at] = v;
+      out_block[at] = b;
+    }
+  }
+};
+
 }  // namespace gb200

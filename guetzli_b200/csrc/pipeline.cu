@@ -67,6 +67,22 @@ ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device, bool pr
   owned_.push_back(weights_);
   partial_ = static_cast<float*>(dev_alloc(sizeof(float) * 1024));
   owned_.push_back(partial_);
+  const size_t slots = static_cast<size_t>(g_.nblocks) * 192;
+  z_idx_ = static_cast<uint8_t*>(dev_alloc(slots));
+  owned_.push_back(z_idx_);
+  z_err_ = static_cast<float*>(dev_alloc(slots * sizeof(float)));
+  owned_.push_back(z_err_);
+  z_cnt_ = static_cast<int*>(dev_alloc(sizeof(int) * g_.nblocks));
+  owned_.push_back(z_cnt_);
+  d_last_index_ = static_cast<int*>(dev_alloc(sizeof(int) * g_.nblocks));
+  owned_.push_back(d_last_index_);
+  d_max_err_ = static_cast<float*>(dev_alloc(sizeof(float) * g_.nblocks));
+  owned_.push_back(d_max_err_);
+  d_hist_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * (65536 + 1)));
+  owned_.push_back(d_hist_);
+  sel_cap_ = 0;
+  d_sel_val_ = nullptr;
+  d_sel_block_ = nullptr;
 
   ps0_ = planes(kPsychoPlanes);
   lin_ = planes(3);
@@ -124,6 +140,8 @@ void ImageContext::prepare() {
 
 ImageContext::~ImageContext() {
   stream_sync(s_);
+  if (d_sel_val_) dev_free(d_sel_val_);
+  if (d_sel_block_) dev_free(d_sel_block_);
   for (size_t i = 0; i < owned_.size(); ++i) dev_free(owned_[i]);
   destroy_stream(s_);
 }
@@ -262,9 +280,9 @@ void ImageContext::block_weights(int direction, int radius, double target_distan
 void ImageContext::zeroing_orders(float block_error_limit, int lookahead, std::vector<uint8_t>* idx,
                                   std::vector<float>* err, std::vector<int>* count) {
   const size_t slots = static_cast<size_t>(g_.nblocks) * 192;
-  uint8_t* d_idx = static_cast<uint8_t*>(dev_alloc(slots));
-  float* d_err = static_cast<float*>(dev_alloc(slots * sizeof(float)));
-  int* d_cnt = static_cast<int*>(dev_alloc(sizeof(int) * g_.nblocks));
+  uint8_t* d_idx = z_idx_;
+  float* d_err = z_err_;
+  int* d_cnt = z_cnt_;
   ZeroingOrders z;
   z.cand = d_cand_;
   z.orig = d_orig_;
@@ -285,9 +303,50 @@ void ImageContext::zeroing_orders(float block_error_limit, int lookahead, std::v
   d2h(idx->data(), d_idx, slots, s_);
   d2h(err->data(), d_err, slots * sizeof(float), s_);
   d2h(count->data(), d_cnt, sizeof(int) * g_.nblocks, s_);
-  dev_free(d_idx);
-  dev_free(d_err);
-  dev_free(d_cnt);
+}
+
+size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_index,
+                                    const std::vector<float>& max_err, size_t k, std::vector<float>* val,
+                                    std::vector<int>* block) {
+  h2d(d_last_index_, last_index.data(), sizeof(int) * g_.nblocks, s_);
+  h2d(d_max_err_, max_err.data(), sizeof(float) * g_.nblocks, s_);
+  dev_zero(d_hist_, sizeof(unsigned int) * (65536 + 1), s_);
+  OrderKeyCommon c;
+  c.err = z_err_;
+  c.count = z_cnt_;
+  c.last_index = d_last_index_;
+  c.max_err = d_max_err_;
+  c.weight = weights_;
+  c.direction = direction;
+  launch_2d(s_, OrderKeyHist{c, d_hist_}, 192, g_.nblocks, "order_key_hist");
+  std::vector<unsigned int> hist(65536);
+  d2h(hist.data(), d_hist_, sizeof(unsigned int) * 65536, s_);
+  size_t total = 0, below = 0;
+  for (int i = 0; i < 65536; ++i) total += hist[i];
+  unsigned int bin = 65535;
+  for (int i = 0; i < 65536; ++i) {
+    below += hist[i];
+    if (below >= k) {
+      bin = static_cast<unsigned int>(i);
+      break;
+    }
+  }
+  if (below > sel_cap_) {
+    if (d_sel_val_) dev_free(d_sel_val_);
+    if (d_sel_block_) dev_free(d_sel_block_);
+    sel_cap_ = below + below / 2 + 1024;
+    d_sel_val_ = static_cast<float*>(dev_alloc(sel_cap_ * sizeof(float)));
+    d_sel_block_ = static_cast<int*>(dev_alloc(sel_cap_ * sizeof(int)));
+  }
+  launch_2d(s_, OrderKeyCompact{c, bin, d_hist_ + 65536, d_sel_val_, d_sel_block_, static_cast<unsigned int>(sel_cap_)},
+            192, g_.nblocks, "order_key_compact");
+  val->resize(below);
+  block->resize(below);
+  if (below) {
+    d2h(val->data(), d_sel_val_, below * sizeof(float), s_);
+    d2h(block->data(), d_sel_block_, below * sizeof(int), s_);
+  }
+  return total;
 }
 
 void ImageContext::debug_blur(const float* in, float* out, int id) {

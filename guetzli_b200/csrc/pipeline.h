@@ -16,6 +16,7 @@ struct KernelStat {
   std::string name;
   long launches;
   double ms;  // CUDA-event time accumulated when profiling is on
+  double elements;  // pixels / blocks launched (for algorithmic-bytes rooflines)
 };
 
 class ImageContext {
@@ -58,6 +59,12 @@ class ImageContext {
   // idx/err are [nblocks][192] slots, count[nblocks] valid entries each.
   void zeroing_orders(float block_error_limit, int lookahead, std::vector<uint8_t>* idx,
                       std::vector<float>* err, std::vector<int>* count);
+
+  // a16: the entries of the walk order whose keys are among (at least) the k
+  // smallest, unsorted.  Needs zeroing_orders() and the weights of the latest
+  // block_weights() call on the device.  Returns the total number of entries.
+  size_t order_smallest(int direction, const std::vector<int>& last_index, const std::vector<float>& max_err,
+                        size_t k, std::vector<float>* val, std::vector<int>* block);
 
   // test hooks: run single stages on caller-provided planes (packed [n][h][w]).
   void debug_blur(const float* in, float* out, int id);
@@ -118,6 +125,15 @@ class ImageContext {
   float* weights_;    // [nblocks]
   float* partial_;    // [1024]
   float* zero_block_max_;
+  uint8_t* z_idx_;   // [nblocks][192] candidate coefficient index
+  float* z_err_;     // [nblocks][192] candidate block error
+  int* z_cnt_;       // [nblocks]
+  int* d_last_index_;
+  float* d_max_err_;
+  unsigned int* d_hist_;  // [65536] + 1 counter
+  float* d_sel_val_;
+  int* d_sel_block_;
+  size_t sel_cap_;
   MaltaParams malta_[6];
   double asym_w0_, asym_w1_;
 };

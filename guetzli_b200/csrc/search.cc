@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cmath>
 #include <set>
+#include <stdexcept>
 #include <vector>
 
 #include "jpeg_out.h"
@@ -285,96 +286,181 @@ class Search {
     return best.dist_ok;
   }
 
+  // ---- a12/a16: frequency masking ----------------------------------------
+  struct Sfm {
+    std::vector<int> offsets;          // [nblocks+1] into cand_idx / cand_err
+    std::vector<uint8_t> cand_idx;     // coefficient index (c*64+k) per candidate
+    std::vector<float> cand_err;       // monotone block error per candidate
+    SymbolHistogram ac_h[3];
+    std::vector<uint8_t> ac_depths;
+    int ac_histogram_size, header_size, dc_size;
+    std::vector<float> max_block_error;
+    std::vector<int> last_indexes;
+    std::vector<char> block_changed;
+    std::vector<int> edit_index;
+    std::vector<int16_t> edit_value, edit_old;
+  };
+
+  struct WalkOutcome {
+    size_t consumed = 0;       // entries applied
+    bool stopped = false;      // stop test fired (else: ran out of entries)
+    size_t changed_blocks = 0;
+    float val_threshold = 0.0f;
+    int est_jpg_size = 0;
+  };
+
+  // The sequential selection walk (g/processor.cc:700-750) over `order`.
+  // The walk only *reads* the size estimate in its stop test, and the stop test
+  // cannot fire before min_coeffs_to_change entries are consumed; so the entropy
+  // codes (refreshed at every 10th entry) and the estimate are evaluated only in
+  // the 10-entry windows that can reach the test, or that contain the last entry.
+  // Same integers as the reference's eager loop.
+  WalkOutcome walk(Sfm& m, const std::vector<std::pair<int, float> >& order, int direction,
+                   int min_coeffs_to_change, double min_size_delta, int prev_size) {
+    const std::vector<int16_t>& orig = ctx_->orig_coeffs();
+    const size_t per = static_cast<size_t>(img_.nblocks) * 64;
+    WalkOutcome out;
+    out.est_jpg_size = prev_size;
+    std::fill(m.block_changed.begin(), m.block_changed.end(), 0);
+    m.edit_index.clear();
+    m.edit_value.clear();
+    m.edit_old.clear();
+    int changed_coeffs = 0;
+    const size_t n_order = order.size();
+    for (size_t i = 0; i < n_order; ++i) {
+      const int block_ix = order[i].first;
+      const int last_idx = m.last_indexes[block_ix];
+      const uint8_t* candidates = &m.cand_idx[m.offsets[block_ix]];
+      const int idx = candidates[last_idx + std::min(direction, 0)];
+      const int c = idx / 64;
+      const int k = idx % 64;
+      const int* quant = img_.q[c];
+      const int16_t* orig_block = &orig[c * per + static_cast<size_t>(block_ix) * 64];
+      const int newval = direction > 0 ? 0 : quantize_coeff(orig_block[k], quant[k]);
+      int16_t* block = &cand_[c * per + static_cast<size_t>(block_ix) * 64];
+      ac_symbols_of_block(block, quant, -1, &m.ac_h[c]);
+      bool precious = false;
+      if (k == 1 || k == 8) {
+        double sum_of_hf = 0;
+        for (int ii = 3; ii < 64; ++ii) {
+          if ((ii & 7) < 3 && ii < 3 * 8) continue;
+          sum_of_hf += std::abs(orig_block[ii]);
+        }
+        const int limit = sum_of_hf < 60 ? 4 : 8;
+        precious = std::abs(orig_block[k]) >= limit;
+      }
+      if (!precious || newval != 0) {
+        m.edit_index.push_back(static_cast<int>(c * per + static_cast<size_t>(block_ix) * 64 + k));
+        m.edit_value.push_back(static_cast<int16_t>(newval));
+        m.edit_old.push_back(block[k]);
+        block[k] = static_cast<int16_t>(newval);
+      }
+      ac_symbols_of_block(block, quant, 1, &m.ac_h[c]);
+      m.last_indexes[block_ix] += direction;
+      if (!m.block_changed[block_ix]) {
+        m.block_changed[block_ix] = 1;
+        ++out.changed_blocks;
+      }
+      out.val_threshold = order[i].second;
+      ++changed_coeffs;
+      out.consumed = i + 1;
+      if (i % 10 == 0) {
+        const bool window_can_test = static_cast<long long>(i) + 9 >= min_coeffs_to_change;
+        const bool window_has_last = n_order - 1 <= i + 9;
+        if (window_can_test || window_has_last)
+          m.ac_histogram_size = static_cast<int>(compute_entropy_codes(m.ac_h, m.ac_depths.data()));
+      }
+      const bool can_test = changed_coeffs > min_coeffs_to_change;
+      if (can_test || i + 1 == n_order) {
+        out.est_jpg_size = m.header_size + m.dc_size + m.ac_histogram_size +
+                           static_cast<int>(entropy_coded_bytes(m.ac_h, m.ac_depths.data()));
+        if (can_test && std::abs(out.est_jpg_size - prev_size) > min_size_delta) {
+          out.stopped = true;
+          break;
+        }
+      }
+    }
+    return out;
+  }
+
+  // Rolls the host state back to before walk() (used when the partial order turns
+  // out to be insufficient or ambiguous).
+  void unwalk(Sfm& m, const std::vector<std::pair<int, float> >& order, const WalkOutcome& out, int direction,
+              const SymbolHistogram saved_h[3], int saved_hist_size, const std::vector<uint8_t>& saved_depths) {
+    for (size_t i = m.edit_index.size(); i-- > 0;) cand_[m.edit_index[i]] = m.edit_old[i];
+    for (size_t i = 0; i < out.consumed; ++i) m.last_indexes[order[i].first] -= direction;
+    for (int c = 0; c < 3; ++c) m.ac_h[c] = saved_h[c];
+    m.ac_histogram_size = saved_hist_size;
+    m.ac_depths = saved_depths;
+  }
+
   void select_frequency_masking(const double target_mul) {
     const int num_blocks = img_.nblocks;
-    const int block_width = img_.bw;
-    const std::vector<int16_t>& orig = ctx_->orig_coeffs();
-    const size_t per = static_cast<size_t>(num_blocks) * 64;
-
+    Sfm m;
     // a13 + a14 on the device: per-block candidate lists
-    std::vector<int> offsets(num_blocks + 1);
-    std::vector<uint8_t> cand_idx;
-    std::vector<float> cand_err;
+    m.offsets.resize(num_blocks + 1);
+    std::vector<int> count;
     {
       Clock::time_point t0 = Clock::now();
       std::vector<uint8_t> idx;
       std::vector<float> err;
-      std::vector<int> count;
       ctx_->zeroing_orders(params_.butteraugli_target, params_.zeroing_greedy_lookahead, &idx, &err, &count);
       size_t total = 0;
       for (int b = 0; b < num_blocks; ++b) total += count[b];
-      cand_idx.reserve(total);
-      cand_err.reserve(total);
+      m.cand_idx.reserve(total);
+      m.cand_err.reserve(total);
       for (int b = 0; b < num_blocks; ++b) {
-        offsets[b] = static_cast<int>(cand_idx.size());
-        cand_idx.insert(cand_idx.end(), &idx[static_cast<size_t>(b) * 192], &idx[static_cast<size_t>(b) * 192] + count[b]);
-        cand_err.insert(cand_err.end(), &err[static_cast<size_t>(b) * 192], &err[static_cast<size_t>(b) * 192] + count[b]);
+        m.offsets[b] = static_cast<int>(m.cand_idx.size());
+        m.cand_idx.insert(m.cand_idx.end(), &idx[static_cast<size_t>(b) * 192], &idx[static_cast<size_t>(b) * 192] + count[b]);
+        m.cand_err.insert(m.cand_err.end(), &err[static_cast<size_t>(b) * 192], &err[static_cast<size_t>(b) * 192] + count[b]);
       }
-      offsets[num_blocks] = static_cast<int>(cand_idx.size());
+      m.offsets[num_blocks] = static_cast<int>(m.cand_idx.size());
       st_->ms_zeroing += ms_since(t0);
     }
 
-    SymbolHistogram ac_h[3];
-    const int header_size = static_cast<int>(jpeg_header_bytes(img_));
-    const int dc_size = static_cast<int>(estimate_dc_bytes(img_));
-    build_ac_histograms(img_, ac_h);
-    std::vector<uint8_t> ac_depths(3 * SymbolHistogram::kSize);
-    int ac_histogram_size = static_cast<int>(compute_entropy_codes(ac_h, ac_depths.data()));
-    const int base_size =
-        header_size + dc_size + ac_histogram_size + static_cast<int>(entropy_coded_bytes(ac_h, ac_depths.data()));
+    m.header_size = static_cast<int>(jpeg_header_bytes(img_));
+    m.dc_size = static_cast<int>(estimate_dc_bytes(img_));
+    build_ac_histograms(img_, m.ac_h);
+    m.ac_depths.resize(3 * SymbolHistogram::kSize);
+    m.ac_histogram_size = static_cast<int>(compute_entropy_codes(m.ac_h, m.ac_depths.data()));
+    const int base_size = m.header_size + m.dc_size + m.ac_histogram_size +
+                          static_cast<int>(entropy_coded_bytes(m.ac_h, m.ac_depths.data()));
     int prev_size = base_size;
 
-    std::vector<float> max_block_error(num_blocks);
-    std::vector<int> last_indexes(num_blocks);
+    m.max_block_error.assign(num_blocks, 0.0f);
+    m.last_indexes.assign(num_blocks, 0);
+    m.block_changed.assign(num_blocks, 0);
     std::vector<float> block_weight(num_blocks);
-    std::vector<int> edit_index;
-    std::vector<int16_t> edit_value;
+    size_t last_consumed = 0;
 
     bool first_up_iter = true;
     const int directions[2] = {1, -1};
     for (int di = 0; di < 2; ++di) {
       const int direction = directions[di];
       for (;;) {
-        std::vector<std::pair<int, float> > global_order;
+        // a15 on the device; entry counts from the per-block bookkeeping (:625-669)
+        size_t order_size = 0;
         int blocks_to_change = 0;
         for (int rblock = 1; rblock <= 4; ++rblock) {
           ctx_->block_weights(direction, rblock, params_.butteraugli_target * target_mul, first_up_iter,
                               block_weight.data());
-          global_order.clear();
+          order_size = 0;
           blocks_to_change = 0;
-          for (int block_ix = 0; block_ix < num_blocks; ++block_ix) {
-            const int last_index = last_indexes[block_ix];
-            const int offset = offsets[block_ix];
-            const int num_candidates = offsets[block_ix + 1] - offset;
-            const float* candidate_errors = &cand_err[offset];
-            const float max_err = max_block_error[block_ix];
-            if (block_weight[block_ix] == 0) continue;
+          for (int b = 0; b < num_blocks; ++b) {
+            if (block_weight[b] == 0) continue;
+            const int li = m.last_indexes[b];
+            const int nc = m.offsets[b + 1] - m.offsets[b];
             if (direction > 0) {
-              for (int i = last_index; i < num_candidates; ++i) {
-                const float val = (candidate_errors[i] - max_err) / block_weight[block_ix];
-                global_order.push_back(std::make_pair(block_ix, val));
-              }
-              blocks_to_change += (last_index < num_candidates ? 1 : 0);
+              order_size += li < nc ? nc - li : 0;
+              blocks_to_change += (li < nc ? 1 : 0);
             } else {
-              for (int i = last_index - 1; i >= 0; --i) {
-                const float val = (max_err - candidate_errors[i]) / block_weight[block_ix];
-                global_order.push_back(std::make_pair(block_ix, val));
-              }
-              blocks_to_change += (last_index > 0 ? 1 : 0);
+              order_size += li > 0 ? li : 0;
+              blocks_to_change += (li > 0 ? 1 : 0);
             }
           }
-          if (!global_order.empty()) break;
+          if (order_size != 0) break;
         }
-        if (global_order.empty()) break;
-
-        {
-          Clock::time_point t0 = Clock::now();
-          std::sort(global_order.begin(), global_order.end(),
-                    [](const std::pair<int, float>& a, const std::pair<int, float>& b) {
-                      return a.second < b.second;
-                    });
-          st_->ms_sort += ms_since(t0);
-        }
+        if (order_size == 0) break;
 
         double rel_size_delta = direction > 0 ? 0.01 : 0.0005;
         if (direction > 0 && distance_ok(1.0)) rel_size_delta = 0.05;
@@ -382,74 +468,111 @@ class Search {
         const float coeffs_to_change_per_block = direction > 0 ? 2.0f : 1 * 1 * 0.2f;
         int min_coeffs_to_change = coeffs_to_change_per_block * blocks_to_change;
 
-        if (first_up_iter) {
-          const float limit = 0.75f * params_.butteraugli_target;
-          std::vector<std::pair<int, float> >::iterator it = std::partition_point(
-              global_order.begin(), global_order.end(),
-              [=](const std::pair<int, float>& a) { return a.second < limit; });
-          min_coeffs_to_change = std::max<int>(min_coeffs_to_change, it - global_order.begin());
-          first_up_iter = false;
-        }
-
-        Clock::time_point tw = Clock::now();
-        std::set<int> changed_blocks;
-        float val_threshold = 0.0;
-        int changed_coeffs = 0;
-        int est_jpg_size = prev_size;
-        edit_index.clear();
-        edit_value.clear();
-        for (size_t i = 0; i < global_order.size(); ++i) {
-          const int block_ix = global_order[i].first;
-          const int last_idx = last_indexes[block_ix];
-          const uint8_t* candidates = &cand_idx[offsets[block_ix]];
-          const int idx = candidates[last_idx + std::min(direction, 0)];
-          const int c = idx / 64;
-          const int k = idx % 64;
-          const int* quant = img_.q[c];
-          const int16_t* orig_block = &orig[c * per + static_cast<size_t>(block_ix) * 64];
-          const int newval = direction > 0 ? 0 : quantize_coeff(orig_block[k], quant[k]);
-          int16_t* block = &cand_[c * per + static_cast<size_t>(block_ix) * 64];
-          ac_symbols_of_block(block, quant, -1, &ac_h[c]);
-          double sum_of_hf = 0;
-          for (int ii = 3; ii < 64; ++ii) {
-            if ((ii & 7) < 3 && ii < 3 * 8) continue;
-            sum_of_hf += std::abs(orig_block[ii]);
+        std::vector<std::pair<int, float> > order;
+        WalkOutcome out;
+        bool done = false;
+        // Fast path ("down" iterations consume a tiny prefix of the order): fetch only
+        // the smallest keys from the device, sort those, and fall back to the complete
+        // reference-ordered sort whenever the result could depend on how std::sort
+        // places equal keys of different blocks, or the prefix runs out.
+        if (direction < 0 && order_size > 16384) {
+          size_t want = std::max<size_t>(4096, 8 * last_consumed + 4 * static_cast<size_t>(min_coeffs_to_change) + 1024);
+          while (!done && want < order_size / 2) {
+            Clock::time_point t0 = Clock::now();
+            std::vector<float> val;
+            std::vector<int> blk;
+            const size_t total = ctx_->order_smallest(direction, m.last_indexes, m.max_block_error, want, &val, &blk);
+            if (total != order_size) throw std::runtime_error("order_smallest: entry count mismatch");
+            if (val.size() >= order_size) break;
+            order.resize(val.size());
+            for (size_t i = 0; i < val.size(); ++i) order[i] = std::make_pair(blk[i], val[i]);
+            std::sort(order.begin(), order.end(), [](const std::pair<int, float>& a, const std::pair<int, float>& b) {
+              return a.second < b.second;
+            });
+            st_->ms_sort += ms_since(t0);
+            Clock::time_point tw = Clock::now();
+            SymbolHistogram saved_h[3] = {m.ac_h[0], m.ac_h[1], m.ac_h[2]};
+            const int saved_hist_size = m.ac_histogram_size;
+            const std::vector<uint8_t> saved_depths = m.ac_depths;
+            out = walk(m, order, direction, min_coeffs_to_change, min_size_delta, prev_size);
+            st_->ms_walk += ms_since(tw);
+            // usable only if the walk stopped strictly inside the fetched prefix and no
+            // two equal keys of different blocks occur up to (and including) the boundary
+            bool ok = out.stopped && out.consumed < order.size();
+            if (ok) {
+              for (size_t i = 0; i < out.consumed; ++i) {
+                if (!(order[i].second < order[i + 1].second) && order[i].first != order[i + 1].first) {
+                  ok = false;
+                  break;
+                }
+              }
+              if (ok) {
+                done = true;
+                break;
+              }
+              unwalk(m, order, out, direction, saved_h, saved_hist_size, saved_depths);
+              break;  // ambiguous tie: take the exact path
+            }
+            unwalk(m, order, out, direction, saved_h, saved_hist_size, saved_depths);
+            want *= 8;
           }
-          const int limit = sum_of_hf < 60 ? 4 : 8;
-          const bool precious = (k == 1 || k == 8) && std::abs(orig_block[k]) >= limit;
-          if (!precious || newval != 0) {
-            block[k] = static_cast<int16_t>(newval);
-            edit_index.push_back(static_cast<int>(c * per + static_cast<size_t>(block_ix) * 64 + k));
-            edit_value.push_back(static_cast<int16_t>(newval));
-          }
-          ac_symbols_of_block(block, quant, 1, &ac_h[c]);
-          last_indexes[block_ix] += direction;
-          changed_blocks.insert(block_ix);
-          val_threshold = global_order[i].second;
-          ++changed_coeffs;
-          if (i % 10 == 0) ac_histogram_size = static_cast<int>(compute_entropy_codes(ac_h, ac_depths.data()));
-          est_jpg_size = header_size + dc_size + ac_histogram_size +
-                         static_cast<int>(entropy_coded_bytes(ac_h, ac_depths.data()));
-          if (changed_coeffs > min_coeffs_to_change && std::abs(est_jpg_size - prev_size) > min_size_delta) break;
         }
-        const size_t global_order_size = global_order.size();
-        std::vector<std::pair<int, float> >().swap(global_order);
-        st_->ms_walk += ms_since(tw);
-        (void)block_width;
+        if (!done) {
+          // complete order, built and sorted exactly like the reference (:636-678)
+          Clock::time_point t0 = Clock::now();
+          order.clear();
+          order.reserve(order_size);
+          for (int block_ix = 0; block_ix < num_blocks; ++block_ix) {
+            if (block_weight[block_ix] == 0) continue;
+            const int last_index = m.last_indexes[block_ix];
+            const int offset = m.offsets[block_ix];
+            const int num_candidates = m.offsets[block_ix + 1] - offset;
+            const float* candidate_errors = &m.cand_err[offset];
+            const float max_err = m.max_block_error[block_ix];
+            if (direction > 0) {
+              for (int i = last_index; i < num_candidates; ++i) {
+                const float val = (candidate_errors[i] - max_err) / block_weight[block_ix];
+                order.push_back(std::make_pair(block_ix, val));
+              }
+            } else {
+              for (int i = last_index - 1; i >= 0; --i) {
+                const float val = (max_err - candidate_errors[i]) / block_weight[block_ix];
+                order.push_back(std::make_pair(block_ix, val));
+              }
+            }
+          }
+          std::sort(order.begin(), order.end(), [](const std::pair<int, float>& a, const std::pair<int, float>& b) {
+            return a.second < b.second;
+          });
+          st_->ms_sort += ms_since(t0);
+          if (first_up_iter) {
+            const float limit = 0.75f * params_.butteraugli_target;
+            std::vector<std::pair<int, float> >::iterator it = std::partition_point(
+                order.begin(), order.end(), [=](const std::pair<int, float>& a) { return a.second < limit; });
+            min_coeffs_to_change = std::max<int>(min_coeffs_to_change, it - order.begin());
+          }
+          Clock::time_point tw = Clock::now();
+          out = walk(m, order, direction, min_coeffs_to_change, min_size_delta, prev_size);
+          st_->ms_walk += ms_since(tw);
+        }
+        first_up_iter = false;
+        last_consumed = out.consumed;
+        std::vector<std::pair<int, float> >().swap(order);
 
-        for (int i = 0; i < num_blocks; ++i) max_block_error[i] += block_weight[i] * val_threshold * direction;
+        for (int i = 0; i < num_blocks; ++i)
+          m.max_block_error[i] += block_weight[i] * out.val_threshold * direction;
 
         ++st_->iterations;
         if (direction > 0) ++st_->iterations_up; else ++st_->iterations_down;
-        ctx_->scatter_coeffs(edit_index, edit_value);
+        ctx_->scatter_coeffs(m.edit_index, m.edit_value);
         std::string encoded = timed_write();
         logf("Iter %2d: %s(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
-             st_->iterations, "f111111", 7, direction > 0 ? "up" : "down", changed_coeffs, global_order_size,
-             changed_blocks.size(), blocks_to_change, num_blocks, val_threshold, encoded.size(),
-             100.0 - (100.0 * est_jpg_size) / encoded.size());
+             st_->iterations, "f111111", 7, direction > 0 ? "up" : "down", static_cast<int>(out.consumed),
+             order_size, out.changed_blocks, blocks_to_change, num_blocks, out.val_threshold, encoded.size(),
+             100.0 - (100.0 * out.est_jpg_size) / encoded.size());
         compare();
         maybe_output(encoded);
-        prev_size = est_jpg_size;
+        prev_size = out.est_jpg_size;
       }
     }
   }

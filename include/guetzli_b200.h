@@ -121,7 +121,7 @@ int gb200_write_jpeg(const int16_t* coeffs, int w, int h, const int* q, uint8_t*
 void gb200_profile_enable(int on);
 void gb200_profile_reset(void);
 /* fills up to cap entries; returns the number of distinct kernels */
-int gb200_profile_get(char (*names)[48], long* launches, double* ms, int cap);
+int gb200_profile_get(char (*names)[48], long* launches, double* ms, double* elements, int cap);
 
 #ifdef __cplusplus
 }
