@@ -1,0 +1,225 @@
+// Device side of a11: entropy-coding of the candidate coefficients without
+// moving them over PCIe.  Per iteration the search needs the exact size of the
+// sequential JPEG (g/jpeg_data_writer.cc:455-536) and, a few times per image, its
+// bytes.  Kernels:
+//   JpegHistAcc    DC/AC symbol histograms (privatised global atomics)
+//   JpegHistSum    reduction of the private copies
+//   [host: cluster histograms, build canonical Huffman codes -- 1.5 KB of tables]
+//   JpegMcuBits    code length of every MCU (Y, Cb, Cr block)   -> exclusive scan
+//   JpegEmit       every MCU ORs its bits into the scan at its bit offset
+//   JpegCountFF    bytes equal to 0xFF (each needs a stuffed zero byte)
+// All integer; bit-exact by construction against the host serialiser (jpeg_out.cc).
+#pragma once
+#include "hd.h"
+#include "kernels.h"
+
+namespace gb200 {
+
+static const int kHistCopies = 256;   // private histogram copies (block index & 255)
+static const int kHistStride = 6 * 257;  // [dc0 dc1 dc2 ac0 ac1 ac2][257]
+
+GB_HD int hd_floor_log2_nz(unsigned int n) {
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz(n);
+#else
+  return 31 ^ __builtin_clz(n);
+#endif
+}
+
+// Visits the entropy-coding symbols of one 8x8 block in scan order
+// (EncodeDCTBlockSequential, g/jpeg_data_writer.cc:455): v.dc(nbits, extra),
+// v.ac(symbol, nbits, extra).  dq = dequantised coefficients, q = quant table,
+// prev_dc = quantised DC of the previous block of the same component.
+template <class V>
+GB_HD void visit_block_symbols(const int16_t* dq, const int* q, int prev_dc, const int* zigzag, V& v) {
+  const int16_t dc = static_cast<int16_t>(dq[0] / q[0]);
+  int16_t diff = static_cast<int16_t>(dc - prev_dc);
+  int16_t low = diff;
+  if (diff < 0) {
+    diff = static_cast<int16_t>(-diff);
+    --low;
+  }
+  const unsigned int mag = static_cast<unsigned int>(static_cast<int>(diff));
+  const int nb = mag == 0 ? 0 : hd_floor_log2_nz(mag) + 1;
+  v.dc(nb, static_cast<unsigned int>(low) & ((1u << nb) - 1u));
+  int run = 0;
+  for (int k = 1; k < 64; ++k) {
+    const int nat = zigzag[k];
+    int c = dq[nat];
+    if (c == 0) {
+      ++run;
+      continue;
+    }
+    c /= q[nat];
+    int m = c, lo = c;
+    if (c < 0) {
+      m = -c;
+      lo = ~m;
+    }
+    while (run > 15) {
+      v.ac(0xf0, 0, 0u);
+      run -= 16;
+    }
+    const int nbits = hd_floor_log2_nz(static_cast<unsigned int>(m)) + 1;
+    v.ac((run << 4) + nbits, nbits, static_cast<unsigned int>(lo) & ((1u << nbits) - 1u));
+    run = 0;
+  }
+  if (run > 0) v.ac(0, 0, 0u);
+}
+
+struct JpegHistAcc {  // 1D over 3*nblocks: i = c*nblocks + b
+  const int16_t* cand;
+  const int* q;          // [192]
+  const int* zigzag;     // [64]
+  unsigned int* hist;    // [kHistCopies][6][257]
+  unsigned int* chroma_nonzero;
+  int nblocks;
+  struct Visitor {
+    unsigned int* dc_h;
+    unsigned int* ac_h;
+    GB_HD void dc(int nbits, unsigned int) { hd_atomic_add(&dc_h[nbits], 1u); }
+    GB_HD void ac(int symbol, int, unsigned int) { hd_atomic_add(&ac_h[symbol], 1u); }
+  };
+  GB_HD void operator()(int i) const {
+    const int c = i / nblocks, b = i - c * nblocks;
+    const int16_t* blk = cand + static_cast<size_t>(i) * 64;
+    const int* qc = q + 64 * c;
+    const int prev = b > 0 ? (blk - 64)[0] / qc[0] : 0;
+    unsigned int* base = hist + static_cast<size_t>(b & (kHistCopies - 1)) * kHistStride;
+    Visitor v{base + c * 257, base + (3 + c) * 257};
+    visit_block_symbols(blk, qc, prev, zigzag, v);
+    if (c > 0) {
+      bool any = false;
+      for (int k = 0; k < 64; ++k) any = any || (blk[k] != 0);
+      if (any) *chroma_nonzero = 1u;
+    }
+  }
+};
+
+struct JpegHistSum {  // 1D over 6*257
+  const unsigned int* hist;
+  unsigned int* out;
+  GB_HD void operator()(int i) const {
+    unsigned int s = 0;
+    for (int k = 0; k < kHistCopies; ++k) s += hist[static_cast<size_t>(k) * kHistStride + i];
+    out[i] = s;
+  }
+};
+
+struct JpegCodes {
+  const uint8_t* depth;    // [6][256]  dc0 dc1 dc2 ac0 ac1 ac2
+  const uint16_t* code;    // [6][256]
+};
+
+struct JpegMcuBits {  // 1D over nblocks
+  const int16_t* cand;
+  const int* q;
+  const int* zigzag;
+  JpegCodes codes;
+  unsigned int* bits;
+  int nblocks, ncomp;
+  struct Visitor {
+    const uint8_t* dc_d;
+    const uint8_t* ac_d;
+    unsigned int n;
+    GB_HD void dc(int nbits, unsigned int) { n += dc_d[nbits] + nbits; }
+    GB_HD void ac(int symbol, int nbits, unsigned int) { n += ac_d[symbol] + nbits; }
+  };
+  GB_HD void operator()(int b) const {
+    unsigned int total = 0;
+    for (int c = 0; c < ncomp; ++c) {
+      const int16_t* blk = cand + (static_cast<size_t>(c) * nblocks + b) * 64;
+      const int* qc = q + 64 * c;
+      const int prev = b > 0 ? (blk - 64)[0] / qc[0] : 0;
+      Visitor v{codes.depth + c * 256, codes.depth + (3 + c) * 256, 0u};
+      visit_block_symbols(blk, qc, prev, zigzag, v);
+      total += v.n;
+    }
+    bits[b] = total;
+  }
+};
+
+// Bit sink writing MSB-first into big-endian 32-bit words with atomic OR (the
+// first and last word of an MCU are shared with its neighbours).
+struct BitCursor {
+  unsigned int* words;
+  unsigned long long pos;  // absolute bit position
+  GB_HD void put(int n, unsigned int value) {
+    // n <= 27 here (16-bit code, or 11-bit extra), may straddle two words
+    while (n > 0) {
+      const unsigned int w = static_cast<unsigned int>(pos >> 5);
+      const int used = static_cast<int>(pos & 31);
+      const int room = 32 - used;
+      const int take = n < room ? n : room;
+      const unsigned int chunk = (value >> (n - take)) & (take == 32 ? 0xffffffffu : ((1u << take) - 1u));
+      hd_atomic_or(&words[w], chunk << (room - take));
+      pos += take;
+      n -= take;
+    }
+  }
+};
+
+struct JpegEmit {  // 1D over nblocks
+  const int16_t* cand;
+  const int* q;
+  const int* zigzag;
+  JpegCodes codes;
+  const unsigned int* offset;  // exclusive scan of JpegMcuBits
+  unsigned int* words;
+  int nblocks, ncomp;
+  struct Visitor {
+    const uint8_t* dc_d;
+    const uint16_t* dc_c;
+    const uint8_t* ac_d;
+    const uint16_t* ac_c;
+    BitCursor cur;
+    GB_HD void dc(int nbits, unsigned int extra) {
+      cur.put(dc_d[nbits], dc_c[nbits]);
+      if (nbits > 0) cur.put(nbits, extra);
+    }
+    GB_HD void ac(int symbol, int nbits, unsigned int extra) {
+      cur.put(ac_d[symbol], ac_c[symbol]);
+      if (nbits > 0) cur.put(nbits, extra);
+    }
+  };
+  GB_HD void operator()(int b) const {
+    BitCursor cur{words, offset[b]};
+    for (int c = 0; c < ncomp; ++c) {
+      const int16_t* blk = cand + (static_cast<size_t>(c) * nblocks + b) * 64;
+      const int* qc = q + 64 * c;
+      const int prev = b > 0 ? (blk - 64)[0] / qc[0] : 0;
+      Visitor v{codes.depth + c * 256, codes.code + c * 256, codes.depth + (3 + c) * 256,
+                codes.code + (3 + c) * 256, cur};
+      visit_block_symbols(blk, qc, prev, zigzag, v);
+      cur = v.cur;
+    }
+  }
+};
+
+// Pads the last byte with one-bits (JumpToByteBoundary, g/jpeg_bit_writer.h:90) and
+// counts 0xFF bytes; 1D over the words of the scan.
+struct JpegCountFF {
+  unsigned int* words;
+  unsigned long long total_bits;
+  unsigned int* counter;
+  GB_HD void operator()(int w) const {
+    const unsigned long long nbytes = (total_bits + 7) >> 3;
+    unsigned int v = words[w];
+    const unsigned long long first_bit = static_cast<unsigned long long>(w) << 5;
+    if (total_bits > first_bit && total_bits - first_bit < 32 && (total_bits & 7)) {
+      // this word holds the final partial byte
+      const int used = static_cast<int>(total_bits - first_bit);
+      const int pad = 8 - (used & 7);
+      v |= ((1u << pad) - 1u) << (32 - used - pad);
+      words[w] = v;
+    }
+    unsigned int n = 0;
+    for (int k = 0; k < 4; ++k) {
+      const unsigned long long byte_index = (static_cast<unsigned long long>(w) << 2) + k;
+      if (byte_index < nbytes && ((v >> (24 - 8 * k)) & 0xffu) == 0xffu) ++n;
+    }
+    if (n) hd_atomic_add(counter, n);
+  }
+};
+
+}  // namespace gb200

@@ -326,13 +326,15 @@ size_t entropy_coded_bytes(const SymbolHistogram* h3, const uint8_t* depths) {
   return (bits + 7) / 8;
 }
 
-std::string write_jpeg(const CoeffImage& img) {
+JpegPlan plan_jpeg(const CoeffImage& img, int ncomp, SymbolHistogram* dc_h, SymbolHistogram* ac_h) {
   const int K = SymbolHistogram::kSize;
-  const int ncomp = num_output_components(img);
+  JpegPlan plan;
+  plan.ncomp = ncomp;
+  memset(plan.depth, 0, sizeof(plan.depth));
+  memset(plan.code, 0, sizeof(plan.code));
   const QuantSet qs = dedup_quant(img, ncomp);
   const int* zz = zigzag_to_natural();
-  std::string out;
-  out.reserve(static_cast<size_t>(img.nblocks) * 48 + 1024);
+  std::string& out = plan.prefix;
   auto byte = [&out](int b) { out.push_back(static_cast<char>(b)); };
 
   // SOI + JFIF APP0 (g/jpeg_data_writer.cc:52-63)
@@ -368,16 +370,11 @@ std::string write_jpeg(const CoeffImage& img) {
     }
   }
   // Huffman codes: cluster DC then AC histograms
-  SymbolHistogram dc_h[3], ac_h[3];
-  build_dc_histograms(img, ncomp, dc_h);
   size_t num_dc = ncomp, num_ac = ncomp;
   int dc_index[4], ac_index[4];
   std::vector<uint8_t> dc_depth(3 * K), ac_depth(3 * K);
   cluster_histograms(dc_h, &num_dc, dc_index, dc_depth.data());
-  for (int c = 0; c < ncomp; ++c)
-    for (int b = 0; b < img.nblocks; ++b) ac_symbols_of_block(img.block(c, b), img.q[c], 1, &ac_h[c]);
   cluster_histograms(ac_h, &num_ac, ac_index, ac_depth.data());
-  CodeTable dc_table[3], ac_table[3];
   {
     int total_symbols = 0;
     for (size_t i = 0; i < num_dc; ++i) total_symbols += dc_h[i].num_symbols();
@@ -392,8 +389,13 @@ std::string write_jpeg(const CoeffImage& img) {
       CodeTable table;
       canonical_code(is_dc ? &dc_depth[idx * K] : &ac_depth[idx * K], counts, values, &table);
       for (int c = 0; c < ncomp; ++c) {
-        if (is_dc && dc_index[c] == idx) dc_table[c] = table;
-        if (!is_dc && ac_index[c] == idx) ac_table[c] = table;
+        const bool mine = is_dc ? dc_index[c] == idx : ac_index[c] == idx;
+        if (!mine) continue;
+        const int slot = is_dc ? c : 3 + c;
+        for (int s = 0; s < 256; ++s) {
+          plan.depth[slot][s] = table.depth[s] == 255 ? 0 : table.depth[s];
+          plan.code[slot][s] = table.depth[s] == 255 ? 0 : static_cast<uint16_t>(table.code[s]);
+        }
       }
       int max_len = 16;
       while (max_len > 0 && counts[max_len] == 0) --max_len;
@@ -416,6 +418,25 @@ std::string write_jpeg(const CoeffImage& img) {
     }
     byte(0); byte(63); byte(0);
   }
+  return plan;
+}
+
+void host_symbol_histograms(const CoeffImage& img, int ncomp, SymbolHistogram* dc_h, SymbolHistogram* ac_h) {
+  build_dc_histograms(img, ncomp, dc_h);
+  for (int c = 0; c < ncomp; ++c)
+    for (int b = 0; b < img.nblocks; ++b) ac_symbols_of_block(img.block(c, b), img.q[c], 1, &ac_h[c]);
+}
+
+std::string write_jpeg(const CoeffImage& img) {
+  const int ncomp = num_output_components(img);
+  const int* zz = zigzag_to_natural();
+  SymbolHistogram dc_h[3], ac_h[3];
+  host_symbol_histograms(img, ncomp, dc_h, ac_h);
+  JpegPlan plan = plan_jpeg(img, ncomp, dc_h, ac_h);
+  std::string out;
+  out.reserve(static_cast<size_t>(img.nblocks) * 48 + 1024);
+  out = plan.prefix;
+  auto byte = [&out](int b) { out.push_back(static_cast<char>(b)); };
   // entropy-coded scan, one block of each component per MCU (444)
   {
     BitSink bw(&out);
@@ -424,8 +445,10 @@ std::string write_jpeg(const CoeffImage& img) {
       for (int c = 0; c < ncomp; ++c) {
         const int16_t* dq = img.block(c, b);
         const int* q = img.q[c];
-        const CodeTable& dct = dc_table[c];
-        const CodeTable& act = ac_table[c];
+        const uint8_t* dcd = plan.depth[c];
+        const uint16_t* dcc = plan.code[c];
+        const uint8_t* acd = plan.depth[3 + c];
+        const uint16_t* acc = plan.code[3 + c];
         // DC difference (g/jpeg_data_writer.cc:460-474), int16 arithmetic
         const int16_t dc = static_cast<int16_t>(dq[0] / q[0]);
         int16_t diff = static_cast<int16_t>(dc - last_dc[c]);
@@ -436,7 +459,7 @@ std::string write_jpeg(const CoeffImage& img) {
           --bits;
         }
         int nbits = floor_log2(static_cast<uint32_t>(static_cast<int>(diff))) + 1;
-        bw.put(dct.depth[nbits], dct.code[nbits]);
+        bw.put(dcd[nbits], dcc[nbits]);
         if (nbits > 0) bw.put(nbits, bits & ((1 << nbits) - 1));
         int run = 0;
         for (int k = 1; k < 64; ++k) {
@@ -453,21 +476,35 @@ std::string write_jpeg(const CoeffImage& img) {
             low = ~mag;
           }
           while (run > 15) {
-            bw.put(act.depth[0xf0], act.code[0xf0]);
+            bw.put(acd[0xf0], acc[0xf0]);
             run -= 16;
           }
           nbits = floor_log2_nz(mag) + 1;
           const int symbol = (run << 4) + nbits;
-          bw.put(act.depth[symbol], act.code[symbol]);
+          bw.put(acd[symbol], acc[symbol]);
           bw.put(nbits, low & ((1 << nbits) - 1));
           run = 0;
         }
-        if (run > 0) bw.put(act.depth[0], act.code[0]);
+        if (run > 0) bw.put(acd[0], acc[0]);
       }
     }
     bw.finish();
   }
   byte(0xff); byte(0xd9);
+  return out;
+}
+
+// Turns the raw (unstuffed, padded) scan bytes into the final file.
+std::string assemble_jpeg(const JpegPlan& plan, const uint8_t* scan, size_t nbytes) {
+  std::string out;
+  out.reserve(plan.prefix.size() + nbytes + nbytes / 64 + 16);
+  out = plan.prefix;
+  for (size_t i = 0; i < nbytes; ++i) {
+    out.push_back(static_cast<char>(scan[i]));
+    if (scan[i] == 0xff) out.push_back(0);
+  }
+  out.push_back(static_cast<char>(0xff));
+  out.push_back(static_cast<char>(0xd9));
   return out;
 }
 

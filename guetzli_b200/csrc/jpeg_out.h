@@ -65,6 +65,19 @@ size_t jpeg_header_bytes(const CoeffImage& img);                        // g/jpe
 size_t compute_entropy_codes(const SymbolHistogram* h3, uint8_t* depths);
 size_t entropy_coded_bytes(const SymbolHistogram* h3, const uint8_t* depths);  // g/processor.cc:518
 
+// Everything of the file that precedes the entropy-coded scan (SOI, APP0, DQT,
+// SOF1, DHT, SOS) plus the canonical codes of the scan, derived from symbol
+// histograms (which the clustering modifies).  Slots: dc0 dc1 dc2 ac0 ac1 ac2.
+struct JpegPlan {
+  std::string prefix;
+  int ncomp;
+  uint8_t depth[6][256];
+  uint16_t code[6][256];
+};
+JpegPlan plan_jpeg(const CoeffImage& img, int ncomp, SymbolHistogram* dc_h, SymbolHistogram* ac_h);
+void host_symbol_histograms(const CoeffImage& img, int ncomp, SymbolHistogram* dc_h, SymbolHistogram* ac_h);
+std::string assemble_jpeg(const JpegPlan& plan, const uint8_t* scan, size_t nbytes);
+
 // SaveToJpegData + WriteJpeg (strip_metadata path): the complete JPEG file.
 std::string write_jpeg(const CoeffImage& img);
 

@@ -5,8 +5,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <stdexcept>
 
 #include "block_math.h"
+#include "jpeg_dev.h"
 
 namespace gb200 {
 
@@ -83,6 +85,21 @@ ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device, bool pr
   sel_cap_ = 0;
   d_sel_val_ = nullptr;
   d_sel_block_ = nullptr;
+  j_hist_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * (static_cast<size_t>(kHistCopies + 1) * kHistStride + 2)));
+  owned_.push_back(j_hist_);
+  j_bits_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * g_.nblocks));
+  owned_.push_back(j_bits_);
+  j_offset_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * g_.nblocks));
+  owned_.push_back(j_offset_);
+  j_sums_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * (g_.nblocks / 1024 + 32)));
+  owned_.push_back(j_sums_);
+  j_depth_ = static_cast<uint8_t*>(dev_alloc(6 * 256));
+  owned_.push_back(j_depth_);
+  j_code_ = static_cast<uint16_t*>(dev_alloc(6 * 256 * sizeof(uint16_t)));
+  owned_.push_back(j_code_);
+  j_words_ = nullptr;
+  j_words_cap_ = 0;
+  j_nbytes_ = 0;
 
   ps0_ = planes(kPsychoPlanes);
   lin_ = planes(3);
@@ -116,6 +133,12 @@ void ImageContext::prepare() {
   // a2: one-time forward DCT; the host search keeps a copy of the coefficients.
   launch_1d(s_, FdctBlocks{d_rgb_, d_orig_, g_}, g_.nblocks, "fdct_blocks");
   d2d(d_cand_, d_orig_, ncoef * 2, s_);
+  {
+    int ones[192];
+    for (int i = 0; i < 192; ++i) ones[i] = 1;
+    h2d(d_q_, ones, sizeof(ones), s_);
+    stream_sync(s_);
+  }
   orig_host_.resize(ncoef);
   d2h(orig_host_.data(), d_orig_, ncoef * 2, s_);
 
@@ -142,6 +165,7 @@ ImageContext::~ImageContext() {
   stream_sync(s_);
   if (d_sel_val_) dev_free(d_sel_val_);
   if (d_sel_block_) dev_free(d_sel_block_);
+  if (j_words_) dev_free(j_words_);
   for (size_t i = 0; i < owned_.size(); ++i) dev_free(owned_[i]);
   destroy_stream(s_);
 }
@@ -347,6 +371,156 @@ size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_
     d2h(block->data(), d_sel_block_, below * sizeof(int), s_);
   }
   return total;
+}
+
+// ---------------------------------------------------------------------------
+// a11 on the device
+#if defined(GB200_HOSTSIM)
+void ImageContext::exclusive_scan(const unsigned int* in, unsigned int* out, int n, unsigned long long* total) {
+  unsigned long long acc = 0;
+  for (int i = 0; i < n; ++i) {
+    out[i] = static_cast<unsigned int>(acc);
+    acc += in[i];
+  }
+  *total = acc;
+}
+#else
+namespace {
+// 1024 elements per CTA (256 threads x 4): local exclusive scan + CTA total.
+__global__ void __launch_bounds__(256) k_scan_local(const unsigned int* in, unsigned int* out, unsigned int* sums, int n) {
+  __shared__ unsigned int warp_tot[8];
+  const int base = blockIdx.x * 1024 + threadIdx.x * 4;
+  unsigned int v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = (base + k < n) ? in[base + k] : 0u;
+  const unsigned int mine = v[0] + v[1] + v[2] + v[3];
+  unsigned int incl = mine;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  unsigned int warp_base = 0;
+  for (int k = 0; k < warp; ++k) warp_base += warp_tot[k];
+  unsigned int run = warp_base + incl - mine;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+  if (threadIdx.x == 255) sums[blockIdx.x] = warp_base + incl;
+}
+// Single CTA: exclusive scan of the CTA totals (64-bit running sum), grand total.
+__global__ void __launch_bounds__(1024) k_scan_sums(unsigned int* sums, int m, unsigned long long* total) {
+  __shared__ unsigned long long carry;
+  __shared__ unsigned long long warp_tot[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int start = 0; start < m; start += 1024) {
+    const int i = start + threadIdx.x;
+    const unsigned long long v = i < m ? sums[i] : 0ull;
+    unsigned long long incl = v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned long long wb = 0;
+    for (int k = 0; k < warp; ++k) wb += warp_tot[k];
+    const unsigned long long excl = carry + wb + incl - v;
+    if (i < m) sums[i] = static_cast<unsigned int>(excl);
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(256) k_scan_add(unsigned int* out, const unsigned int* sums, int n) {
+  const int base = blockIdx.x * 1024 + threadIdx.x * 4;
+  const unsigned int s = sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (base + k < n) out[base + k] += s;
+}
+}  // namespace
+
+void ImageContext::exclusive_scan(const unsigned int* in, unsigned int* out, int n, unsigned long long* total) {
+  const int ctas = (n + 1023) / 1024;
+  unsigned long long* d_total = reinterpret_cast<unsigned long long*>(j_sums_ + ((ctas + 3) & ~1) + 2);
+  // keep the 64-bit total 8-byte aligned inside the scratch buffer
+  d_total = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(d_total) + 7) & ~static_cast<uintptr_t>(7));
+  note_launch("scan_local", s_, n);
+  k_scan_local<<<ctas, 256, 0, s_>>>(in, out, j_sums_, n);
+  note_launch_end("scan_local", s_);
+  note_launch("scan_sums", s_, ctas);
+  k_scan_sums<<<1, 1024, 0, s_>>>(j_sums_, ctas, d_total);
+  note_launch_end("scan_sums", s_);
+  note_launch("scan_add", s_, n);
+  k_scan_add<<<ctas, 256, 0, s_>>>(out, j_sums_, n);
+  note_launch_end("scan_add", s_);
+  d2h(total, d_total, sizeof(unsigned long long), s_);
+}
+#endif
+
+void ImageContext::jpeg_histograms(unsigned int* hist, bool* chroma_nonzero) {
+  const size_t priv = static_cast<size_t>(kHistCopies) * kHistStride;
+  dev_zero(j_hist_, sizeof(unsigned int) * (priv + kHistStride + 2), s_);
+  unsigned int* flag = j_hist_ + priv + kHistStride;
+  launch_1d(s_, JpegHistAcc{d_cand_, d_q_, t_.zigzag, j_hist_, flag, g_.nblocks}, 3 * g_.nblocks, "jpeg_hist_acc");
+  launch_1d(s_, JpegHistSum{j_hist_, j_hist_ + priv}, kHistStride, "jpeg_hist_sum");
+  std::vector<unsigned int> buf(kHistStride + 2);
+  d2h(buf.data(), j_hist_ + priv, sizeof(unsigned int) * (kHistStride + 2), s_);
+  memcpy(hist, buf.data(), sizeof(unsigned int) * kHistStride);
+  *chroma_nonzero = buf[kHistStride] != 0;
+}
+
+void ImageContext::jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint16_t* code, size_t* nbytes,
+                                    size_t* num_ff) {
+  h2d(j_depth_, depth, 6 * 256, s_);
+  h2d(j_code_, code, 6 * 256 * sizeof(uint16_t), s_);
+  JpegCodes codes{j_depth_, j_code_};
+  launch_1d(s_, JpegMcuBits{d_cand_, d_q_, t_.zigzag, codes, j_bits_, g_.nblocks, ncomp}, g_.nblocks, "jpeg_mcu_bits");
+  unsigned long long total_bits = 0;
+  exclusive_scan(j_bits_, j_offset_, g_.nblocks, &total_bits);
+  if (total_bits >= (1ull << 32)) throw std::runtime_error("jpeg scan exceeds 2^32 bits");
+  const size_t nwords = static_cast<size_t>((total_bits + 31) >> 5);
+  if (nwords + 1 > j_words_cap_) {
+    if (j_words_) dev_free(j_words_);
+    j_words_cap_ = nwords + nwords / 4 + 1024;
+    j_words_ = static_cast<unsigned int*>(dev_alloc(j_words_cap_ * sizeof(unsigned int)));
+  }
+  dev_zero(j_words_, (nwords + 1) * sizeof(unsigned int), s_);
+  launch_1d(s_, JpegEmit{d_cand_, d_q_, t_.zigzag, codes, j_offset_, j_words_, g_.nblocks, ncomp}, g_.nblocks,
+            "jpeg_emit");
+  unsigned int* counter = j_hist_ + static_cast<size_t>(kHistCopies + 1) * kHistStride + 1;
+  dev_zero(counter, sizeof(unsigned int), s_);
+  launch_1d(s_, JpegCountFF{j_words_, total_bits, counter}, static_cast<int>(nwords), "jpeg_count_ff");
+  unsigned int ff = 0;
+  d2h(&ff, counter, sizeof(unsigned int), s_);
+  j_nbytes_ = static_cast<size_t>((total_bits + 7) >> 3);
+  *nbytes = j_nbytes_;
+  *num_ff = ff;
+}
+
+void ImageContext::jpeg_fetch_scan(std::vector<uint8_t>* scan) {
+  const size_t nwords = (j_nbytes_ + 3) / 4;
+  std::vector<unsigned int> words(nwords);
+  if (nwords) d2h(words.data(), j_words_, nwords * sizeof(unsigned int), s_);
+  scan->resize(nwords * 4);
+  for (size_t i = 0; i < nwords; ++i) {
+    const unsigned int v = words[i];
+    (*scan)[4 * i + 0] = static_cast<uint8_t>(v >> 24);
+    (*scan)[4 * i + 1] = static_cast<uint8_t>(v >> 16);
+    (*scan)[4 * i + 2] = static_cast<uint8_t>(v >> 8);
+    (*scan)[4 * i + 3] = static_cast<uint8_t>(v);
+  }
+  scan->resize(j_nbytes_);
 }
 
 void ImageContext::debug_blur(const float* in, float* out, int id) {

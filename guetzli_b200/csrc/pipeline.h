@@ -66,6 +66,16 @@ class ImageContext {
   size_t order_smallest(int direction, const std::vector<int>& last_index, const std::vector<float>& max_err,
                         size_t k, std::vector<float>* val, std::vector<int>* block);
 
+  // a11 on the device.  Symbol histograms of the candidate (raw counts):
+  // hist[6][257] = dc0 dc1 dc2 ac0 ac1 ac2; *chroma_nonzero tells whether the
+  // saved JPEG has 3 components (g/output_image.cc:357).
+  void jpeg_histograms(unsigned int* hist, bool* chroma_nonzero);
+  // Entropy-codes the scan with the given canonical codes (depth/code [6][256]).
+  // Returns the number of scan bytes before 0xFF stuffing and the number of 0xFF
+  // bytes among them; the bytes stay on the device until jpeg_fetch_scan().
+  void jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint16_t* code, size_t* nbytes, size_t* num_ff);
+  void jpeg_fetch_scan(std::vector<uint8_t>* scan);  // nbytes raw (unstuffed, padded) bytes
+
   // test hooks: run single stages on caller-provided planes (packed [n][h][w]).
   void debug_blur(const float* in, float* out, int id);
   void debug_opsin(const float* rgb_lin, float* xyb);
@@ -134,6 +144,16 @@ class ImageContext {
   float* d_sel_val_;
   int* d_sel_block_;
   size_t sel_cap_;
+  unsigned int* j_hist_;      // [kHistCopies][6][257] + [6][257] + flag + ff counter
+  unsigned int* j_bits_;      // [nblocks] MCU bit lengths
+  unsigned int* j_offset_;    // [nblocks] exclusive scan
+  unsigned int* j_sums_;      // scan scratch
+  uint8_t* j_depth_;          // [6][256]
+  uint16_t* j_code_;          // [6][256]
+  unsigned int* j_words_;     // scan bits, big-endian 32-bit words
+  size_t j_words_cap_;
+  size_t j_nbytes_;
+  void exclusive_scan(const unsigned int* in, unsigned int* out, int n, unsigned long long* total);
   MaltaParams malta_[6];
   double asym_w0_, asym_w1_;
 };

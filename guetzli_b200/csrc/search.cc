@@ -163,11 +163,11 @@ class Search {
     const float target = params_.butteraugli_target;
     // the q=1 JPEG is the fallback output (g/processor.cc:826-846)
     img_.as_encoded = true;
-    std::string encoded = timed_write();
-    img_.as_encoded = false;
-    logf("Original Out[%7zd]", encoded.size());
+    const size_t encoded = encoded_size();
+    logf("Original Out[%7zd]", encoded);
     compare();
     maybe_output(encoded);
+    img_.as_encoded = false;
     int best_q[3][64];
     for (int c = 0; c < 3; ++c)
       for (int k = 0; k < 64; ++k) best_q[c][k] = 1;
@@ -200,9 +200,33 @@ class Search {
     }
   }
 
-  std::string timed_write() {
+  // a11 on the device: exact size of the candidate's JPEG; the bytes are fetched
+  // only when the candidate becomes the best output.
+  size_t encoded_size() {
     Clock::time_point t0 = Clock::now();
-    std::string s = write_jpeg(img_);
+    unsigned int hist[6][257];
+    bool chroma = false;
+    ctx_->jpeg_histograms(&hist[0][0], &chroma);
+    const int ncomp = img_.as_encoded ? 3 : (chroma ? 3 : 1);
+    SymbolHistogram dc_h[3], ac_h[3];
+    for (int c = 0; c < ncomp; ++c)
+      for (int i = 0; i < 256; ++i) {
+        dc_h[c].counts[i] = 2 * hist[c][i];
+        ac_h[c].counts[i] = 2 * hist[3 + c][i];
+      }
+    plan_ = plan_jpeg(img_, ncomp, dc_h, ac_h);
+    size_t nbytes = 0, num_ff = 0;
+    ctx_->jpeg_encode_scan(ncomp, &plan_.depth[0][0], &plan_.code[0][0], &nbytes, &num_ff);
+    scan_bytes_ = nbytes;
+    st_->ms_jpeg += ms_since(t0);
+    return plan_.prefix.size() + nbytes + num_ff + 2;
+  }
+
+  std::string fetch_encoded() {
+    Clock::time_point t0 = Clock::now();
+    std::vector<uint8_t> scan;
+    ctx_->jpeg_fetch_scan(&scan);
+    std::string s = assemble_jpeg(plan_, scan.data(), scan.size());
     st_->ms_jpeg += ms_since(t0);
     return s;
   }
@@ -219,11 +243,12 @@ class Search {
     return distance_ <= target_mul * params_.butteraugli_target;
   }
 
-  void maybe_output(const std::string& encoded) {
-    const double score = score_jpeg(distance_, static_cast<int>(encoded.size()), params_.butteraugli_target);
+  void maybe_output(size_t encoded_bytes) {
+    const double score = score_jpeg(distance_, static_cast<int>(encoded_bytes), params_.butteraugli_target);
     logf(" Score[%.4f]", score);
     if (score < best_score_ || best_score_ < 0) {
-      *best_ = encoded;
+      *best_ = fetch_encoded();
+      if (best_->size() != encoded_bytes) throw std::runtime_error("device JPEG size mismatch");
       best_score_ = score;
       logf(" (*)");
     }
@@ -247,15 +272,15 @@ class Search {
     QuantTrial data;
     memcpy(data.q, q, sizeof(data.q));
     set_global_quant(q);
-    std::string encoded = timed_write();
+    const size_t encoded = encoded_size();
     logf("Iter %2d: %s quantization matrix:\n", st_->iterations + 1, "f111111");
     log_quant(q);
     logf("Iter %2d: %s GQ[%5.2f] Out[%7zd]", st_->iterations + 1, "f111111", quant_heuristic_score(q),
-         encoded.size());
+         encoded);
     ++st_->iterations;
     compare();
     data.dist_ok = distance_ok(target_mul);
-    data.jpg_size = encoded.size();
+    data.jpg_size = encoded;
     maybe_output(encoded);
     return data;
   }
@@ -565,11 +590,11 @@ class Search {
         ++st_->iterations;
         if (direction > 0) ++st_->iterations_up; else ++st_->iterations_down;
         ctx_->scatter_coeffs(m.edit_index, m.edit_value);
-        std::string encoded = timed_write();
+        const size_t encoded = encoded_size();
         logf("Iter %2d: %s(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
              st_->iterations, "f111111", 7, direction > 0 ? "up" : "down", static_cast<int>(out.consumed),
-             order_size, out.changed_blocks, blocks_to_change, num_blocks, out.val_threshold, encoded.size(),
-             100.0 - (100.0 * out.est_jpg_size) / encoded.size());
+             order_size, out.changed_blocks, blocks_to_change, num_blocks, out.val_threshold, encoded,
+             100.0 - (100.0 * out.est_jpg_size) / encoded);
         compare();
         maybe_output(encoded);
         prev_size = out.est_jpg_size;
@@ -587,6 +612,8 @@ class Search {
   float distance_;
   CoeffImage img_;
   std::vector<int16_t> cand_;
+  JpegPlan plan_;
+  size_t scan_bytes_ = 0;
 };
 
 }  // namespace

@@ -150,6 +150,7 @@ Tables build_tables(int w, int h, Stream s, std::vector<void*>* owned, HostTable
   t.cb_g = upload(ht.cb_g, s, owned);
 
   t.idct = upload(std::vector<int>(kIdctBasis, kIdctBasis + 64), s, owned);
+  t.zigzag = upload(std::vector<int>(zigzag_to_natural(), zigzag_to_natural() + 64), s, owned);
 
   std::vector<float> csf(192), bias(192);
   for (int i = 0; i < 192; ++i) {

@@ -38,6 +38,7 @@ struct Tables {
   const int* cr_g;           // [256] :72
   const int* cb_g;           // [256] :107
   const int* idct;           // [64]  idct.cc:29
+  const int* zigzag;         // [64]  zig-zag scan position -> natural index
   const float* order_csf;    // [192] order.inc
   const float* order_bias;   // [192]
   const double* block_csf;   // [37]  butteraugli_comparator.cc:94
