@@ -163,6 +163,33 @@ void ac_symbols_of_block(const int16_t* dq, const int* q, int weight, SymbolHist
   if (run > 0) h->add(0, weight);
 }
 
+// Same symbols as ac_symbols_of_block, restricted to zig-zag positions (a, b] where a is
+// a nonzero coefficient (or 0 = the DC slot) and b the next position to stop after
+// (a nonzero coefficient, or 64 = run to the end incl. the end-of-block symbol).
+// The run counter restarts after every nonzero coefficient, so the symbols of a
+// range depend only on the coefficients inside it.
+void ac_symbols_of_range(const int16_t* dq, const int* q, int a, int b, int weight, SymbolHistogram* h) {
+  const int* zz = zigzag_to_natural();
+  int run = 0;
+  const int last = b < 64 ? b : 63;
+  for (int k = a + 1; k <= last; ++k) {
+    const int nat = zz[k];
+    const int16_t coeff = dq[nat];
+    if (coeff == 0) {
+      ++run;
+      continue;
+    }
+    while (run > 15) {
+      h->add(0xf0, weight);
+      run -= 16;
+    }
+    const int nbits = floor_log2_nz(abs(coeff / q[nat])) + 1;
+    h->add((run << 4) + nbits, weight);
+    run = 0;
+  }
+  if (b >= 64 && run > 0) h->add(0, weight);
+}
+
 void build_ac_histograms(const CoeffImage& img, SymbolHistogram* h3) {
   const int ncomp = num_output_components(img);
   for (int c = 0; c < ncomp; ++c)

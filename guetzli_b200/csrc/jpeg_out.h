@@ -58,6 +58,7 @@ size_t cluster_histograms(SymbolHistogram* h, size_t* num, int* index, uint8_t* 
 
 int num_output_components(const CoeffImage& img);                     // g/output_image.cc:357
 void ac_symbols_of_block(const int16_t* dq_block, const int* q, int weight, SymbolHistogram* h);  // g/processor.cc:471
+void ac_symbols_of_range(const int16_t* dq_block, const int* q, int a, int b, int weight, SymbolHistogram* h);
 void build_ac_histograms(const CoeffImage& img, SymbolHistogram* h3);  // g/jpeg_data_writer.cc:258
 size_t estimate_dc_bytes(const CoeffImage& img);                        // g/processor.cc:528
 size_t jpeg_header_bytes(const CoeffImage& img);                        // g/jpeg_data_writer.cc:269

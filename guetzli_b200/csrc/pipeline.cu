@@ -97,6 +97,9 @@ ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device, bool pr
   owned_.push_back(j_depth_);
   j_code_ = static_cast<uint16_t*>(dev_alloc(6 * 256 * sizeof(uint16_t)));
   owned_.push_back(j_code_);
+  d_edit_i_ = nullptr;
+  d_edit_v_ = nullptr;
+  edit_cap_ = 0;
   j_words_ = nullptr;
   j_words_cap_ = 0;
   j_nbytes_ = 0;
@@ -166,6 +169,8 @@ ImageContext::~ImageContext() {
   if (d_sel_val_) dev_free(d_sel_val_);
   if (d_sel_block_) dev_free(d_sel_block_);
   if (j_words_) dev_free(j_words_);
+  if (d_edit_i_) dev_free(d_edit_i_);
+  if (d_edit_v_) dev_free(d_edit_v_);
   for (size_t i = 0; i < owned_.size(); ++i) dev_free(owned_[i]);
   destroy_stream(s_);
 }
@@ -198,14 +203,18 @@ void ImageContext::apply_global_quant(const int q[192]) {
 void ImageContext::scatter_coeffs(const std::vector<int>& index, const std::vector<int16_t>& value) {
   const int n = static_cast<int>(index.size());
   if (n == 0) return;
-  int* d_i = static_cast<int*>(dev_alloc(n * sizeof(int)));
-  int16_t* d_v = static_cast<int16_t*>(dev_alloc(n * sizeof(int16_t)));
-  h2d(d_i, index.data(), n * sizeof(int), s_);
-  h2d(d_v, value.data(), n * sizeof(int16_t), s_);
-  launch_1d(s_, ScatterCoeffs{d_i, d_v, d_cand_}, n, "scatter_coeffs");
-  stream_sync(s_);
-  dev_free(d_i);
-  dev_free(d_v);
+  if (static_cast<size_t>(n) > edit_cap_) {
+    stream_sync(s_);
+    if (d_edit_i_) dev_free(d_edit_i_);
+    if (d_edit_v_) dev_free(d_edit_v_);
+    edit_cap_ = static_cast<size_t>(n) * 2 + 4096;
+    d_edit_i_ = static_cast<int*>(dev_alloc(edit_cap_ * sizeof(int)));
+    d_edit_v_ = static_cast<int16_t*>(dev_alloc(edit_cap_ * sizeof(int16_t)));
+  }
+  h2d(d_edit_i_, index.data(), n * sizeof(int), s_);
+  h2d(d_edit_v_, value.data(), n * sizeof(int16_t), s_);
+  launch_1d(s_, ScatterCoeffs{d_edit_i_, d_edit_v_, d_cand_}, n, "scatter_coeffs");
+  stream_sync(s_);  // the host vectors may be reused by the caller
 }
 
 void ImageContext::upload_candidate(const int16_t* coeffs) {

@@ -144,6 +144,9 @@ class ImageContext {
   float* d_sel_val_;
   int* d_sel_block_;
   size_t sel_cap_;
+  int* d_edit_i_;
+  int16_t* d_edit_v_;
+  size_t edit_cap_;
   unsigned int* j_hist_;      // [kHistCopies][6][257] + [6][257] + flag + ff counter
   unsigned int* j_bits_;      // [nblocks] MCU bit lengths
   unsigned int* j_offset_;    // [nblocks] exclusive scan

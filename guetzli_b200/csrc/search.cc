@@ -346,6 +346,8 @@ class Search {
     const size_t per = static_cast<size_t>(img_.nblocks) * 64;
     WalkOutcome out;
     out.est_jpg_size = prev_size;
+    const int* zz2nat = zigzag_to_natural();
+    const int* nat2zz = natural_to_zigzag();
     std::fill(m.block_changed.begin(), m.block_changed.end(), 0);
     m.edit_index.clear();
     m.edit_value.clear();
@@ -363,7 +365,14 @@ class Search {
       const int16_t* orig_block = &orig[c * per + static_cast<size_t>(block_ix) * 64];
       const int newval = direction > 0 ? 0 : quantize_coeff(orig_block[k], quant[k]);
       int16_t* block = &cand_[c * per + static_cast<size_t>(block_ix) * 64];
-      ac_symbols_of_block(block, quant, -1, &m.ac_h[c]);
+      // only the symbols between the neighbouring nonzero coefficients (in zig-zag
+      // order) can change: UpdateACHistogram(-1) / (+1) of the reference restricted
+      // to that range
+      const int zp = nat2zz[k];
+      int za = zp - 1, zb = zp + 1;
+      while (za > 0 && block[zz2nat[za]] == 0) --za;
+      while (zb < 64 && block[zz2nat[zb]] == 0) ++zb;
+      ac_symbols_of_range(block, quant, za, zb, -1, &m.ac_h[c]);
       bool precious = false;
       if (k == 1 || k == 8) {
         double sum_of_hf = 0;
@@ -380,7 +389,7 @@ class Search {
         m.edit_old.push_back(block[k]);
         block[k] = static_cast<int16_t>(newval);
       }
-      ac_symbols_of_block(block, quant, 1, &m.ac_h[c]);
+      ac_symbols_of_range(block, quant, za, zb, 1, &m.ac_h[c]);
       m.last_indexes[block_ix] += direction;
       if (!m.block_changed[block_ix]) {
         m.block_changed[block_ix] = 1;
@@ -406,6 +415,37 @@ class Search {
       }
     }
     return out;
+  }
+
+  // The walk's outcome depends on the order of equal keys only through the *sets*
+  // of entries applied before each evaluation point: the entropy-code refreshes at
+  // indices 10m (those that feed a test) and the stop tests at indices
+  // >= min_coeffs_to_change, the last of which is the stop index.  Entries carry just
+  // a block index, so permuting equal keys of one block changes nothing.  Hence the
+  // result equals the reference's for ANY sort of the keys unless a tie group with
+  // two different blocks straddles one of those boundaries.
+  static bool order_is_unambiguous(const std::vector<std::pair<int, float> >& order, int min_coeffs_to_change,
+                                   size_t stop) {
+    const size_t n = order.size();
+    auto straddles = [&](size_t e) -> bool {  // boundary between entries e and e+1
+      if (e + 1 >= n) return false;
+      if (order[e].second < order[e + 1].second) return false;
+      const float key = order[e].second;
+      size_t lo = e, hi = e + 1;
+      while (lo > 0 && !(order[lo - 1].second < key)) --lo;
+      while (hi + 1 < n && !(key < order[hi + 1].second)) ++hi;
+      for (size_t j = lo + 1; j <= hi; ++j)
+        if (order[j].first != order[lo].first) return true;
+      return false;
+    };
+    const long long first_test = min_coeffs_to_change;  // stop test evaluated at indices >= this
+    for (long long r = ((first_test - 9 + 9) / 10) * 10 - 10; r <= static_cast<long long>(stop); r += 10) {
+      if (r < 0 || r + 9 < first_test) continue;
+      if (straddles(static_cast<size_t>(r))) return false;
+    }
+    for (long long i = first_test < 0 ? 0 : first_test; i <= static_cast<long long>(stop); ++i)
+      if (straddles(static_cast<size_t>(i))) return false;
+    return true;
   }
 
   // Rolls the host state back to before walk() (used when the partial order turns
@@ -508,6 +548,7 @@ class Search {
             std::vector<int> blk;
             const size_t total = ctx_->order_smallest(direction, m.last_indexes, m.max_block_error, want, &val, &blk);
             if (total != order_size) throw std::runtime_error("order_smallest: entry count mismatch");
+            if (getenv("GB200_DEBUG_ORDER")) fprintf(stderr, "[order] size %zu want %zu got %zu\n", order_size, want, val.size());
             if (val.size() >= order_size) break;
             order.resize(val.size());
             for (size_t i = 0; i < val.size(); ++i) order[i] = std::make_pair(blk[i], val[i]);
@@ -521,22 +562,17 @@ class Search {
             const std::vector<uint8_t> saved_depths = m.ac_depths;
             out = walk(m, order, direction, min_coeffs_to_change, min_size_delta, prev_size);
             st_->ms_walk += ms_since(tw);
-            // usable only if the walk stopped strictly inside the fetched prefix and no
-            // two equal keys of different blocks occur up to (and including) the boundary
+            // usable only if the walk stopped strictly inside the fetched prefix and the
+            // result cannot depend on how std::sort orders equal keys of different blocks
             bool ok = out.stopped && out.consumed < order.size();
             if (ok) {
-              for (size_t i = 0; i < out.consumed; ++i) {
-                if (!(order[i].second < order[i + 1].second) && order[i].first != order[i + 1].first) {
-                  ok = false;
-                  break;
-                }
+              if (!order_is_unambiguous(order, min_coeffs_to_change, out.consumed - 1)) {
+                ++tie_fallbacks_;
+                unwalk(m, order, out, direction, saved_h, saved_hist_size, saved_depths);
+                break;  // ambiguous tie at an evaluation point: take the exact path
               }
-              if (ok) {
-                done = true;
-                break;
-              }
-              unwalk(m, order, out, direction, saved_h, saved_hist_size, saved_depths);
-              break;  // ambiguous tie: take the exact path
+              done = true;
+              break;
             }
             unwalk(m, order, out, direction, saved_h, saved_hist_size, saved_depths);
             want *= 8;
@@ -614,6 +650,7 @@ class Search {
   std::vector<int16_t> cand_;
   JpegPlan plan_;
   size_t scan_bytes_ = 0;
+  int tie_fallbacks_ = 0;
 };
 
 }  // namespace
