@@ -614,28 +614,104 @@ struct OrderKeyCommon {
   }
 };
 
-struct OrderKeyHist {
+// Device-resident state of the two-level radix select over the keys' sortable
+// 32-bit images: level 0 bins the upper 16 bits, level 1 the lower 16 bits of the
+// keys that fell into the level-0 threshold bin.
+struct OrderSelectState {
+  unsigned int want;       // rank wanted (number of smallest keys)
+  unsigned int hi_bin;     // level-0 threshold bin
+  unsigned int below_hi;   // entries in bins < hi_bin
+  unsigned int threshold;  // final: entries with sortable key <= threshold are kept
+  unsigned int kept;       // number of such entries
+  unsigned int total;      // all entries
+  unsigned int counter;    // compaction cursor
+};
+
+GB_HD void order_hist_add(unsigned int* hist, unsigned int bin) {
+#if defined(__CUDA_ARCH__)
+  // warp-aggregated: one atomic per distinct bin per warp (keys of one block are
+  // monotone, so neighbouring lanes mostly share a bin)
+  const unsigned int active = __activemask();
+  const unsigned int peers = __match_any_sync(active, bin);
+  const int leader = __ffs(peers) - 1;
+  if ((threadIdx.y * blockDim.x + threadIdx.x) % 32 == leader) atomicAdd(&hist[bin], __popc(peers));
+#else
+  hd_atomic_add(&hist[bin], 1u);
+#endif
+}
+
+struct OrderKeyHist {  // level 0 (level = 0) or level 1 (level = 1)
   OrderKeyCommon c;
   unsigned int* hist;  // [65536]
+  const OrderSelectState* st;
+  int level;
   GB_HD void operator()(int slot, int b) const {
     float v;
     if (!c.key(slot, b, &v)) return;
-    hd_atomic_add(&hist[hd_float_sortable(v) >> 16], 1u);
+    const unsigned int u = hd_float_sortable(v);
+    if (level == 0) {
+      order_hist_add(hist, u >> 16);
+    } else if ((u >> 16) == st->hi_bin) {
+      order_hist_add(hist, u & 0xffffu);
+    }
+  }
+};
+
+// One invocation (launch_1d over 1 element): scans the 65536-bin histogram for the
+// bin where the cumulative count reaches the wanted rank.
+struct OrderSelectBin {
+  const unsigned int* hist;
+  OrderSelectState* st;
+  int level;
+  GB_HD void operator()(int) const {
+    if (level == 0) {
+      unsigned int cum = 0, bin = 65535, below = 0;
+      unsigned int total = 0;
+      bool found = false;
+      for (unsigned int i = 0; i < 65536; ++i) {
+        const unsigned int h = hist[i];
+        if (!found && cum + h >= st->want) {
+          bin = i;
+          below = cum;
+          found = true;
+        }
+        cum += h;
+      }
+      total = cum;
+      if (!found) below = cum - hist[65535];
+      st->hi_bin = bin;
+      st->below_hi = below;
+      st->total = total;
+    } else {
+      const unsigned int want = st->want > st->below_hi ? st->want - st->below_hi : 0;
+      unsigned int cum = 0, bin = 65535;
+      bool found = false;
+      for (unsigned int i = 0; i < 65536; ++i) {
+        cum += hist[i];
+        if (!found && cum >= want) {
+          bin = i;
+          found = true;
+          break;
+        }
+      }
+      st->threshold = (st->hi_bin << 16) | bin;
+      st->kept = st->below_hi + cum;
+      st->counter = 0;
+    }
   }
 };
 
 struct OrderKeyCompact {
   OrderKeyCommon c;
-  unsigned int threshold_bin;
-  unsigned int* counter;
+  OrderSelectState* st;
   float* out_val;
   int* out_block;
   unsigned int cap;
   GB_HD void operator()(int slot, int b) const {
     float v;
     if (!c.key(slot, b, &v)) return;
-    if ((hd_float_sortable(v) >> 16) > threshold_bin) return;
-    const unsigned int at = hd_atomic_add(counter, 1u);
+    if (hd_float_sortable(v) > st->threshold) return;
+    const unsigned int at = hd_atomic_add(&st->counter, 1u);
     if (at < cap) {
       out_val[at] = v;
       out_block[at] = b;

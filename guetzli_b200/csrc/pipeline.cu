@@ -9,6 +9,9 @@
 
 #include "block_math.h"
 #include "jpeg_dev.h"
+#if !defined(GB200_HOSTSIM)
+#include "tiled_kernels.cuh"
+#endif
 
 namespace gb200 {
 
@@ -80,7 +83,7 @@ ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device, bool pr
   owned_.push_back(d_last_index_);
   d_max_err_ = static_cast<float*>(dev_alloc(sizeof(float) * g_.nblocks));
   owned_.push_back(d_max_err_);
-  d_hist_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * (65536 + 1)));
+  d_hist_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * (65536 + 16)));
   owned_.push_back(d_hist_);
   sel_cap_ = 0;
   d_sel_val_ = nullptr;
@@ -176,8 +179,12 @@ ImageContext::~ImageContext() {
 }
 
 void ImageContext::blur(const float* in, float* out, int nplanes, int id) {
+#if defined(GB200_HOSTSIM)
   launch_2d(s_, BlurX{in, tmp_, t_.blur[id], g_}, g_.w, g_.h * nplanes, "blur_x");
   launch_2d(s_, BlurY{tmp_, out, t_.blur[id], g_}, g_.w, g_.h * nplanes, "blur_y");
+#else
+  launch_blur_tiled(s_, in, tmp_, out, nplanes, t_.blur[id], g_);
+#endif
 }
 
 void ImageContext::opsin(const float* lin, float* xyb) {
@@ -233,6 +240,7 @@ float ImageContext::compare() {
   opsin(lin_, xyb_);
   separate(xyb_, ps1_);
   // S7 Malta: uhf[Y], uhf[X] with 9-tap lines; hf[Y], hf[X], mf[Y], mf[X] with 5-tap lines
+#if defined(GB200_HOSTSIM)
   static const int kMaltaPlane[6] = {kUhfY, kUhfX, kHfY, kHfX, kMfY, kMfX};
   static const int kMaltaAcc[6] = {1, 0, 1, 0, 1, 0};
   for (int i = 0; i < 6; ++i) {
@@ -248,6 +256,21 @@ float ImageContext::compare() {
     acc.g = g_;
     launch_2d(s_, acc, g_.w, g_.h, i < 2 ? "malta_acc_hf" : "malta_acc_lf");
   }
+#else
+  for (int ch = 0; ch < 2; ++ch) {  // 0 = X, 1 = Y
+    MaltaChannelArgs a;
+    const int planes[3] = {kUhfX + ch, kHfX + ch, kMfX + ch};
+    const int calls[3] = {ch == 1 ? 0 : 1, ch == 1 ? 2 : 3, ch == 1 ? 4 : 5};  // call order, tables.h
+    for (int k = 0; k < 3; ++k) {
+      a.lum0[k] = ps0_ + planes[k] * P;
+      a.lum1[k] = ps1_ + planes[k] * P;
+      a.mp[k] = malta_[calls[k]];
+    }
+    a.acc = ac_ + ch * P;
+    a.g = g_;
+    launch_malta_channel(s_, a);
+  }
+#endif
   // S8 + S9 on block_diff_ac[Y]
   launch_2d(s_, NoisePre{ps0_ + kHfY * P, ps1_ + kHfY * P, noise_, g_}, g_.w, g_.h, "noise_pre");
   blur(noise_, noise_ + P, 1, kBlurNoise);
@@ -343,7 +366,11 @@ size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_
                                     std::vector<int>* block) {
   h2d(d_last_index_, last_index.data(), sizeof(int) * g_.nblocks, s_);
   h2d(d_max_err_, max_err.data(), sizeof(float) * g_.nblocks, s_);
-  dev_zero(d_hist_, sizeof(unsigned int) * (65536 + 1), s_);
+  OrderSelectState init;
+  memset(&init, 0, sizeof(init));
+  init.want = static_cast<unsigned int>(k);
+  OrderSelectState* st = reinterpret_cast<OrderSelectState*>(d_hist_ + 65536);
+  h2d(st, &init, sizeof(init), s_);
   OrderKeyCommon c;
   c.err = z_err_;
   c.count = z_cnt_;
@@ -351,35 +378,40 @@ size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_
   c.max_err = d_max_err_;
   c.weight = weights_;
   c.direction = direction;
-  launch_2d(s_, OrderKeyHist{c, d_hist_}, 192, g_.nblocks, "order_key_hist");
-  std::vector<unsigned int> hist(65536);
-  d2h(hist.data(), d_hist_, sizeof(unsigned int) * 65536, s_);
-  size_t total = 0, below = 0;
-  for (int i = 0; i < 65536; ++i) total += hist[i];
-  unsigned int bin = 65535;
-  for (int i = 0; i < 65536; ++i) {
-    below += hist[i];
-    if (below >= k) {
-      bin = static_cast<unsigned int>(i);
-      break;
-    }
-  }
-  if (below > sel_cap_) {
+  // two-level radix select of the k-th smallest key, entirely on the device
+  dev_zero(d_hist_, sizeof(unsigned int) * 65536, s_);
+  launch_2d(s_, OrderKeyHist{c, d_hist_, st, 0}, 192, g_.nblocks, "order_key_hist");
+#if defined(GB200_HOSTSIM)
+  launch_1d(s_, OrderSelectBin{d_hist_, st, 0}, 1, "order_select_bin");
+#else
+  launch_order_select_bin(s_, d_hist_, st, 0);
+#endif
+  dev_zero(d_hist_, sizeof(unsigned int) * 65536, s_);
+  launch_2d(s_, OrderKeyHist{c, d_hist_, st, 1}, 192, g_.nblocks, "order_key_hist");
+#if defined(GB200_HOSTSIM)
+  launch_1d(s_, OrderSelectBin{d_hist_, st, 1}, 1, "order_select_bin");
+#else
+  launch_order_select_bin(s_, d_hist_, st, 1);
+#endif
+  OrderSelectState got;
+  d2h(&got, st, sizeof(got), s_);
+  const size_t kept = got.kept;
+  if (kept > sel_cap_) {
     if (d_sel_val_) dev_free(d_sel_val_);
     if (d_sel_block_) dev_free(d_sel_block_);
-    sel_cap_ = below + below / 2 + 1024;
+    sel_cap_ = kept + kept / 2 + 1024;
     d_sel_val_ = static_cast<float*>(dev_alloc(sel_cap_ * sizeof(float)));
     d_sel_block_ = static_cast<int*>(dev_alloc(sel_cap_ * sizeof(int)));
   }
-  launch_2d(s_, OrderKeyCompact{c, bin, d_hist_ + 65536, d_sel_val_, d_sel_block_, static_cast<unsigned int>(sel_cap_)},
-            192, g_.nblocks, "order_key_compact");
-  val->resize(below);
-  block->resize(below);
-  if (below) {
-    d2h(val->data(), d_sel_val_, below * sizeof(float), s_);
-    d2h(block->data(), d_sel_block_, below * sizeof(int), s_);
+  launch_2d(s_, OrderKeyCompact{c, st, d_sel_val_, d_sel_block_, static_cast<unsigned int>(sel_cap_)}, 192,
+            g_.nblocks, "order_key_compact");
+  val->resize(kept);
+  block->resize(kept);
+  if (kept) {
+    d2h(val->data(), d_sel_val_, kept * sizeof(float), s_);
+    d2h(block->data(), d_sel_block_, kept * sizeof(int), s_);
   }
-  return total;
+  return got.total;
 }
 
 // ---------------------------------------------------------------------------

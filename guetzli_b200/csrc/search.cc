@@ -541,7 +541,8 @@ class Search {
         // reference-ordered sort whenever the result could depend on how std::sort
         // places equal keys of different blocks, or the prefix runs out.
         if (direction < 0 && order_size > 16384) {
-          size_t want = std::max<size_t>(4096, 8 * last_consumed + 4 * static_cast<size_t>(min_coeffs_to_change) + 1024);
+          // the walk usually stops right after min_coeffs_to_change entries
+          size_t want = std::max<size_t>(last_consumed, static_cast<size_t>(min_coeffs_to_change)) * 5 / 4 + 512;
           while (!done && want < order_size / 2) {
             Clock::time_point t0 = Clock::now();
             std::vector<float> val;
@@ -575,7 +576,7 @@ class Search {
               break;
             }
             unwalk(m, order, out, direction, saved_h, saved_hist_size, saved_depths);
-            want *= 8;
+            want *= 4;
           }
         }
         if (!done) {
