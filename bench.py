@@ -42,16 +42,22 @@ WORKLOADS = {
 # Algorithmic bytes per launched element (pixel of one plane, or 8x8 block) of the
 # staged v1 kernels: compulsory reads + writes of that stage ("kernels").
 ALG_BYTES = {
-    "blur_x": 8, "blur_y": 8, "sub_planes": 12, "opsin_px": 36, "split_mf_hf": 44, "split_hf_uhf": 68,
+    "malta_channel": 28, "blur_x": 8, "blur_y": 8, "sub_planes": 12, "opsin_px": 36, "split_mf_hf": 44, "split_hf_uhf": 68,
     "malta_pre": 12, "malta_acc_hf": 8, "malta_acc_lf": 12, "noise_pre": 12, "noise_asym_acc": 20,
     "mask_diff_pre": 40, "combine_sqrt": 44, "diffmap_mix": 12, "render_blocks": 1152,
     "block_max": 260, "linearize_rgb": 15, "quantize_coeffs": 4, "fdct_blocks": 576,
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu
+# --set full captures (profiles/), bytes; None until captured.
+NCU_TRAFFIC = {}
+
+
 def make_image(spec, rank=0):
     from guetzli_b200 import synth
-    seed = spec["seed"] + rank
+    from guetzli_b200.distributed import image_seed
+    seed = image_seed(spec["seed"], rank)
     if spec["gen"] == "noise":
         return synth.noise(spec["h"], spec["w"], seed)
     return synth.gradnoise(spec["h"], spec["w"], seed)
@@ -103,34 +109,18 @@ class ClockSampler:
 
 
 def dist_setup(n_gpus):
-    """-> (rank, world, local_rank, dist or None)"""
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
-        return rank, world, local, dist
-    return 0, 1, 0, None
+    from guetzli_b200 import distributed as gdist
+    return gdist.setup("nccl")
 
 
 def barrier_sync(dist):
-    import torch
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
+    from guetzli_b200 import distributed as gdist
+    gdist.barrier(dist, cuda=True)
 
 
 def max_over_ranks(dist, seconds, local):
-    if dist is None:
-        return seconds
-    import torch
-    t = torch.tensor([seconds], dtype=torch.float64, device=f"cuda:{local}")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    from guetzli_b200 import distributed as gdist
+    return gdist.max_over_ranks(dist, seconds, device=f"cuda:{local}")
 
 
 def cpu_reference_seconds(spec, quality):
@@ -196,6 +186,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="noise1080p_q95", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=16,
+                    help="images per GPU per step, encoded concurrently (one host thread + CUDA stream each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -204,6 +196,7 @@ def main():
         run_reference(args, wl, args.workload)
         return
 
+    from concurrent.futures import ThreadPoolExecutor
     rank, world, local, dist = dist_setup(args.gpus)
     import torch
     import guetzli_b200 as gb
@@ -211,77 +204,92 @@ def main():
     if lib.gb200_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
     torch.cuda.set_device(local)
-    rgb = make_image(wl, rank)
-    h, w, _ = rgb.shape
+    M = args.batch
+    # weak scaling: rank r encodes images r*M .. r*M+M-1 of the generator, every step
+    images = [make_image(wl, rank * M + j) for j in range(M)]
+    h, w, _ = images[0].shape
     params = gb.Params(butteraugli_target=gb.butteraugli_score_for_quality(wl["quality"]))
     px = h * w
+    pool = ThreadPoolExecutor(M)
+    shas = [set() for _ in range(M)]
 
-    # warm-up (also the bit-exactness guard for the timed runs: every run of the
-    # same image must return the same bytes)
-    shas = set()
-    for _ in range(args.warmup):
-        ok, jpeg = gb.process(params, None, rgb, w, h, device=local)
+    def encode_host(j):  # reference-facing call: host buffer in, JPEG bytes out
+        st = gb.ProcessStats()
+        ok, jpeg = gb.process(params, st, images[j], w, h, device=local)
         assert ok
-        shas.add(hashlib.sha256(jpeg).hexdigest())
+        shas[j].add(hashlib.sha256(jpeg).hexdigest())
+        return st
 
-    # ---- value: image already resident in HBM when the timed region starts ----
-    images = [gb.DeviceImage(rgb, device=local, prepare=False) for _ in range(args.steps)]
-    lib.gb200_profile_reset()
-    lib.gb200_profile_enable(1)
-    sampler = ClockSampler(local)
-    barrier_sync(dist)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    launches = 0
-    stats_list = []
-    for img in images:
+    def encode_resident(args_):  # image already uploaded
+        j, img = args_
         st = gb.ProcessStats()
         ok, jpeg = img.process(params, st)
         assert ok
-        shas.add(hashlib.sha256(jpeg).hexdigest())
-        launches += st.device["gpu_launches"]
-        stats_list.append(st)
+        shas[j].add(hashlib.sha256(jpeg).hexdigest())
+        return st
+
+    for _ in range(args.warmup):
+        list(pool.map(encode_host, range(M)))
+
+    # ---- value: images already resident in HBM when the timed region starts ----
+    resident = [[gb.DeviceImage(images[j], device=local, prepare=False) for j in range(M)]
+                for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    barrier_sync(dist)
+    sampler.start()
+    n0, _, _ = gb.counters()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    stats_list = []
+    for step in range(args.steps):
+        stats_list = list(pool.map(encode_resident, list(enumerate(resident[step]))))
     ev1.record()
     barrier_sync(dist)
     clocks = sampler.stop()
+    n1, _, _ = gb.counters()
     dt = max_over_ranks(dist, ev0.elapsed_time(ev1) / 1e3, local)
-    lib.gb200_profile_enable(0)
-    for img in images:
-        img.close()
-    value = world * args.steps * px / dt / 1e6
-
-    # per-kernel CUDA-event times of the timed region
-    import ctypes as C
-    cap = 64
-    names = ((C.c_char * 48) * cap)()
-    kl = (C.c_long * cap)()
-    kms = (C.c_double * cap)()
-    kel = (C.c_double * cap)()
-    nk = lib.gb200_profile_get(names, kl, kms, kel, cap)
-    kernels = []
-    for i in range(min(nk, cap)):
-        kernels.append({"name": names[i].value.decode(), "launches": kl[i], "ms": kms[i], "elements": kel[i]})
-    kernels.sort(key=lambda k: -k["ms"])
-    gpu_ms = sum(k["ms"] for k in kernels)
+    launches = n1 - n0
+    for row in resident:
+        for img in row:
+            img.close()
+    value = world * args.steps * M * px / dt / 1e6
 
     # ---- e2e: same job through the reference-facing call with HOST buffers ----
     barrier_sync(dist)
+    _, a0, b0 = gb.counters()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    h2d = d2h = 0
     for _ in range(args.steps):
-        st = gb.ProcessStats()
-        ok, jpeg = gb.process(params, st, rgb, w, h, device=local)
-        assert ok
-        shas.add(hashlib.sha256(jpeg).hexdigest())
-        h2d, d2h = st.device["h2d_bytes"], st.device["d2h_bytes"]
+        list(pool.map(encode_host, range(M)))
     e1.record()
     barrier_sync(dist)
+    _, a1, b1 = gb.counters()
     dt_e2e = max_over_ranks(dist, e0.elapsed_time(e1) / 1e3, local)
-    e2e_value = world * args.steps * px / dt_e2e / 1e6
-    assert len(shas) == 1, "non-deterministic output"
+    e2e_value = world * args.steps * M * px / dt_e2e / 1e6
+    h2d, d2h = (a1 - a0) / args.steps, (b1 - b0) / args.steps
+    assert all(len(x) == 1 for x in shas), "non-deterministic output"
 
+    # ---- per-kernel CUDA-event times: one more image, alone on the GPU ----------
+    kernels, gpu_ms, prof_st = [], 0.0, None
+    if rank == 0:
+        import ctypes as C
+        lib.gb200_profile_reset()
+        lib.gb200_profile_enable(1)
+        img = gb.DeviceImage(images[0], device=local, prepare=False)
+        prof_st = encode_resident((0, img))
+        img.close()
+        lib.gb200_profile_enable(0)
+        cap = 64
+        names = ((C.c_char * 48) * cap)()
+        kl = (C.c_long * cap)()
+        kms = (C.c_double * cap)()
+        kel = (C.c_double * cap)()
+        nk = lib.gb200_profile_get(names, kl, kms, kel, cap)
+        for i in range(min(nk, cap)):
+            kernels.append({"name": names[i].value.decode(), "launches": kl[i], "ms": kms[i], "elements": kel[i]})
+        kernels.sort(key=lambda k: -k["ms"])
+        gpu_ms = sum(k["ms"] for k in kernels)
+    barrier_sync(dist)
     if rank != 0:
         return
 
@@ -291,35 +299,39 @@ def main():
     else:
         peak, peak_kind = 6650.0, "fallback (B200_PROFILING.md)"
     roofline = None
-    if kernels:
-        top = kernels[0]
-        bpe = ALG_BYTES.get(top["name"])
-        if bpe and top["ms"] > 0:
-            achieved = bpe * top["elements"] / (top["ms"] * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": top["name"], "achieved": achieved, "peak": peak,
-                        "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                        "peak_source": peak_kind, "avg_launch_us": top["ms"] / max(1, top["launches"]) * 1e3,
-                        "share_of_gpu_time": top["ms"] / gpu_ms if gpu_ms else None}
+    ranked = [k for k in kernels if k["name"] in ALG_BYTES and k["launches"] > 1]
+    if ranked:
+        top = ranked[0]
+        bpe = ALG_BYTES[top["name"]]
+        achieved = bpe * top["elements"] / (top["ms"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": top["name"], "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(top["name"]),
+                    "peak_source": peak_kind, "avg_launch_us": top["ms"] / max(1, top["launches"]) * 1e3,
+                    "share_of_gpu_time": top["ms"] / gpu_ms if gpu_ms else None,
+                    "alg_bytes_per_element": bpe,
+                    "measured_on": "one extra image encoded alone (single stream) after the timed region"}
     st = stats_list[-1]
     line = {
         "metric": "MPix/s (bit-exact JPEG, guetzli::Process)", "value": value, "unit": "MPix/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (+f64 sub-expressions), int16/int32", "data": "synthetic",
-        "config": {"workload": args.workload, "image": f"{wl['gen']}({h},{w},seed {wl['seed']}+rank)",
-                   "quality": wl["quality"], "input_sha256_rank0": hashlib.sha256(rgb.tobytes()).hexdigest(),
-                   "output_sha256_rank0": sorted(shas)[0], "iterations": st.counters["number of iterations"],
-                   "sharding": f"{world} independent images, one per GPU",
-                   "l2_policy": "per-iteration working set (>=40 float planes) exceeds L2 at this size"},
+        "config": {"workload": args.workload, "batch_per_gpu": M,
+                   "image": f"{wl['gen']}({h},{w},seed {wl['seed']}+rank*{M}+j), j<{M}",
+                   "quality": wl["quality"], "input_sha256_rank0_img0": hashlib.sha256(images[0].tobytes()).hexdigest(),
+                   "output_sha256_rank0_img0": sorted(shas[0])[0],
+                   "iterations_img_last": st.counters["number of iterations"],
+                   "sharding": f"{world} GPU(s) x {M} independent images per step, one host thread + stream each",
+                   "l2_policy": "working set of one step (>= 16 images x 45 float planes) exceeds L2"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "MPix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": dt_e2e / args.steps * 1e3},
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "host_breakdown_ms": {k: round(st.device[k], 1) for k in
-                              ("ms_total", "ms_compare", "ms_zeroing", "ms_jpeg", "ms_sort", "ms_walk")},
-        "gpu_kernel_ms_per_step": round(gpu_ms / args.steps, 2),
-        "top_kernels": [{"name": k["name"], "ms": round(k["ms"], 2), "launches": k["launches"]} for k in kernels[:8]],
+        "single_image_ms": {k: round(prof_st.device[k], 1) for k in
+                            ("ms_total", "ms_compare", "ms_zeroing", "ms_jpeg", "ms_sort", "ms_walk")},
+        "single_image_gpu_kernel_ms": round(gpu_ms, 2),
+        "top_kernels": [{"name": k["name"], "ms": round(k["ms"], 2), "launches": k["launches"]} for k in kernels[:10]],
     }
     if world == 1 and not args.no_cpu_baseline:
         import reflib

@@ -77,6 +77,7 @@ def load_library(path=None):
     lib.gb200_image_debug_opsin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gb200_image_debug_separate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gb200_write_jpeg.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, P(P(C.c_uint8)), P(C.c_size_t)]
+    lib.gb200_counters.argtypes = [P(C.c_long), P(C.c_longlong), P(C.c_longlong)]
     lib.gb200_profile_enable.argtypes = [C.c_int]
     lib.gb200_profile_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     _libs[path] = lib
@@ -159,6 +160,14 @@ def process(params, stats, rgb, w, h, device=0, lib=None):
         if "CUDA" in msg or "no CUDA device" in msg:
             raise RuntimeError(msg)
     return bool(ok), data
+
+
+def counters(lib=None):
+    """-> (kernel launches, h2d bytes, d2h bytes): process-wide running totals."""
+    lib = lib or load_library()
+    n, a, b = C.c_long(), C.c_longlong(), C.c_longlong()
+    lib.gb200_counters(C.byref(n), C.byref(a), C.byref(b))
+    return n.value, a.value, b.value
 
 
 def write_jpeg(coeffs, w, h, q, lib=None):

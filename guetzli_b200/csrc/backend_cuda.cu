@@ -86,8 +86,8 @@ struct Prof {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t> > pending;
   };
   std::map<std::string, Entry> by_name;
-  cudaEvent_t cur_start = nullptr;
 };
+thread_local cudaEvent_t t_cur_start = nullptr;
 Prof& prof() {
   static Prof p;
   return p;
@@ -117,7 +117,7 @@ void note_launch(const char* name, Stream s, double elements) {
     cudaEvent_t a;
     cudaEventCreate(&a);
     cudaEventRecord(a, s);
-    p.cur_start = a;
+    t_cur_start = a;
   }
 }
 
@@ -126,13 +126,13 @@ void note_launch_end(const char* name, Stream s) {
   if (err != cudaSuccess) cuda_fail(err, name, __FILE__, __LINE__);
   Prof& p = prof();
   std::lock_guard<std::mutex> lock(p.mu);
-  if (p.on && p.cur_start) {
+  if (p.on && t_cur_start) {
     cudaEvent_t b;
     cudaEventCreate(&b);
     cudaEventRecord(b, s);
     Prof::Entry& e = p.by_name[name];
-    e.pending.push_back(std::make_pair(p.cur_start, b));
-    p.cur_start = nullptr;
+    e.pending.push_back(std::make_pair(t_cur_start, b));
+    t_cur_start = nullptr;
     if (e.pending.size() > 256) drain(e);
   }
 }

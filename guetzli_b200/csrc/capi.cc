@@ -16,6 +16,8 @@
 
 namespace gb200 {
 long total_launches();
+long long h2d_bytes_total();
+long long d2h_bytes_total();
 void profiling_enable(bool on);
 std::vector<KernelStat> profiling_snapshot();
 void profiling_reset();
@@ -164,7 +166,7 @@ gb200_image* gb200_image_create2(const uint8_t* rgb, int w, int h, int device, i
 
 void gb200_image_destroy(gb200_image* img) {
   if (!img) return;
-  guarded([&]() { delete img->ctx; });
+  guarded([&]() { img->ctx->bind(); delete img->ctx; });
   delete img;
 }
 
@@ -172,22 +174,24 @@ int gb200_image_num_blocks(const gb200_image* img) { return img->ctx->geom().nbl
 
 int gb200_image_orig_coeffs(gb200_image* img, int16_t* out) {
   return guarded([&]() {
+    img->ctx->bind();
     const std::vector<int16_t>& c = img->ctx->orig_coeffs();
     memcpy(out, c.data(), c.size() * sizeof(int16_t));
   });
 }
 
 int gb200_image_apply_global_quant(gb200_image* img, const int* q) {
-  return guarded([&]() { img->ctx->apply_global_quant(q); });
+  return guarded([&]() { img->ctx->bind(); img->ctx->apply_global_quant(q); });
 }
 int gb200_image_upload_candidate(gb200_image* img, const int16_t* coeffs) {
-  return guarded([&]() { img->ctx->upload_candidate(coeffs); });
+  return guarded([&]() { img->ctx->bind(); img->ctx->upload_candidate(coeffs); });
 }
 int gb200_image_download_candidate(gb200_image* img, int16_t* coeffs) {
-  return guarded([&]() { img->ctx->download_candidate(coeffs); });
+  return guarded([&]() { img->ctx->bind(); img->ctx->download_candidate(coeffs); });
 }
 int gb200_image_scatter(gb200_image* img, const int* index, const int16_t* value, int n) {
   return guarded([&]() {
+    img->ctx->bind();
     img->ctx->scatter_coeffs(std::vector<int>(index, index + n), std::vector<int16_t>(value, value + n));
   });
 }
@@ -195,11 +199,11 @@ int gb200_image_compare(gb200_image* img, float* distance) {
   return guarded([&]() { *distance = img->ctx->compare(); });
 }
 int gb200_image_distmap(gb200_image* img, float* out) {
-  return guarded([&]() { img->ctx->download_distmap(out); });
+  return guarded([&]() { img->ctx->bind(); img->ctx->download_distmap(out); });
 }
 int gb200_image_block_weights(gb200_image* img, int direction, int radius, double target_distance,
                               int zero_distmap, float* out) {
-  return guarded([&]() { img->ctx->block_weights(direction, radius, target_distance, zero_distmap != 0, out); });
+  return guarded([&]() { img->ctx->bind(); img->ctx->block_weights(direction, radius, target_distance, zero_distmap != 0, out); });
 }
 int gb200_image_zeroing_orders(gb200_image* img, float block_error_limit, int lookahead, uint8_t* idx,
                                float* err, int* count) {
@@ -207,6 +211,7 @@ int gb200_image_zeroing_orders(gb200_image* img, float block_error_limit, int lo
     std::vector<uint8_t> vi;
     std::vector<float> ve;
     std::vector<int> vc;
+    img->ctx->bind();
     img->ctx->zeroing_orders(block_error_limit, lookahead, &vi, &ve, &vc);
     memcpy(idx, vi.data(), vi.size());
     memcpy(err, ve.data(), ve.size() * sizeof(float));
@@ -214,22 +219,22 @@ int gb200_image_zeroing_orders(gb200_image* img, float block_error_limit, int lo
   });
 }
 int gb200_image_debug_blur(gb200_image* img, const float* in, float* out, int blur_id) {
-  return guarded([&]() { img->ctx->debug_blur(in, out, blur_id); });
+  return guarded([&]() { img->ctx->bind(); img->ctx->debug_blur(in, out, blur_id); });
 }
 int gb200_image_debug_opsin(gb200_image* img, const float* rgb_linear, float* xyb) {
-  return guarded([&]() { img->ctx->debug_opsin(rgb_linear, xyb); });
+  return guarded([&]() { img->ctx->bind(); img->ctx->debug_opsin(rgb_linear, xyb); });
 }
 int gb200_image_debug_separate(gb200_image* img, const float* xyb, float* psycho10) {
-  return guarded([&]() { img->ctx->debug_separate(xyb, psycho10); });
+  return guarded([&]() { img->ctx->bind(); img->ctx->debug_separate(xyb, psycho10); });
 }
 int gb200_image_debug_render(gb200_image* img, float* linear_rgb) {
-  return guarded([&]() { img->ctx->debug_render(linear_rgb); });
+  return guarded([&]() { img->ctx->bind(); img->ctx->debug_render(linear_rgb); });
 }
 int gb200_image_debug_psycho0(gb200_image* img, float* psycho10) {
-  return guarded([&]() { img->ctx->debug_psycho0(psycho10); });
+  return guarded([&]() { img->ctx->bind(); img->ctx->debug_psycho0(psycho10); });
 }
 int gb200_image_debug_corner_mask(gb200_image* img, float* out) {
-  return guarded([&]() { img->ctx->debug_corner_mask(out); });
+  return guarded([&]() { img->ctx->bind(); img->ctx->debug_corner_mask(out); });
 }
 
 int gb200_write_jpeg(const int16_t* coeffs, int w, int h, const int* q, uint8_t** out, size_t* out_len) {
@@ -247,6 +252,12 @@ int gb200_write_jpeg(const int16_t* coeffs, int w, int h, const int* q, uint8_t*
     memcpy(*out, s.data(), s.size());
     *out_len = s.size();
   });
+}
+
+void gb200_counters(long* launches, long long* h2d_bytes, long long* d2h_bytes) {
+  if (launches) *launches = gb200::total_launches();
+  if (h2d_bytes) *h2d_bytes = gb200::h2d_bytes_total();
+  if (d2h_bytes) *d2h_bytes = gb200::d2h_bytes_total();
 }
 
 void gb200_profile_enable(int on) { gb200::profiling_enable(on != 0); }

@@ -132,7 +132,10 @@ ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device, bool pr
   if (prepare_now) prepare();
 }
 
+void ImageContext::bind() { select_device(device_); }
+
 void ImageContext::prepare() {
+  bind();
   if (prepared_) return;
   prepared_ = true;
   const size_t ncoef = static_cast<size_t>(3) * g_.nblocks * 64;

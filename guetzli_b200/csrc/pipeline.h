@@ -27,6 +27,8 @@ class ImageContext {
   // the one-time kernels (idempotent); split from the upload so that a caller can
   // time the job with the image already resident in HBM
   void prepare();
+  // makes this context's device current for the calling host thread
+  void bind();
   ~ImageContext();
 
   int width() const { return g_.w; }

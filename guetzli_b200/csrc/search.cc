@@ -355,6 +355,23 @@ class Search {
     int changed_coeffs = 0;
     const size_t n_order = order.size();
     for (size_t i = 0; i < n_order; ++i) {
+      // every entry touches a different block: hide the cache misses
+      if (i + 12 < n_order) {
+        const int pb = order[i + 12].first;
+        __builtin_prefetch(&m.last_indexes[pb]);
+        __builtin_prefetch(&m.offsets[pb]);
+        __builtin_prefetch(&m.block_changed[pb]);
+      }
+      if (i + 6 < n_order) {
+        const int pb = order[i + 6].first;
+        const int pli = m.last_indexes[pb] + std::min(direction, 0);
+        const uint8_t* pc = &m.cand_idx[m.offsets[pb]];
+        __builtin_prefetch(pc + (pli < 0 ? 0 : pli));
+        for (int c = 0; c < 3; ++c) {
+          __builtin_prefetch(&cand_[c * per + static_cast<size_t>(pb) * 64]);
+          __builtin_prefetch(&cand_[c * per + static_cast<size_t>(pb) * 64 + 32]);
+        }
+      }
       const int block_ix = order[i].first;
       const int last_idx = m.last_indexes[block_ix];
       const uint8_t* candidates = &m.cand_idx[m.offsets[block_ix]];
