@@ -329,9 +329,10 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roofline,
         "single_image_ms": {k: round(prof_st.device[k], 1) for k in
-                            ("ms_total", "ms_compare", "ms_zeroing", "ms_jpeg", "ms_sort", "ms_walk")},
+                            ("ms_total", "ms_compare", "ms_zeroing", "ms_jpeg", "ms_sort", "ms_walk",
+                             "order_partial", "order_exact")},
         "single_image_gpu_kernel_ms": round(gpu_ms, 2),
-        "top_kernels": [{"name": k["name"], "ms": round(k["ms"], 2), "launches": k["launches"]} for k in kernels[:10]],
+        "top_kernels": [{"name": k["name"], "ms": round(k["ms"], 2), "launches": k["launches"]} for k in kernels[:30]],
     }
     if world == 1 and not args.no_cpu_baseline:
         import reflib

@@ -28,7 +28,7 @@ class _CStats(C.Structure):
                 ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
                 ("ms_total", C.c_double), ("ms_device_setup", C.c_double), ("ms_compare", C.c_double),
                 ("ms_zeroing", C.c_double), ("ms_jpeg", C.c_double), ("ms_sort", C.c_double),
-                ("ms_walk", C.c_double)]
+                ("ms_walk", C.c_double), ("order_partial", C.c_int), ("order_exact", C.c_int)]
 
 
 _LOG_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)

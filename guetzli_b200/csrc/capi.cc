@@ -77,6 +77,8 @@ void fill_stats(const gb200::SearchStats& st, gb200_stats* stats) {
   stats->ms_jpeg = st.ms_jpeg;
   stats->ms_sort = st.ms_sort;
   stats->ms_walk = st.ms_walk;
+  stats->order_partial = st.order_partial;
+  stats->order_exact = st.order_exact;
 }
 }  // namespace
 

@@ -139,23 +139,34 @@ struct JpegMcuBits {  // 1D over nblocks
   }
 };
 
-// Bit sink writing MSB-first into big-endian 32-bit words with atomic OR (the
-// first and last word of an MCU are shared with its neighbours).
+// Bit sink writing MSB-first into big-endian 32-bit words.  Bits are gathered in a
+// 64-bit register and leave as whole words with one atomic OR each (the first and
+// last word of an MCU are shared with its neighbours; the bits that belong to the
+// neighbours are zero in our word, so OR-ing is safe).
 struct BitCursor {
   unsigned int* words;
-  unsigned long long pos;  // absolute bit position
-  GB_HD void put(int n, unsigned int value) {
-    // n <= 27 here (16-bit code, or 11-bit extra), may straddle two words
-    while (n > 0) {
-      const unsigned int w = static_cast<unsigned int>(pos >> 5);
-      const int used = static_cast<int>(pos & 31);
-      const int room = 32 - used;
-      const int take = n < room ? n : room;
-      const unsigned int chunk = (value >> (n - take)) & (take == 32 ? 0xffffffffu : ((1u << take) - 1u));
-      hd_atomic_or(&words[w], chunk << (room - take));
-      pos += take;
-      n -= take;
+  unsigned long long word;  // index of the next word to write
+  unsigned long long acc;   // pending bits, right-aligned
+  int nacc;                 // number of pending bits (< 32 between calls)
+  GB_HD void start(unsigned int* w, unsigned long long bit_pos) {
+    words = w;
+    word = bit_pos >> 5;
+    acc = 0;
+    nacc = static_cast<int>(bit_pos & 31);  // leading zero bits stand in for the neighbour's bits
+  }
+  GB_HD void put(int n, unsigned int value) {  // n <= 27
+    acc = (acc << n) | value;
+    nacc += n;
+    if (nacc >= 32) {
+      nacc -= 32;
+      hd_atomic_or(&words[word], static_cast<unsigned int>(acc >> nacc));
+      ++word;
+      acc &= (1ull << nacc) - 1ull;
     }
+  }
+  GB_HD void finish() {
+    if (nacc > 0) hd_atomic_or(&words[word], static_cast<unsigned int>(acc << (32 - nacc)));
+    nacc = 0;
   }
 };
 
@@ -183,7 +194,8 @@ struct JpegEmit {  // 1D over nblocks
     }
   };
   GB_HD void operator()(int b) const {
-    BitCursor cur{words, offset[b]};
+    BitCursor cur;
+    cur.start(words, offset[b]);
     for (int c = 0; c < ncomp; ++c) {
       const int16_t* blk = cand + (static_cast<size_t>(c) * nblocks + b) * 64;
       const int* qc = q + 64 * c;
@@ -193,6 +205,7 @@ struct JpegEmit {  // 1D over nblocks
       visit_block_symbols(blk, qc, prev, zigzag, v);
       cur = v.cur;
     }
+    cur.finish();
   }
 };
 

@@ -126,6 +126,15 @@ struct RenderBlocks {
   }
 };
 
+// The same for a list of blocks (only blocks whose coefficients changed since the
+// last render need new pixels: SetCoeffBlock's incremental update,
+// g/output_image.cc:123-145).
+struct RenderBlockList {
+  RenderBlocks r;
+  const int* list;
+  GB_HD void operator()(int i) const { r(list[i]); }
+};
+
 // ---------------------------------------------------------------------------
 // Separable blur (b/butteraugli.cc:184-233), split into an x pass and a y pass.
 // Both take a group of `n` contiguous planes (launched over w x n*h).
@@ -614,14 +623,17 @@ struct OrderKeyCommon {
   }
 };
 
-// Device-resident state of the two-level radix select over the keys' sortable
-// 32-bit images: level 0 bins the upper 16 bits, level 1 the lower 16 bits of the
-// keys that fell into the level-0 threshold bin.
+// Device-resident state of the key selection.  Keys are binned by the upper
+// kOrderBinBits bits of their order-preserving 32-bit image (sign, exponent and the
+// top mantissa bits: relative resolution 2^-9); every entry whose bin is <= the bin
+// in which the cumulative count reaches `want` is kept -- a superset of the `want`
+// smallest keys that is a prefix of the sorted order (all ties included).
+static const int kOrderBinBits = 18;
+static const int kOrderBins = 1 << kOrderBinBits;
+
 struct OrderSelectState {
   unsigned int want;       // rank wanted (number of smallest keys)
-  unsigned int hi_bin;     // level-0 threshold bin
-  unsigned int below_hi;   // entries in bins < hi_bin
-  unsigned int threshold;  // final: entries with sortable key <= threshold are kept
+  unsigned int threshold;  // entries with sortable key <= threshold are kept
   unsigned int kept;       // number of such entries
   unsigned int total;      // all entries
   unsigned int counter;    // compaction cursor
@@ -629,8 +641,7 @@ struct OrderSelectState {
 
 GB_HD void order_hist_add(unsigned int* hist, unsigned int bin) {
 #if defined(__CUDA_ARCH__)
-  // warp-aggregated: one atomic per distinct bin per warp (keys of one block are
-  // monotone, so neighbouring lanes mostly share a bin)
+  // warp-aggregated: one atomic per distinct bin per warp
   const unsigned int active = __activemask();
   const unsigned int peers = __match_any_sync(active, bin);
   const int leader = __ffs(peers) - 1;
@@ -640,64 +651,37 @@ GB_HD void order_hist_add(unsigned int* hist, unsigned int bin) {
 #endif
 }
 
-struct OrderKeyHist {  // level 0 (level = 0) or level 1 (level = 1)
+struct OrderKeyHist {
   OrderKeyCommon c;
-  unsigned int* hist;  // [65536]
-  const OrderSelectState* st;
-  int level;
+  unsigned int* hist;  // [kOrderBins]
   GB_HD void operator()(int slot, int b) const {
     float v;
     if (!c.key(slot, b, &v)) return;
-    const unsigned int u = hd_float_sortable(v);
-    if (level == 0) {
-      order_hist_add(hist, u >> 16);
-    } else if ((u >> 16) == st->hi_bin) {
-      order_hist_add(hist, u & 0xffffu);
-    }
+    order_hist_add(hist, hd_float_sortable(v) >> (32 - kOrderBinBits));
   }
 };
 
-// One invocation (launch_1d over 1 element): scans the 65536-bin histogram for the
-// bin where the cumulative count reaches the wanted rank.
+// One invocation (launch_1d over 1 element): scans the histogram for the bin where
+// the cumulative count reaches the wanted rank.
 struct OrderSelectBin {
   const unsigned int* hist;
   OrderSelectState* st;
-  int level;
   GB_HD void operator()(int) const {
-    if (level == 0) {
-      unsigned int cum = 0, bin = 65535, below = 0;
-      unsigned int total = 0;
-      bool found = false;
-      for (unsigned int i = 0; i < 65536; ++i) {
-        const unsigned int h = hist[i];
-        if (!found && cum + h >= st->want) {
-          bin = i;
-          below = cum;
-          found = true;
-        }
-        cum += h;
+    unsigned int cum = 0, bin = kOrderBins - 1, kept = 0;
+    bool found = false;
+    for (int i = 0; i < kOrderBins; ++i) {
+      cum += hist[i];
+      if (!found && cum >= st->want) {
+        bin = static_cast<unsigned int>(i);
+        kept = cum;
+        found = true;
       }
-      total = cum;
-      if (!found) below = cum - hist[65535];
-      st->hi_bin = bin;
-      st->below_hi = below;
-      st->total = total;
-    } else {
-      const unsigned int want = st->want > st->below_hi ? st->want - st->below_hi : 0;
-      unsigned int cum = 0, bin = 65535;
-      bool found = false;
-      for (unsigned int i = 0; i < 65536; ++i) {
-        cum += hist[i];
-        if (!found && cum >= want) {
-          bin = i;
-          found = true;
-          break;
-        }
-      }
-      st->threshold = (st->hi_bin << 16) | bin;
-      st->kept = st->below_hi + cum;
-      st->counter = 0;
     }
+    if (!found) kept = cum;
+    st->threshold = (bin << (32 - kOrderBinBits)) | ((1u << (32 - kOrderBinBits)) - 1u);
+    st->kept = kept;
+    st->total = cum;
+    st->counter = 0;
   }
 };
 

@@ -83,7 +83,7 @@ ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device, bool pr
   owned_.push_back(d_last_index_);
   d_max_err_ = static_cast<float*>(dev_alloc(sizeof(float) * g_.nblocks));
   owned_.push_back(d_max_err_);
-  d_hist_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * (65536 + 16)));
+  d_hist_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * (kOrderBins + 16)));
   owned_.push_back(d_hist_);
   sel_cap_ = 0;
   d_sel_val_ = nullptr;
@@ -127,6 +127,10 @@ ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device, bool pr
 
   metric_ = (w >= 32 && h >= 32);  // g/processor.cc:940: no Butteraugli below 32x32
   prepared_ = false;
+  render_all_ = true;
+  num_dirty_ = 0;
+  d_dirty_ = static_cast<int*>(dev_alloc(sizeof(int) * g_.nblocks));
+  owned_.push_back(d_dirty_);
   h2d(d_rgb_, rgb, static_cast<size_t>(3) * w * h, s_);
   stream_sync(s_);
   if (prepare_now) prepare();
@@ -186,7 +190,7 @@ void ImageContext::blur(const float* in, float* out, int nplanes, int id) {
   launch_2d(s_, BlurX{in, tmp_, t_.blur[id], g_}, g_.w, g_.h * nplanes, "blur_x");
   launch_2d(s_, BlurY{tmp_, out, t_.blur[id], g_}, g_.w, g_.h * nplanes, "blur_y");
 #else
-  launch_blur_tiled(s_, in, tmp_, out, nplanes, t_.blur[id], g_);
+  launch_blur_tiled(s_, in, tmp_, out, nplanes, t_.blur[id], ht_.blur_taps_n[id].data(), g_);
 #endif
 }
 
@@ -205,6 +209,7 @@ void ImageContext::separate(const float* xyb, float* ps) {
 }
 
 void ImageContext::apply_global_quant(const int q[192]) {
+  render_all_ = true;
   h2d(d_q_, q, 192 * sizeof(int), s_);
   launch_1d(s_, QuantizeCoeffs{d_orig_, d_cand_, d_q_, g_.nblocks}, 3 * g_.nblocks * 64,
             "quantize_coeffs");
@@ -224,10 +229,22 @@ void ImageContext::scatter_coeffs(const std::vector<int>& index, const std::vect
   h2d(d_edit_i_, index.data(), n * sizeof(int), s_);
   h2d(d_edit_v_, value.data(), n * sizeof(int16_t), s_);
   launch_1d(s_, ScatterCoeffs{d_edit_i_, d_edit_v_, d_cand_}, n, "scatter_coeffs");
+  // blocks to re-render at the next compare()
+  if (!render_all_) {
+    if (dirty_flag_.empty()) dirty_flag_.assign(g_.nblocks, 0);
+    for (int i = 0; i < n; ++i) {
+      const int b = (index[i] / 64) % g_.nblocks;
+      if (!dirty_flag_[b]) {
+        dirty_flag_[b] = 1;
+        dirty_list_.push_back(b);
+      }
+    }
+  }
   stream_sync(s_);  // the host vectors may be reused by the caller
 }
 
 void ImageContext::upload_candidate(const int16_t* coeffs) {
+  render_all_ = true;
   h2d(d_cand_, coeffs, static_cast<size_t>(3) * g_.nblocks * 64 * 2, s_);
   stream_sync(s_);
 }
@@ -238,8 +255,17 @@ void ImageContext::download_candidate(int16_t* coeffs) {
 
 float ImageContext::compare() {
   const size_t P = g_.plane;
-  // S0 render, S1 opsin, S2-S6 frequency split
-  launch_1d(s_, RenderBlocks{d_cand_, lin_, g_, t_}, g_.nblocks, "render_blocks");
+  // S0 render (only blocks edited since the last render), S1 opsin, S2-S6 frequency split
+  if (render_all_ || dirty_list_.size() > static_cast<size_t>(g_.nblocks) / 2) {
+    launch_1d(s_, RenderBlocks{d_cand_, lin_, g_, t_}, g_.nblocks, "render_blocks");
+  } else if (!dirty_list_.empty()) {
+    const int nd = static_cast<int>(dirty_list_.size());
+    h2d(d_dirty_, dirty_list_.data(), sizeof(int) * nd, s_);
+    launch_1d(s_, RenderBlockList{RenderBlocks{d_cand_, lin_, g_, t_}, d_dirty_}, nd, "render_blocks");
+  }
+  render_all_ = false;
+  for (size_t i = 0; i < dirty_list_.size(); ++i) dirty_flag_[dirty_list_[i]] = 0;
+  dirty_list_.clear();
   opsin(lin_, xyb_);
   separate(xyb_, ps1_);
   // S7 Malta: uhf[Y], uhf[X] with 9-tap lines; hf[Y], hf[X], mf[Y], mf[X] with 5-tap lines
@@ -372,7 +398,7 @@ size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_
   OrderSelectState init;
   memset(&init, 0, sizeof(init));
   init.want = static_cast<unsigned int>(k);
-  OrderSelectState* st = reinterpret_cast<OrderSelectState*>(d_hist_ + 65536);
+  OrderSelectState* st = reinterpret_cast<OrderSelectState*>(d_hist_ + kOrderBins);
   h2d(st, &init, sizeof(init), s_);
   OrderKeyCommon c;
   c.err = z_err_;
@@ -381,20 +407,13 @@ size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_
   c.max_err = d_max_err_;
   c.weight = weights_;
   c.direction = direction;
-  // two-level radix select of the k-th smallest key, entirely on the device
-  dev_zero(d_hist_, sizeof(unsigned int) * 65536, s_);
-  launch_2d(s_, OrderKeyHist{c, d_hist_, st, 0}, 192, g_.nblocks, "order_key_hist");
+  // bin the keys, find the bin of the k-th smallest, entirely on the device
+  dev_zero(d_hist_, sizeof(unsigned int) * kOrderBins, s_);
+  launch_2d(s_, OrderKeyHist{c, d_hist_}, 192, g_.nblocks, "order_key_hist");
 #if defined(GB200_HOSTSIM)
-  launch_1d(s_, OrderSelectBin{d_hist_, st, 0}, 1, "order_select_bin");
+  launch_1d(s_, OrderSelectBin{d_hist_, st}, 1, "order_select_bin");
 #else
-  launch_order_select_bin(s_, d_hist_, st, 0);
-#endif
-  dev_zero(d_hist_, sizeof(unsigned int) * 65536, s_);
-  launch_2d(s_, OrderKeyHist{c, d_hist_, st, 1}, 192, g_.nblocks, "order_key_hist");
-#if defined(GB200_HOSTSIM)
-  launch_1d(s_, OrderSelectBin{d_hist_, st, 1}, 1, "order_select_bin");
-#else
-  launch_order_select_bin(s_, d_hist_, st, 1);
+  launch_order_select_bin(s_, d_hist_, st);
 #endif
   OrderSelectState got;
   d2h(&got, st, sizeof(got), s_);
@@ -574,6 +593,7 @@ void ImageContext::debug_blur(const float* in, float* out, int id) {
 }
 
 void ImageContext::debug_opsin(const float* rgb_lin, float* xyb) {
+  render_all_ = true;
   upload_planes(rgb_lin, lin_, 3);
   opsin(lin_, xyb_);
   download_planes(xyb_, xyb, 3);

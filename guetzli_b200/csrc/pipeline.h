@@ -149,6 +149,11 @@ class ImageContext {
   int* d_edit_i_;
   int16_t* d_edit_v_;
   size_t edit_cap_;
+  bool render_all_;
+  int num_dirty_;
+  int* d_dirty_;
+  std::vector<char> dirty_flag_;
+  std::vector<int> dirty_list_;
   unsigned int* j_hist_;      // [kHistCopies][6][257] + [6][257] + flag + ff counter
   unsigned int* j_bits_;      // [nblocks] MCU bit lengths
   unsigned int* j_offset_;    // [nblocks] exclusive scan

@@ -332,6 +332,7 @@ class Search {
     size_t changed_blocks = 0;
     float val_threshold = 0.0f;
     int est_jpg_size = 0;
+    bool ambiguous = false;    // check_ties only: result depends on the order of equal keys
   };
 
   // The sequential selection walk (g/processor.cc:700-750) over `order`.
@@ -340,14 +341,67 @@ class Search {
   // codes (refreshed at every 10th entry) and the estimate are evaluated only in
   // the 10-entry windows that can reach the test, or that contain the last entry.
   // Same integers as the reference's eager loop.
-  WalkOutcome walk(Sfm& m, const std::vector<std::pair<int, float> >& order, int direction,
-                   int min_coeffs_to_change, double min_size_delta, int prev_size) {
+  // What consuming the next candidate of block_ix does (no side effects).
+  struct Edit {
+    int c, k, za, zb, newval;
+    bool store;  // false: "precious" coefficient kept (g/processor.cc:722-733)
+  };
+  Edit plan_edit(const Sfm& m, int block_ix, int direction) const {
     const std::vector<int16_t>& orig = ctx_->orig_coeffs();
+    const size_t per = static_cast<size_t>(img_.nblocks) * 64;
+    const int* zz2nat = zigzag_to_natural();
+    const int* nat2zz = natural_to_zigzag();
+    Edit e;
+    const int last_idx = m.last_indexes[block_ix];
+    const uint8_t* candidates = &m.cand_idx[m.offsets[block_ix]];
+    const int idx = candidates[last_idx + std::min(direction, 0)];
+    e.c = idx / 64;
+    e.k = idx % 64;
+    const int* quant = img_.q[e.c];
+    const int16_t* orig_block = &orig[e.c * per + static_cast<size_t>(block_ix) * 64];
+    e.newval = direction > 0 ? 0 : quantize_coeff(orig_block[e.k], quant[e.k]);
+    const int16_t* block = &cand_[e.c * per + static_cast<size_t>(block_ix) * 64];
+    // only the symbols between the neighbouring nonzero coefficients (in zig-zag
+    // order) can change
+    const int zp = nat2zz[e.k];
+    e.za = zp - 1;
+    e.zb = zp + 1;
+    while (e.za > 0 && block[zz2nat[e.za]] == 0) --e.za;
+    while (e.zb < 64 && block[zz2nat[e.zb]] == 0) ++e.zb;
+    bool precious = false;
+    if (e.k == 1 || e.k == 8) {
+      double sum_of_hf = 0;
+      for (int ii = 3; ii < 64; ++ii) {
+        if ((ii & 7) < 3 && ii < 3 * 8) continue;
+        sum_of_hf += std::abs(orig_block[ii]);
+      }
+      const int limit = sum_of_hf < 60 ? 4 : 8;
+      precious = std::abs(orig_block[e.k]) >= limit;
+    }
+    e.store = !precious || e.newval != 0;
+    return e;
+  }
+
+  // The sequential selection walk (g/processor.cc:700-750) over `order`.
+  // The walk only *reads* the size estimate in its stop test, and the stop test
+  // cannot fire before min_coeffs_to_change entries are consumed; so the entropy
+  // codes (refreshed at every 10th entry) and the estimate are evaluated only in
+  // the 10-entry windows that can reach the test, or that contain the last entry.
+  // Same integers as the reference's eager loop.
+  //
+  // check_ties: `order` is sorted by key but equal keys may be arranged differently
+  // from the reference's std::sort.  Entries carry only a block index, so that
+  // matters solely where two different blocks with equal keys straddle a point at
+  // which the walk looks at its state: an entropy-code refresh or a stop test.  At
+  // a stop test the alternative (the other block first) is evaluated as well; if
+  // both arrangements decide "continue" the states coincide again one entry later.
+  // Anything else sets out.ambiguous and the caller redoes the iteration with the
+  // complete reference-ordered sort.
+  WalkOutcome walk(Sfm& m, const std::vector<std::pair<int, float> >& order, int direction,
+                   int min_coeffs_to_change, double min_size_delta, int prev_size, bool check_ties) {
     const size_t per = static_cast<size_t>(img_.nblocks) * 64;
     WalkOutcome out;
     out.est_jpg_size = prev_size;
-    const int* zz2nat = zigzag_to_natural();
-    const int* nat2zz = natural_to_zigzag();
     std::fill(m.block_changed.begin(), m.block_changed.end(), 0);
     m.edit_index.clear();
     m.edit_value.clear();
@@ -373,40 +427,49 @@ class Search {
         }
       }
       const int block_ix = order[i].first;
-      const int last_idx = m.last_indexes[block_ix];
-      const uint8_t* candidates = &m.cand_idx[m.offsets[block_ix]];
-      const int idx = candidates[last_idx + std::min(direction, 0)];
-      const int c = idx / 64;
-      const int k = idx % 64;
-      const int* quant = img_.q[c];
-      const int16_t* orig_block = &orig[c * per + static_cast<size_t>(block_ix) * 64];
-      const int newval = direction > 0 ? 0 : quantize_coeff(orig_block[k], quant[k]);
-      int16_t* block = &cand_[c * per + static_cast<size_t>(block_ix) * 64];
-      // only the symbols between the neighbouring nonzero coefficients (in zig-zag
-      // order) can change: UpdateACHistogram(-1) / (+1) of the reference restricted
-      // to that range
-      const int zp = nat2zz[k];
-      int za = zp - 1, zb = zp + 1;
-      while (za > 0 && block[zz2nat[za]] == 0) --za;
-      while (zb < 64 && block[zz2nat[zb]] == 0) ++zb;
-      ac_symbols_of_range(block, quant, za, zb, -1, &m.ac_h[c]);
-      bool precious = false;
-      if (k == 1 || k == 8) {
-        double sum_of_hf = 0;
-        for (int ii = 3; ii < 64; ++ii) {
-          if ((ii & 7) < 3 && ii < 3 * 8) continue;
-          sum_of_hf += std::abs(orig_block[ii]);
+      const bool refresh_here =
+          (i % 10 == 0) && (static_cast<long long>(i) + 9 >= min_coeffs_to_change || n_order - 1 <= i + 9);
+      const bool can_test = changed_coeffs + 1 > min_coeffs_to_change;
+      const bool eval_here = can_test || i + 1 == n_order;
+      // two different blocks with equal keys across the boundary i | i+1 ?
+      bool straddle = false;
+      if (check_ties && (refresh_here || eval_here) && i + 1 < n_order &&
+          !(order[i].second < order[i + 1].second) && order[i + 1].first != block_ix) {
+        straddle = true;
+      }
+      int alt_est = 0;
+      bool have_alt = false;
+      if (straddle) {
+        // tractable case: a tie group of exactly two entries at a plain stop test
+        const bool pair_only = (i == 0 || order[i - 1].second < order[i].second) && i + 2 < n_order &&
+                               order[i + 1].second < order[i + 2].second;
+        if (!pair_only || refresh_here || !can_test) {
+          out.ambiguous = true;
+          return out;
         }
-        const int limit = sum_of_hf < 60 ? 4 : 8;
-        precious = std::abs(orig_block[k]) >= limit;
+        const int other = order[i + 1].first;
+        const Edit e2 = plan_edit(m, other, direction);
+        SymbolHistogram alt[3] = {m.ac_h[0], m.ac_h[1], m.ac_h[2]};
+        int16_t tmp[64];
+        memcpy(tmp, &cand_[e2.c * per + static_cast<size_t>(other) * 64], sizeof(tmp));
+        ac_symbols_of_range(tmp, img_.q[e2.c], e2.za, e2.zb, -1, &alt[e2.c]);
+        if (e2.store) tmp[e2.k] = static_cast<int16_t>(e2.newval);
+        ac_symbols_of_range(tmp, img_.q[e2.c], e2.za, e2.zb, 1, &alt[e2.c]);
+        alt_est = m.header_size + m.dc_size + m.ac_histogram_size +
+                  static_cast<int>(entropy_coded_bytes(alt, m.ac_depths.data()));
+        have_alt = true;
       }
-      if (!precious || newval != 0) {
-        m.edit_index.push_back(static_cast<int>(c * per + static_cast<size_t>(block_ix) * 64 + k));
-        m.edit_value.push_back(static_cast<int16_t>(newval));
-        m.edit_old.push_back(block[k]);
-        block[k] = static_cast<int16_t>(newval);
+      const Edit e = plan_edit(m, block_ix, direction);
+      const int* quant = img_.q[e.c];
+      int16_t* block = &cand_[e.c * per + static_cast<size_t>(block_ix) * 64];
+      ac_symbols_of_range(block, quant, e.za, e.zb, -1, &m.ac_h[e.c]);
+      if (e.store) {
+        m.edit_index.push_back(static_cast<int>(e.c * per + static_cast<size_t>(block_ix) * 64 + e.k));
+        m.edit_value.push_back(static_cast<int16_t>(e.newval));
+        m.edit_old.push_back(block[e.k]);
+        block[e.k] = static_cast<int16_t>(e.newval);
       }
-      ac_symbols_of_range(block, quant, za, zb, 1, &m.ac_h[c]);
+      ac_symbols_of_range(block, quant, e.za, e.zb, 1, &m.ac_h[e.c]);
       m.last_indexes[block_ix] += direction;
       if (!m.block_changed[block_ix]) {
         m.block_changed[block_ix] = 1;
@@ -415,54 +478,25 @@ class Search {
       out.val_threshold = order[i].second;
       ++changed_coeffs;
       out.consumed = i + 1;
-      if (i % 10 == 0) {
-        const bool window_can_test = static_cast<long long>(i) + 9 >= min_coeffs_to_change;
-        const bool window_has_last = n_order - 1 <= i + 9;
-        if (window_can_test || window_has_last)
-          m.ac_histogram_size = static_cast<int>(compute_entropy_codes(m.ac_h, m.ac_depths.data()));
-      }
-      const bool can_test = changed_coeffs > min_coeffs_to_change;
-      if (can_test || i + 1 == n_order) {
+      if (refresh_here) m.ac_histogram_size = static_cast<int>(compute_entropy_codes(m.ac_h, m.ac_depths.data()));
+      if (eval_here) {
         out.est_jpg_size = m.header_size + m.dc_size + m.ac_histogram_size +
                            static_cast<int>(entropy_coded_bytes(m.ac_h, m.ac_depths.data()));
-        if (can_test && std::abs(out.est_jpg_size - prev_size) > min_size_delta) {
+        const bool stop = can_test && std::abs(out.est_jpg_size - prev_size) > min_size_delta;
+        if (have_alt) {
+          const bool alt_stop = std::abs(alt_est - prev_size) > min_size_delta;
+          if (stop || alt_stop) {
+            out.ambiguous = true;
+            return out;
+          }
+        }
+        if (stop) {
           out.stopped = true;
           break;
         }
       }
     }
     return out;
-  }
-
-  // The walk's outcome depends on the order of equal keys only through the *sets*
-  // of entries applied before each evaluation point: the entropy-code refreshes at
-  // indices 10m (those that feed a test) and the stop tests at indices
-  // >= min_coeffs_to_change, the last of which is the stop index.  Entries carry just
-  // a block index, so permuting equal keys of one block changes nothing.  Hence the
-  // result equals the reference's for ANY sort of the keys unless a tie group with
-  // two different blocks straddles one of those boundaries.
-  static bool order_is_unambiguous(const std::vector<std::pair<int, float> >& order, int min_coeffs_to_change,
-                                   size_t stop) {
-    const size_t n = order.size();
-    auto straddles = [&](size_t e) -> bool {  // boundary between entries e and e+1
-      if (e + 1 >= n) return false;
-      if (order[e].second < order[e + 1].second) return false;
-      const float key = order[e].second;
-      size_t lo = e, hi = e + 1;
-      while (lo > 0 && !(order[lo - 1].second < key)) --lo;
-      while (hi + 1 < n && !(key < order[hi + 1].second)) ++hi;
-      for (size_t j = lo + 1; j <= hi; ++j)
-        if (order[j].first != order[lo].first) return true;
-      return false;
-    };
-    const long long first_test = min_coeffs_to_change;  // stop test evaluated at indices >= this
-    for (long long r = ((first_test - 9 + 9) / 10) * 10 - 10; r <= static_cast<long long>(stop); r += 10) {
-      if (r < 0 || r + 9 < first_test) continue;
-      if (straddles(static_cast<size_t>(r))) return false;
-    }
-    for (long long i = first_test < 0 ? 0 : first_test; i <= static_cast<long long>(stop); ++i)
-      if (straddles(static_cast<size_t>(i))) return false;
-    return true;
   }
 
   // Rolls the host state back to before walk() (used when the partial order turns
@@ -578,17 +612,16 @@ class Search {
             SymbolHistogram saved_h[3] = {m.ac_h[0], m.ac_h[1], m.ac_h[2]};
             const int saved_hist_size = m.ac_histogram_size;
             const std::vector<uint8_t> saved_depths = m.ac_depths;
-            out = walk(m, order, direction, min_coeffs_to_change, min_size_delta, prev_size);
+            out = walk(m, order, direction, min_coeffs_to_change, min_size_delta, prev_size, true);
             st_->ms_walk += ms_since(tw);
-            // usable only if the walk stopped strictly inside the fetched prefix and the
-            // result cannot depend on how std::sort orders equal keys of different blocks
-            bool ok = out.stopped && out.consumed < order.size();
-            if (ok) {
-              if (!order_is_unambiguous(order, min_coeffs_to_change, out.consumed - 1)) {
-                ++tie_fallbacks_;
-                unwalk(m, order, out, direction, saved_h, saved_hist_size, saved_depths);
-                break;  // ambiguous tie at an evaluation point: take the exact path
-              }
+            if (out.ambiguous) {
+              ++tie_fallbacks_;
+              unwalk(m, order, out, direction, saved_h, saved_hist_size, saved_depths);
+              break;  // take the exact path
+            }
+            // usable only if the walk stopped strictly inside the fetched prefix
+            if (out.stopped && out.consumed < order.size()) {
+              ++st_->order_partial;
               done = true;
               break;
             }
@@ -597,6 +630,7 @@ class Search {
           }
         }
         if (!done) {
+          ++st_->order_exact;
           // complete order, built and sorted exactly like the reference (:636-678)
           Clock::time_point t0 = Clock::now();
           order.clear();
@@ -631,7 +665,7 @@ class Search {
             min_coeffs_to_change = std::max<int>(min_coeffs_to_change, it - order.begin());
           }
           Clock::time_point tw = Clock::now();
-          out = walk(m, order, direction, min_coeffs_to_change, min_size_delta, prev_size);
+          out = walk(m, order, direction, min_coeffs_to_change, min_size_delta, prev_size, false);
           st_->ms_walk += ms_since(tw);
         }
         first_up_iter = false;

@@ -32,6 +32,7 @@ struct SearchStats {
          ms_walk = 0;
   int compares = 0;
   long long h2d_bytes = 0, d2h_bytes = 0;
+  int order_partial = 0, order_exact = 0;
 };
 
 class ImageContext;

@@ -190,6 +190,7 @@ Tables build_tables(int w, int h, Stream s, std::vector<void*>* owned, HostTable
     const float scale_no_border = 1.0f / weight_no_border;
     std::vector<float> taps_n = taps;
     for (int j = 0; j < len; ++j) taps_n[j] *= scale_no_border;
+    ht.blur_taps_n[id] = taps_n;
     std::vector<float> sx(w, 0.0f), sy(h, 0.0f);
     for (int p = 0; p < w; ++p)
       if (p < r || p + r >= w) sx[p] = border_scale(taps, weight_no_border, br, p, w);

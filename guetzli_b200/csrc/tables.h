@@ -69,6 +69,7 @@ struct HostTables {
   std::vector<int> cr_r, cb_b, cr_g, cb_g;
   std::vector<double> mask_lut;  // 4*512
   std::vector<float> blur_taps[kNumBlurs];
+  std::vector<float> blur_taps_n[kNumBlurs];  // interior kernel: taps * (1/sum)
 };
 
 void blur_spec(int id, float* sigma, float* border_ratio);

@@ -6,6 +6,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <stdexcept>
+
 #include "ba_math.h"
 #include "kernels.h"
 #include "malta_unrolled.inc"
@@ -89,15 +91,15 @@ inline void launch_malta_channel(Stream s, const MaltaChannelArgs& a) {
 }
 
 // ---------------------------------------------------------------------------
-// Separable blur (b/butteraugli.cc:184-233) with register blocking.
-//
-// x pass: a CTA stages [8 rows][128 + 2r] input samples in shared memory; each
-// thread produces 4 adjacent outputs of one row, streaming the 2r+4 samples it
-// needs once and adding every product to the right accumulator in ascending tap
-// order (per output the sequence of float additions is the reference's).
-// Border outputs (x < r or x + r >= w) take the raw-tap / scale path.
+// Separable blur (b/butteraugli.cc:184-233), register-blocked, radius known at
+// compile time.  The interior taps travel as a kernel argument, i.e. they sit in
+// the constant bank and every multiply takes its tap as an immediate constant
+// operand (fully unrolled loops): per multiply-add the SM issues one FMUL and one
+// FADD (no FMA: bit-exactness) and per input sample one load.
+// For every output the products are added in ascending tap order, exactly the
+// reference's sequence.  Border outputs (p < r or p + r >= n) take the raw-tap /
+// per-position-scale path of ConvolveBorderColumn.
 #define GB_BLUR_MAX_R 24
-#define GB_BLURX_TW 128
 
 struct BlurArgs {
   const float* in;
@@ -107,23 +109,26 @@ struct BlurArgs {
   int rows;  // total rows = nplanes * h
 };
 
-__global__ void __launch_bounds__(256) k_blur_x(BlurArgs a) {
-  __shared__ float tile[8][GB_BLURX_TW + 2 * GB_BLUR_MAX_R];
-  __shared__ float taps_n[2 * GB_BLUR_MAX_R + 1];
-  __shared__ float taps[2 * GB_BLUR_MAX_R + 1];
-  const int r = a.tab.r;
-  const int len = 2 * r + 1;
+template <int R>
+struct BlurTaps {
+  float n[2 * R + 1];  // taps * (1/sum)
+};
+
+// x pass: a CTA stages [8 rows][256 + 2R] samples in shared memory; a thread makes
+// 8 adjacent outputs of one row.
+#define GB_BLURX_TW 256
+#define GB_BLURX_PT 8
+template <int R>
+__global__ void __launch_bounds__(256) k_blur_x(BlurArgs a, BlurTaps<R> taps) {
+  constexpr int LEN = 2 * R + 1;
+  constexpr int SPAN = GB_BLURX_TW + 2 * R;
+  __shared__ float tile[8][SPAN + 1];
   const int tid = threadIdx.y * 32 + threadIdx.x;
-  if (tid < len) {
-    taps_n[tid] = a.tab.taps_n[tid];
-    taps[tid] = a.tab.taps[tid];
-  }
   const int x0 = blockIdx.x * GB_BLURX_TW;
   const int row0 = blockIdx.y * 8;
-  const int span = GB_BLURX_TW + 2 * r;
-  for (int i = tid; i < 8 * span; i += 256) {
-    const int ry = i / span, sx = i - ry * span;
-    const int x = x0 - r + sx, row = row0 + ry;
+  for (int i = tid; i < 8 * SPAN; i += 256) {
+    const int ry = i / SPAN, sx = i - ry * SPAN;
+    const int x = x0 - R + sx, row = row0 + ry;
     float v = 0.0f;
     if (row < a.rows && x >= 0 && x < a.g.w) v = a.in[static_cast<size_t>(row) * a.g.pitch + x];
     tile[ry][sx] = v;
@@ -132,58 +137,36 @@ __global__ void __launch_bounds__(256) k_blur_x(BlurArgs a) {
   const int ry = threadIdx.y;
   const int row = row0 + ry;
   if (row >= a.rows) return;
-  const int xb = x0 + threadIdx.x * 4;  // first of 4 outputs
-  if (xb >= a.g.w) return;
+  const int w = a.g.w;
   const float* srow = tile[ry];
   float* orow = a.out + static_cast<size_t>(row) * a.g.pitch;
-  const int w = a.g.w;
-  const bool interior = (xb >= r) && (xb + 3 + r < w);
-  if (interior) {
-    float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
-    const int base = threadIdx.x * 4;  // tile index of tap 0 of output 0
-    // sample t (0 .. 2r+3) contributes tap (t - o) to output o
-    for (int t = 0; t < len + 3; ++t) {
-      const float v = srow[base + t];
-      if (t < len) acc0 += v * taps_n[t];
-      if (t >= 1 && t - 1 < len) acc1 += v * taps_n[t - 1];
-      if (t >= 2 && t - 2 < len) acc2 += v * taps_n[t - 2];
-      if (t >= 3) acc3 += v * taps_n[t - 3];
+  // outputs xb + lane-strided: thread handles x = x0 + threadIdx.x + 32*o (o < 8) so that
+  // shared-memory reads of a warp are consecutive (no bank conflicts)
+#pragma unroll
+  for (int o = 0; o < GB_BLURX_PT; ++o) {
+    const int xl = threadIdx.x + 32 * o;  // position inside the tile
+    const int x = x0 + xl;
+    if (x >= w) continue;
+    float sum = 0.0f;
+    if (x >= R && x + R < w) {
+#pragma unroll
+      for (int j = 0; j < LEN; ++j) sum += srow[xl + j] * taps.n[j];
+    } else {
+      const int lo = x < R ? 0 : x - R;
+      const int hi = (x + R < w - 1) ? x + R : w - 1;
+      for (int j = lo; j <= hi; ++j) sum += srow[j - x0 + R] * a.tab.taps[j - x + R];
+      sum = sum * a.tab.scale_x[x];
     }
-    orow[xb] = acc0;
-    orow[xb + 1] = acc1;
-    orow[xb + 2] = acc2;
-    orow[xb + 3] = acc3;
-  } else {
-    for (int o = 0; o < 4; ++o) {
-      const int x = xb + o;
-      if (x >= w) break;
-      float sum = 0.0f;
-      if (x < r || x + r >= w) {
-        const int lo = x < r ? 0 : x - r;
-        const int hi = (x + r < w - 1) ? x + r : w - 1;
-        for (int j = lo; j <= hi; ++j) sum += srow[j - x0 + r] * taps[j - x + r];
-        sum = sum * a.tab.scale_x[x];
-      } else {
-        for (int j = 0; j < len; ++j) sum += srow[x - x0 + j] * taps_n[j];
-      }
-      orow[x] = sum;
-    }
+    orow[x] = sum;
   }
 }
 
-// y pass: each thread owns one column x and produces 8 consecutive rows, streaming
-// the 8 + 2r input rows once (coalesced across the warp) into 8 accumulators.
+// y pass: a thread owns one column and makes 8 consecutive rows, streaming the
+// 8 + 2R input rows once (coalesced across the warp) into 8 accumulators.
 #define GB_BLURY_R 8
-__global__ void __launch_bounds__(128) k_blur_y(BlurArgs a) {
-  __shared__ float taps_n[2 * GB_BLUR_MAX_R + 1];
-  __shared__ float taps[2 * GB_BLUR_MAX_R + 1];
-  const int r = a.tab.r;
-  const int len = 2 * r + 1;
-  if (threadIdx.x < len) {
-    taps_n[threadIdx.x] = a.tab.taps_n[threadIdx.x];
-    taps[threadIdx.x] = a.tab.taps[threadIdx.x];
-  }
-  __syncthreads();
+template <int R>
+__global__ void __launch_bounds__(128) k_blur_y(BlurArgs a, BlurTaps<R> taps) {
+  constexpr int LEN = 2 * R + 1;
   const int x = blockIdx.x * 128 + threadIdx.x;
   if (x >= a.g.w) return;
   const int h = a.g.h;
@@ -193,18 +176,19 @@ __global__ void __launch_bounds__(128) k_blur_y(BlurArgs a) {
   const float* col = a.in + static_cast<size_t>(pl) * a.g.plane + x;
   float* ocol = a.out + static_cast<size_t>(pl) * a.g.plane + x;
   const size_t pitch = a.g.pitch;
-  const bool interior = (yb >= r) && (yb + GB_BLURY_R - 1 + r < h);
+  const bool interior = (yb >= R) && (yb + GB_BLURY_R - 1 + R < h);
   if (interior) {
     float acc[GB_BLURY_R];
 #pragma unroll
     for (int o = 0; o < GB_BLURY_R; ++o) acc[o] = 0.0f;
-    const int ystart = yb - r;
-    for (int t = 0; t < len + GB_BLURY_R - 1; ++t) {
-      const float v = col[static_cast<size_t>(ystart + t) * pitch];
+    const float* p = col + static_cast<size_t>(yb - R) * pitch;
+#pragma unroll
+    for (int t = 0; t < LEN + GB_BLURY_R - 1; ++t) {
+      const float v = p[static_cast<size_t>(t) * pitch];
 #pragma unroll
       for (int o = 0; o < GB_BLURY_R; ++o) {
-        const int j = t - o;
-        if (j >= 0 && j < len) acc[o] += v * taps_n[j];
+        const int j = t - o;  // compile-time after unrolling
+        if (j >= 0 && j < LEN) acc[o] += v * taps.n[j];
       }
     }
 #pragma unroll
@@ -214,44 +198,64 @@ __global__ void __launch_bounds__(128) k_blur_y(BlurArgs a) {
       const int y = yb + o;
       if (y >= h) break;
       float sum = 0.0f;
-      if (y < r || y + r >= h) {
-        const int lo = y < r ? 0 : y - r;
-        const int hi = (y + r < h - 1) ? y + r : h - 1;
-        for (int j = lo; j <= hi; ++j) sum += col[static_cast<size_t>(j) * pitch] * taps[j - y + r];
+      if (y < R || y + R >= h) {
+        const int lo = y < R ? 0 : y - R;
+        const int hi = (y + R < h - 1) ? y + R : h - 1;
+        for (int j = lo; j <= hi; ++j) sum += col[static_cast<size_t>(j) * pitch] * a.tab.taps[j - y + R];
         sum = sum * a.tab.scale_y[y];
       } else {
-        for (int j = 0; j < len; ++j) sum += col[static_cast<size_t>(y - r + j) * pitch] * taps_n[j];
+        for (int j = 0; j < LEN; ++j) sum += col[static_cast<size_t>(y - R + j) * pitch] * a.tab.taps_n[j];
       }
       ocol[static_cast<size_t>(y) * pitch] = sum;
     }
   }
 }
 
-inline void launch_blur_tiled(Stream s, const float* in, float* tmp, float* out, int nplanes, const BlurTab& tab,
-                              const Geom& g) {
+template <int R>
+inline void launch_blur_r(Stream s, const float* in, float* tmp, float* out, int nplanes, const BlurTab& tab,
+                          const float* host_taps_n, const Geom& g) {
+  BlurTaps<R> taps;
+  for (int j = 0; j < 2 * R + 1; ++j) taps.n[j] = host_taps_n[j];
   BlurArgs ax{in, tmp, tab, g, nplanes * g.h};
   dim3 bx(32, 8), gx((g.w + GB_BLURX_TW - 1) / GB_BLURX_TW, (nplanes * g.h + 7) / 8);
   note_launch("blur_x", s, static_cast<double>(g.w) * g.h * nplanes);
-  k_blur_x<<<gx, bx, 0, s>>>(ax);
+  k_blur_x<R><<<gx, bx, 0, s>>>(ax, taps);
   note_launch_end("blur_x", s);
   BlurArgs ay{tmp, out, tab, g, nplanes * g.h};
   const int strips = (g.h + GB_BLURY_R - 1) / GB_BLURY_R;
   dim3 gy((g.w + 127) / 128, strips * nplanes);
   note_launch("blur_y", s, static_cast<double>(g.w) * g.h * nplanes);
-  k_blur_y<<<gy, 128, 0, s>>>(ay);
+  k_blur_y<R><<<gy, 128, 0, s>>>(ay, taps);
   note_launch_end("blur_y", s);
 }
 
+// host_taps_n: the interior kernel (taps * 1/sum) as built by tables.cc.
+inline void launch_blur_tiled(Stream s, const float* in, float* tmp, float* out, int nplanes, const BlurTab& tab,
+                              const float* host_taps_n, const Geom& g) {
+  switch (tab.r) {
+    case 2: launch_blur_r<2>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
+    case 3: launch_blur_r<3>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
+    case 4: launch_blur_r<4>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
+    case 5: launch_blur_r<5>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
+    case 8: launch_blur_r<8>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
+    case 16: launch_blur_r<16>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
+    case 20: launch_blur_r<20>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
+    case 23: launch_blur_r<23>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
+    case 24: launch_blur_r<24>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
+    default: throw std::runtime_error("blur radius without a compiled kernel");
+  }
+}
+
 // ---------------------------------------------------------------------------
-// Parallel form of OrderSelectBin (kernels.h): one CTA of 1024 threads, 64 bins
-// per thread, block-wide scan of the partial sums, then the owning thread walks its
-// 64 bins.  Same result as the serial functor.
-__global__ void __launch_bounds__(1024) k_order_select_bin(const unsigned int* hist, OrderSelectState* st, int level) {
-  __shared__ unsigned int part[1024];
+// Parallel form of OrderSelectBin (kernels.h): one CTA of 1024 threads, each owning
+// kOrderBins/1024 consecutive bins; block-wide scan of the per-thread sums, then the
+// owning thread walks its bins.  Same result as the serial functor.
+__global__ void __launch_bounds__(1024) k_order_select_bin(const unsigned int* hist, OrderSelectState* st) {
+  constexpr int PER = kOrderBins / 1024;
   __shared__ unsigned int warp_tot[32];
   const int t = threadIdx.x;
   unsigned int local = 0;
-  for (int i = 0; i < 64; ++i) local += hist[t * 64 + i];
+  for (int i = 0; i < PER; ++i) local += hist[t * PER + i];
   unsigned int incl = local;
   const int lane = t & 31, warp = t >> 5;
 #pragma unroll
@@ -261,91 +265,43 @@ __global__ void __launch_bounds__(1024) k_order_select_bin(const unsigned int* h
   }
   if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
-  unsigned int base = 0;
-  for (int k = 0; k < warp; ++k) base += warp_tot[k];
-  const unsigned int excl = base + incl - local;  // entries in bins before this thread's range
-  part[t] = excl;
-  __syncthreads();
-  unsigned int total = 0;
-  for (int k = 0; k < 32; ++k) total += warp_tot[k];
-  unsigned int want;
-  if (level == 0) {
-    want = st->want;
-  } else {
-    want = st->want > st->below_hi ? st->want - st->below_hi : 0;
+  unsigned int base = 0, total = 0;
+  for (int k = 0; k < 32; ++k) {
+    if (k < warp) base += warp_tot[k];
+    total += warp_tot[k];
   }
-  // the owner is the thread whose range first reaches `want` (cum >= want)
-  const bool reaches = excl + local >= want;
-  const bool prev_reaches = t > 0 ? (excl >= want) : false;
-  // level 1 with want == 0 selects bin 0 of thread 0 like the serial loop (cum >= 0 at i = 0)
-  bool owner = reaches && !prev_reaches;
-  if (level == 0 && want == 0) owner = false;  // serial loop: found only if cum + h >= want at i=0 -> bin 0
-  __syncthreads();
-  if (level == 0) {
-    if (want == 0) {
-      if (t == 0) {
-        st->hi_bin = 0;
-        st->below_hi = 0;
-        st->total = total;
-      }
-      return;
-    }
-    if (total < want) {
-      if (t == 0) {
-        st->hi_bin = 65535;
-        st->below_hi = total - hist[65535];
-        st->total = total;
-      }
-      return;
-    }
-    if (owner) {
-      unsigned int cum = excl;
-      for (int i = 0; i < 64; ++i) {
-        const unsigned int h = hist[t * 64 + i];
-        if (cum + h >= want) {
-          st->hi_bin = t * 64 + i;
-          st->below_hi = cum;
-          break;
-        }
-        cum += h;
-      }
+  const unsigned int excl = base + incl - local;  // entries in bins before this thread's range
+  const unsigned int want = st->want;
+  const unsigned int shift = 32 - kOrderBinBits;
+  if (total < want || want == 0) {
+    if (t == 0) {
+      // serial loop: want == 0 is reached at bin 0; an unreachable rank keeps everything
+      const unsigned int bin = (want == 0) ? 0u : static_cast<unsigned int>(kOrderBins - 1);
+      st->threshold = (bin << shift) | ((1u << shift) - 1u);
+      st->kept = (want == 0) ? hist[0] : total;
       st->total = total;
+      st->counter = 0;
     }
-  } else {
-    if (total < want) {
-      if (t == 0) {
-        st->threshold = (st->hi_bin << 16) | 65535u;
-        st->kept = st->below_hi + total;
-        st->counter = 0;
-      }
-      return;
-    }
-    if (want == 0) {
-      if (t == 0) {
-        st->threshold = (st->hi_bin << 16) | 0u;
-        st->kept = st->below_hi + hist[0];
-        st->counter = 0;
-      }
-      return;
-    }
-    if (owner) {
-      unsigned int cum = excl;
-      for (int i = 0; i < 64; ++i) {
-        cum += hist[t * 64 + i];
-        if (cum >= want) {
-          st->threshold = (st->hi_bin << 16) | static_cast<unsigned int>(t * 64 + i);
-          st->kept = st->below_hi + cum;
-          st->counter = 0;
-          break;
-        }
+    return;
+  }
+  if (excl < want && excl + local >= want) {  // exactly one thread
+    unsigned int cum = excl;
+    for (int i = 0; i < PER; ++i) {
+      cum += hist[t * PER + i];
+      if (cum >= want) {
+        st->threshold = (static_cast<unsigned int>(t * PER + i) << shift) | ((1u << shift) - 1u);
+        st->kept = cum;
+        break;
       }
     }
+    st->total = total;
+    st->counter = 0;
   }
 }
 
-inline void launch_order_select_bin(Stream s, const unsigned int* hist, OrderSelectState* st, int level) {
-  note_launch("order_select_bin", s, 65536);
-  k_order_select_bin<<<1, 1024, 0, s>>>(hist, st, level);
+inline void launch_order_select_bin(Stream s, const unsigned int* hist, OrderSelectState* st) {
+  note_launch("order_select_bin", s, kOrderBins);
+  k_order_select_bin<<<1, 1024, 0, s>>>(hist, st);
   note_launch_end("order_select_bin", s);
 }
 

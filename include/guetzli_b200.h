@@ -51,6 +51,8 @@ typedef struct gb200_stats {
   long long h2d_bytes; /* host->device bytes copied by this call */
   long long d2h_bytes; /* device->host bytes copied by this call */
   double ms_total, ms_device_setup, ms_compare, ms_zeroing, ms_jpeg, ms_sort, ms_walk;
+  int order_partial; /* selection-walk iterations served by the device top-K order */
+  int order_exact;   /* ... by the complete reference-ordered std::sort */
 } gb200_stats;
 
 /* ProcessStats::debug_output / --verbose sink (guetzli/debug_print.h:28-47). */
