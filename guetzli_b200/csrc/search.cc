@@ -431,18 +431,25 @@ class Search {
           (i % 10 == 0) && (static_cast<long long>(i) + 9 >= min_coeffs_to_change || n_order - 1 <= i + 9);
       const bool can_test = changed_coeffs + 1 > min_coeffs_to_change;
       const bool eval_here = can_test || i + 1 == n_order;
-      // two different blocks with equal keys across the boundary i | i+1 ?
-      bool straddle = false;
+      // does a run of equal keys that contains two different blocks cross the boundary
+      // i | i+1 ?  (then the set of entries applied so far depends on the arrangement)
+      bool straddle = false, pair_only = false;
       if (check_ties && (refresh_here || eval_here) && i + 1 < n_order &&
-          !(order[i].second < order[i + 1].second) && order[i + 1].first != block_ix) {
-        straddle = true;
+          !(order[i].second < order[i + 1].second)) {
+        const float key = order[i].second;
+        size_t lo = i, hi = i + 1;
+        while (lo > 0 && !(order[lo - 1].second < key)) --lo;
+        while (hi + 1 < n_order && !(key < order[hi + 1].second)) ++hi;
+        for (size_t j = lo + 1; j <= hi; ++j)
+          if (order[j].first != order[lo].first) straddle = true;
+        // the run may continue beyond the fetched prefix
+        if (hi + 1 == n_order) straddle = true;
+        pair_only = straddle && lo == i && hi == i + 1;
       }
       int alt_est = 0;
       bool have_alt = false;
       if (straddle) {
-        // tractable case: a tie group of exactly two entries at a plain stop test
-        const bool pair_only = (i == 0 || order[i - 1].second < order[i].second) && i + 2 < n_order &&
-                               order[i + 1].second < order[i + 2].second;
+        // tractable case: a run of exactly two entries at a plain stop test
         if (!pair_only || refresh_here || !can_test) {
           out.ambiguous = true;
           return out;
@@ -591,7 +598,7 @@ class Search {
         // the smallest keys from the device, sort those, and fall back to the complete
         // reference-ordered sort whenever the result could depend on how std::sort
         // places equal keys of different blocks, or the prefix runs out.
-        if (direction < 0 && order_size > 16384) {
+        if (direction < 0 && order_size > 16384 && !getenv("GB200_NO_PARTIAL_ORDER")) {
           // the walk usually stops right after min_coeffs_to_change entries
           size_t want = std::max<size_t>(last_consumed, static_cast<size_t>(min_coeffs_to_change)) * 5 / 4 + 512;
           while (!done && want < order_size / 2) {
@@ -604,6 +611,17 @@ class Search {
             if (val.size() >= order_size) break;
             order.resize(val.size());
             for (size_t i = 0; i < val.size(); ++i) order[i] = std::make_pair(blk[i], val[i]);
+#if defined(GB200_HOSTSIM)
+            // test hook of the CPU port: the device compaction returns the entries in
+            // arbitrary order; emulate that to exercise the tie analysis
+            if (const char* sh = getenv("GB200_SHUFFLE_ORDER")) {
+              unsigned int rng = static_cast<unsigned int>(atoi(sh)) * 2654435761u + static_cast<unsigned int>(st_->iterations);
+              for (size_t i = order.size(); i > 1; --i) {
+                rng = rng * 1664525u + 1013904223u;
+                std::swap(order[i - 1], order[(rng >> 8) % i]);
+              }
+            }
+#endif
             std::sort(order.begin(), order.end(), [](const std::pair<int, float>& a, const std::pair<int, float>& b) {
               return a.second < b.second;
             });
@@ -622,6 +640,11 @@ class Search {
             // usable only if the walk stopped strictly inside the fetched prefix
             if (out.stopped && out.consumed < order.size()) {
               ++st_->order_partial;
+              if (getenv("GB200_DUMP_ITER") && st_->iterations + 1 == atoi(getenv("GB200_DUMP_ITER"))) {
+                fprintf(stderr, "[partial] consumed %zu min %d\n", out.consumed, min_coeffs_to_change);
+                for (size_t i = 0; i < out.consumed + 3 && i < order.size(); ++i)
+                  fprintf(stderr, "[partial] %zu block %d key %.9g\n", i, order[i].first, order[i].second);
+              }
               done = true;
               break;
             }
@@ -667,6 +690,11 @@ class Search {
           Clock::time_point tw = Clock::now();
           out = walk(m, order, direction, min_coeffs_to_change, min_size_delta, prev_size, false);
           st_->ms_walk += ms_since(tw);
+          if (getenv("GB200_DUMP_ITER") && st_->iterations + 1 == atoi(getenv("GB200_DUMP_ITER"))) {
+            fprintf(stderr, "[exact] consumed %zu min %d\n", out.consumed, min_coeffs_to_change);
+            for (size_t i = 0; i < out.consumed + 3 && i < order.size(); ++i)
+              fprintf(stderr, "[exact] %zu block %d key %.9g\n", i, order[i].first, order[i].second);
+          }
         }
         first_up_iter = false;
         last_consumed = out.consumed;

@@ -70,3 +70,17 @@ def test_rejects_low_quality_and_bad_sizes(port_lib):
     assert not ok and jpeg == b""            # rgb.size() != 3*w*h (jpeg_data_encoder.cc:68)
     ok, jpeg = gb.process(gb.Params(force_420=True), None, rgb, 40, 40, lib=port_lib)
     assert not ok                            # YUV420 is out of scope
+
+
+def test_partial_order_is_arrangement_independent(port_lib, ref, monkeypatch):
+    """The device returns the smallest walk-order keys in arbitrary order and equal
+    keys may be arranged differently from the reference's std::sort.  The result must
+    not depend on that: noise images are rich in equal keys; shuffle the fetched
+    entries (test hook of the CPU port) and compare with the reference."""
+    rgb = synth.noise(160, 224, 77)
+    rok, rjpeg, rtrace, _, _ = ref.process_rgb(rgb, 95)
+    for seed in ("1", "2"):
+        monkeypatch.setenv("GB200_SHUFFLE_ORDER", seed)
+        ok, jpeg, trace, st = parity.run_process(port_lib, rgb, 95)
+        assert st.device["order_partial"] > 50
+        assert trace == rtrace and jpeg == rjpeg
