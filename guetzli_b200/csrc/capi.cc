@@ -9,6 +9,9 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+
+#include "exact_sort.h"
 #include "jpeg_out.h"
 #include "pipeline.h"
 #include "search.h"
@@ -254,6 +257,28 @@ int gb200_write_jpeg(const int16_t* coeffs, int w, int h, const int* q, uint8_t*
     memcpy(*out, s.data(), s.size());
     *out_len = s.size();
   });
+}
+
+// test hooks for the prefix-exact std::sort replay (exact_sort.h)
+size_t gb200_debug_partial_sort(int* block, float* key, size_t n, size_t want) {
+  std::vector<gb200::exact_sort::Item> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(block[i], key[i]);
+  const size_t k = gb200::exact_sort::partial_std_sort(v.data(), n, want);
+  for (size_t i = 0; i < n; ++i) {
+    block[i] = v[i].first;
+    key[i] = v[i].second;
+  }
+  return k;
+}
+void gb200_debug_std_sort(int* block, float* key, size_t n) {
+  std::vector<std::pair<int, float> > v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(block[i], key[i]);
+  std::sort(v.begin(), v.end(),
+            [](const std::pair<int, float>& a, const std::pair<int, float>& b) { return a.second < b.second; });
+  for (size_t i = 0; i < n; ++i) {
+    block[i] = v[i].first;
+    key[i] = v[i].second;
+  }
 }
 
 void gb200_counters(long* launches, long long* h2d_bytes, long long* d2h_bytes) {

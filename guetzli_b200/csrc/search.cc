@@ -15,6 +15,7 @@
 #include <stdexcept>
 #include <vector>
 
+#include "exact_sort.h"
 #include "jpeg_out.h"
 #include "pipeline.h"
 #include "tables.h"
@@ -397,7 +398,9 @@ class Search {
   // both arrangements decide "continue" the states coincide again one entry later.
   // Anything else sets out.ambiguous and the caller redoes the iteration with the
   // complete reference-ordered sort.
-  WalkOutcome walk(Sfm& m, const std::vector<std::pair<int, float> >& order, int direction,
+  // `order` may be only a prefix of the complete sorted order of n_total entries; the
+  // caller must then discard the outcome unless the walk stopped inside the prefix.
+  WalkOutcome walk(Sfm& m, const std::vector<std::pair<int, float> >& order, size_t n_total, int direction,
                    int min_coeffs_to_change, double min_size_delta, int prev_size, bool check_ties) {
     const size_t per = static_cast<size_t>(img_.nblocks) * 64;
     WalkOutcome out;
@@ -407,16 +410,17 @@ class Search {
     m.edit_value.clear();
     m.edit_old.clear();
     int changed_coeffs = 0;
-    const size_t n_order = order.size();
-    for (size_t i = 0; i < n_order; ++i) {
+    const size_t n_avail = order.size();
+    const size_t n_order = n_total;
+    for (size_t i = 0; i < n_avail; ++i) {
       // every entry touches a different block: hide the cache misses
-      if (i + 12 < n_order) {
+      if (i + 12 < n_avail) {
         const int pb = order[i + 12].first;
         __builtin_prefetch(&m.last_indexes[pb]);
         __builtin_prefetch(&m.offsets[pb]);
         __builtin_prefetch(&m.block_changed[pb]);
       }
-      if (i + 6 < n_order) {
+      if (i + 6 < n_avail) {
         const int pb = order[i + 6].first;
         const int pli = m.last_indexes[pb] + std::min(direction, 0);
         const uint8_t* pc = &m.cand_idx[m.offsets[pb]];
@@ -434,16 +438,16 @@ class Search {
       // does a run of equal keys that contains two different blocks cross the boundary
       // i | i+1 ?  (then the set of entries applied so far depends on the arrangement)
       bool straddle = false, pair_only = false;
-      if (check_ties && (refresh_here || eval_here) && i + 1 < n_order &&
+      if (check_ties && (refresh_here || eval_here) && i + 1 < n_avail &&
           !(order[i].second < order[i + 1].second)) {
         const float key = order[i].second;
         size_t lo = i, hi = i + 1;
         while (lo > 0 && !(order[lo - 1].second < key)) --lo;
-        while (hi + 1 < n_order && !(key < order[hi + 1].second)) ++hi;
+        while (hi + 1 < n_avail && !(key < order[hi + 1].second)) ++hi;
         for (size_t j = lo + 1; j <= hi; ++j)
           if (order[j].first != order[lo].first) straddle = true;
         // the run may continue beyond the fetched prefix
-        if (hi + 1 == n_order) straddle = true;
+        if (hi + 1 == n_avail && n_avail < n_order) straddle = true;
         pair_only = straddle && lo == i && hi == i + 1;
       }
       int alt_est = 0;
@@ -630,7 +634,7 @@ class Search {
             SymbolHistogram saved_h[3] = {m.ac_h[0], m.ac_h[1], m.ac_h[2]};
             const int saved_hist_size = m.ac_histogram_size;
             const std::vector<uint8_t> saved_depths = m.ac_depths;
-            out = walk(m, order, direction, min_coeffs_to_change, min_size_delta, prev_size, true);
+            out = walk(m, order, order_size, direction, min_coeffs_to_change, min_size_delta, prev_size, true);
             st_->ms_walk += ms_since(tw);
             if (out.ambiguous) {
               ++tie_fallbacks_;
@@ -654,46 +658,56 @@ class Search {
         }
         if (!done) {
           ++st_->order_exact;
-          // complete order, built and sorted exactly like the reference (:636-678)
-          Clock::time_point t0 = Clock::now();
-          order.clear();
-          order.reserve(order_size);
-          for (int block_ix = 0; block_ix < num_blocks; ++block_ix) {
-            if (block_weight[block_ix] == 0) continue;
-            const int last_index = m.last_indexes[block_ix];
-            const int offset = m.offsets[block_ix];
-            const int num_candidates = m.offsets[block_ix + 1] - offset;
-            const float* candidate_errors = &m.cand_err[offset];
-            const float max_err = m.max_block_error[block_ix];
-            if (direction > 0) {
-              for (int i = last_index; i < num_candidates; ++i) {
-                const float val = (candidate_errors[i] - max_err) / block_weight[block_ix];
-                order.push_back(std::make_pair(block_ix, val));
-              }
-            } else {
-              for (int i = last_index - 1; i >= 0; --i) {
-                const float val = (max_err - candidate_errors[i]) / block_weight[block_ix];
-                order.push_back(std::make_pair(block_ix, val));
+          // The reference's own order (:636-678): entries in block-raster / candidate
+          // order, std::sort by key.  Only a prefix is consumed, and introsort never lets
+          // a sub-range influence anything outside itself, so the replay in exact_sort.h
+          // sorts just that prefix (element for element what std::sort would leave there).
+          size_t want = direction > 0 ? order_size
+                                      : std::max<size_t>(4 * static_cast<size_t>(min_coeffs_to_change) + 1024, 4096);
+          for (;;) {
+            Clock::time_point t0 = Clock::now();
+            order.clear();
+            order.reserve(order_size);
+            for (int block_ix = 0; block_ix < num_blocks; ++block_ix) {
+              if (block_weight[block_ix] == 0) continue;
+              const int last_index = m.last_indexes[block_ix];
+              const int offset = m.offsets[block_ix];
+              const int num_candidates = m.offsets[block_ix + 1] - offset;
+              const float* candidate_errors = &m.cand_err[offset];
+              const float max_err = m.max_block_error[block_ix];
+              if (direction > 0) {
+                for (int i = last_index; i < num_candidates; ++i) {
+                  const float val = (candidate_errors[i] - max_err) / block_weight[block_ix];
+                  order.push_back(std::make_pair(block_ix, val));
+                }
+              } else {
+                for (int i = last_index - 1; i >= 0; --i) {
+                  const float val = (max_err - candidate_errors[i]) / block_weight[block_ix];
+                  order.push_back(std::make_pair(block_ix, val));
+                }
               }
             }
-          }
-          std::sort(order.begin(), order.end(), [](const std::pair<int, float>& a, const std::pair<int, float>& b) {
-            return a.second < b.second;
-          });
-          st_->ms_sort += ms_since(t0);
-          if (first_up_iter) {
-            const float limit = 0.75f * params_.butteraugli_target;
-            std::vector<std::pair<int, float> >::iterator it = std::partition_point(
-                order.begin(), order.end(), [=](const std::pair<int, float>& a) { return a.second < limit; });
-            min_coeffs_to_change = std::max<int>(min_coeffs_to_change, it - order.begin());
-          }
-          Clock::time_point tw = Clock::now();
-          out = walk(m, order, direction, min_coeffs_to_change, min_size_delta, prev_size, false);
-          st_->ms_walk += ms_since(tw);
-          if (getenv("GB200_DUMP_ITER") && st_->iterations + 1 == atoi(getenv("GB200_DUMP_ITER"))) {
-            fprintf(stderr, "[exact] consumed %zu min %d\n", out.consumed, min_coeffs_to_change);
-            for (size_t i = 0; i < out.consumed + 3 && i < order.size(); ++i)
-              fprintf(stderr, "[exact] %zu block %d key %.9g\n", i, order[i].first, order[i].second);
+            int min_coeffs = min_coeffs_to_change;
+            if (first_up_iter) {
+              // partition_point of the sorted order (:690-698) == number of keys below the limit
+              const float limit = 0.75f * params_.butteraugli_target;
+              size_t below = 0;
+              for (size_t i = 0; i < order.size(); ++i) below += order[i].second < limit ? 1 : 0;
+              min_coeffs = std::max<int>(min_coeffs, static_cast<int>(below));
+            }
+            if (want > order.size()) want = order.size();
+            const size_t k_end = exact_sort::partial_std_sort(order.data(), order.size(), want);
+            order.resize(k_end);
+            st_->ms_sort += ms_since(t0);
+            Clock::time_point tw = Clock::now();
+            SymbolHistogram saved_h[3] = {m.ac_h[0], m.ac_h[1], m.ac_h[2]};
+            const int saved_hist_size = m.ac_histogram_size;
+            const std::vector<uint8_t> saved_depths = m.ac_depths;
+            out = walk(m, order, order_size, direction, min_coeffs, min_size_delta, prev_size, false);
+            st_->ms_walk += ms_since(tw);
+            if (k_end == order_size || (out.stopped && out.consumed < k_end)) break;
+            unwalk(m, order, out, direction, saved_h, saved_hist_size, saved_depths);
+            want = std::min(order_size, want * 4);
           }
         }
         first_up_iter = false;

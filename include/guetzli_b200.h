@@ -119,6 +119,10 @@ int gb200_image_debug_corner_mask(gb200_image* img, float* out /* [num_blocks][3
  * dequantised coefficients that are multiples of q (host-side serialiser). */
 int gb200_write_jpeg(const int16_t* coeffs, int w, int h, const int* q, uint8_t** out, size_t* out_len);
 
+/* test hooks: prefix-exact replay of std::sort on (block, key) pairs vs std::sort itself */
+size_t gb200_debug_partial_sort(int* block, float* key, size_t n, size_t want);
+void gb200_debug_std_sort(int* block, float* key, size_t n);
+
 /* process-wide running totals: kernels launched, bytes copied host->device and
  * device->host by this library (all threads, all contexts) */
 void gb200_counters(long* launches, long long* h2d_bytes, long long* d2h_bytes);
