@@ -45,13 +45,17 @@ ALG_BYTES = {
     "malta_channel": 28, "blur_x": 8, "blur_y": 8, "sub_planes": 12, "opsin_px": 36, "split_mf_hf": 44, "split_hf_uhf": 68,
     "malta_pre": 12, "malta_acc_hf": 8, "malta_acc_lf": 12, "noise_pre": 12, "noise_asym_acc": 20,
     "mask_diff_pre": 40, "combine_sqrt": 44, "diffmap_mix": 12, "render_blocks": 1152,
-    "block_max": 260, "linearize_rgb": 15, "quantize_coeffs": 4, "fdct_blocks": 576,
+    "block_max": 260, "jpeg_unit_bits": 128, "jpeg_emit": 140, "jpeg_hist_acc": 128, "linearize_rgb": 15, "quantize_coeffs": 4, "fdct_blocks": 576,
 }
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu
 # --set full captures (profiles/), bytes; None until captured.
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {
+    # profiles/r01_ncu_full_malta_blur.csv (noise1080p, per launch: read + write)
+    "malta_channel": 49.8e6 + 8.6e6,
+    "blur_x": 8.33e6, "blur_y": 8.32e6,
+}
 
 
 def make_image(spec, rank=0):

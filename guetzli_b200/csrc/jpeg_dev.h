@@ -5,8 +5,8 @@
 //   JpegHistAcc    DC/AC symbol histograms (privatised global atomics)
 //   JpegHistSum    reduction of the private copies
 //   [host: cluster histograms, build canonical Huffman codes -- 1.5 KB of tables]
-//   JpegMcuBits    code length of every MCU (Y, Cb, Cr block)   -> exclusive scan
-//   JpegEmit       every MCU ORs its bits into the scan at its bit offset
+//   JpegUnitBits   code length of every unit (one block of one component) -> exclusive scan
+//   JpegEmit       every unit ORs its bits into the scan at its bit offset
 //   JpegCountFF    bytes equal to 0xFF (each needs a stuffed zero byte)
 // All integer; bit-exact by construction against the host serialiser (jpeg_out.cc).
 #pragma once
@@ -111,7 +111,9 @@ struct JpegCodes {
   const uint16_t* code;    // [6][256]
 };
 
-struct JpegMcuBits {  // 1D over nblocks
+// One unit = one 8x8 block of one component; units are numbered in scan order
+// u = b * ncomp + c (Y, Cb, Cr block of MCU b).
+struct JpegUnitBits {  // 1D over nblocks * ncomp
   const int16_t* cand;
   const int* q;
   const int* zigzag;
@@ -125,17 +127,14 @@ struct JpegMcuBits {  // 1D over nblocks
     GB_HD void dc(int nbits, unsigned int) { n += dc_d[nbits] + nbits; }
     GB_HD void ac(int symbol, int nbits, unsigned int) { n += ac_d[symbol] + nbits; }
   };
-  GB_HD void operator()(int b) const {
-    unsigned int total = 0;
-    for (int c = 0; c < ncomp; ++c) {
-      const int16_t* blk = cand + (static_cast<size_t>(c) * nblocks + b) * 64;
-      const int* qc = q + 64 * c;
-      const int prev = b > 0 ? (blk - 64)[0] / qc[0] : 0;
-      Visitor v{codes.depth + c * 256, codes.depth + (3 + c) * 256, 0u};
-      visit_block_symbols(blk, qc, prev, zigzag, v);
-      total += v.n;
-    }
-    bits[b] = total;
+  GB_HD void operator()(int u) const {
+    const int b = u / ncomp, c = u - b * ncomp;
+    const int16_t* blk = cand + (static_cast<size_t>(c) * nblocks + b) * 64;
+    const int* qc = q + 64 * c;
+    const int prev = b > 0 ? (blk - 64)[0] / qc[0] : 0;
+    Visitor v{codes.depth + c * 256, codes.depth + (3 + c) * 256, 0u};
+    visit_block_symbols(blk, qc, prev, zigzag, v);
+    bits[u] = v.n;
   }
 };
 
@@ -170,12 +169,12 @@ struct BitCursor {
   }
 };
 
-struct JpegEmit {  // 1D over nblocks
+struct JpegEmit {  // 1D over nblocks * ncomp
   const int16_t* cand;
   const int* q;
   const int* zigzag;
   JpegCodes codes;
-  const unsigned int* offset;  // exclusive scan of JpegMcuBits
+  const unsigned int* offset;  // exclusive scan of JpegUnitBits
   unsigned int* words;
   int nblocks, ncomp;
   struct Visitor {
@@ -193,19 +192,16 @@ struct JpegEmit {  // 1D over nblocks
       if (nbits > 0) cur.put(nbits, extra);
     }
   };
-  GB_HD void operator()(int b) const {
-    BitCursor cur;
-    cur.start(words, offset[b]);
-    for (int c = 0; c < ncomp; ++c) {
-      const int16_t* blk = cand + (static_cast<size_t>(c) * nblocks + b) * 64;
-      const int* qc = q + 64 * c;
-      const int prev = b > 0 ? (blk - 64)[0] / qc[0] : 0;
-      Visitor v{codes.depth + c * 256, codes.code + c * 256, codes.depth + (3 + c) * 256,
-                codes.code + (3 + c) * 256, cur};
-      visit_block_symbols(blk, qc, prev, zigzag, v);
-      cur = v.cur;
-    }
-    cur.finish();
+  GB_HD void operator()(int u) const {
+    const int b = u / ncomp, c = u - b * ncomp;
+    const int16_t* blk = cand + (static_cast<size_t>(c) * nblocks + b) * 64;
+    const int* qc = q + 64 * c;
+    const int prev = b > 0 ? (blk - 64)[0] / qc[0] : 0;
+    Visitor v{codes.depth + c * 256, codes.code + c * 256, codes.depth + (3 + c) * 256,
+              codes.code + (3 + c) * 256, BitCursor()};
+    v.cur.start(words, offset[u]);
+    visit_block_symbols(blk, qc, prev, zigzag, v);
+    v.cur.finish();
   }
 };
 

@@ -597,28 +597,27 @@ struct BlockWeights {
 // a16 ordering: keys of the selection walk, g/processor.cc:636-663.  Entry
 // (block b, candidate slot i) has key (err_i - max_err_b)/w_b ("up", slots
 // >= last_index) or (max_err_b - err_i)/w_b ("down", slots < last_index).
-// Launched over (slot 0..191, block).  Pass 1 histograms the upper 16 bits of
-// the order-preserving integer image of the key; pass 2 compacts every entry
-// whose bin is <= threshold_bin (a superset of the K smallest keys).
+// Launched over the compact list of all candidates (entry -> block, slot).
+// Pass 1 histograms the upper bits of the order-preserving integer image of the
+// key; pass 2 compacts every entry whose bin is <= the threshold bin.
 struct OrderKeyCommon {
   const float* err;        // [nblocks][192]
-  const int* count;        // [nblocks]
+  const int* entry_block;  // [entries]
+  const uint8_t* entry_slot;  // [entries]
   const int* last_index;   // [nblocks]
   const float* max_err;    // [nblocks]
   const float* weight;     // [nblocks]
   int direction;
-  GB_HD bool key(int slot, int b, float* val) const {
+  GB_HD bool key(int entry, int* block, float* val) const {
+    const int b = entry_block[entry];
     const float w = weight[b];
     if (w == 0) return false;
+    const int slot = entry_slot[entry];
     const int li = last_index[b];
+    if (direction > 0 ? slot < li : slot >= li) return false;
     const float e = err[static_cast<size_t>(b) * 192 + slot];
-    if (direction > 0) {
-      if (slot < li || slot >= count[b]) return false;
-      *val = (e - max_err[b]) / w;
-    } else {
-      if (slot >= li) return false;
-      *val = (max_err[b] - e) / w;
-    }
+    *val = direction > 0 ? (e - max_err[b]) / w : (max_err[b] - e) / w;
+    *block = b;
     return true;
   }
 };
@@ -654,9 +653,10 @@ GB_HD void order_hist_add(unsigned int* hist, unsigned int bin) {
 struct OrderKeyHist {
   OrderKeyCommon c;
   unsigned int* hist;  // [kOrderBins]
-  GB_HD void operator()(int slot, int b) const {
+  GB_HD void operator()(int entry) const {
     float v;
-    if (!c.key(slot, b, &v)) return;
+    int b;
+    if (!c.key(entry, &b, &v)) return;
     order_hist_add(hist, hd_float_sortable(v) >> (32 - kOrderBinBits));
   }
 };
@@ -691,9 +691,10 @@ struct OrderKeyCompact {
   float* out_val;
   int* out_block;
   unsigned int cap;
-  GB_HD void operator()(int slot, int b) const {
+  GB_HD void operator()(int entry) const {
     float v;
-    if (!c.key(slot, b, &v)) return;
+    int b;
+    if (!c.key(entry, &b, &v)) return;
     if (hd_float_sortable(v) > st->threshold) return;
     const unsigned int at = hd_atomic_add(&st->counter, 1u);
     if (at < cap) {

@@ -11,6 +11,7 @@
 #include "jpeg_dev.h"
 #if !defined(GB200_HOSTSIM)
 #include "tiled_kernels.cuh"
+#include "zeroing_warp.cuh"
 #endif
 
 namespace gb200 {
@@ -90,16 +91,19 @@ ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device, bool pr
   d_sel_block_ = nullptr;
   j_hist_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * (static_cast<size_t>(kHistCopies + 1) * kHistStride + 2)));
   owned_.push_back(j_hist_);
-  j_bits_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * g_.nblocks));
+  j_bits_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * 3 * g_.nblocks));
   owned_.push_back(j_bits_);
-  j_offset_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * g_.nblocks));
+  j_offset_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * 3 * g_.nblocks));
   owned_.push_back(j_offset_);
-  j_sums_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * (g_.nblocks / 1024 + 32)));
+  j_sums_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * (3 * g_.nblocks / 1024 + 32)));
   owned_.push_back(j_sums_);
   j_depth_ = static_cast<uint8_t*>(dev_alloc(6 * 256));
   owned_.push_back(j_depth_);
   j_code_ = static_cast<uint16_t*>(dev_alloc(6 * 256 * sizeof(uint16_t)));
   owned_.push_back(j_code_);
+  e_block_ = nullptr;
+  e_slot_ = nullptr;
+  num_entries_ = 0;
   d_edit_i_ = nullptr;
   d_edit_v_ = nullptr;
   edit_cap_ = 0;
@@ -181,6 +185,8 @@ ImageContext::~ImageContext() {
   if (j_words_) dev_free(j_words_);
   if (d_edit_i_) dev_free(d_edit_i_);
   if (d_edit_v_) dev_free(d_edit_v_);
+  if (e_block_) dev_free(e_block_);
+  if (e_slot_) dev_free(e_slot_);
   for (size_t i = 0; i < owned_.size(); ++i) dev_free(owned_[i]);
   destroy_stream(s_);
 }
@@ -381,13 +387,49 @@ void ImageContext::zeroing_orders(float block_error_limit, int lookahead, std::v
   z.scale8 = t_.opsin_scale8;
   z.lookahead = lookahead;
   z.block_error_limit = block_error_limit;
+#if defined(GB200_HOSTSIM)
   launch_1d(s_, z, g_.nblocks, "zeroing_orders");
+#else
+  {
+    ZeroingWarpArgs zw;
+    zw.cand = z.cand;
+    zw.orig = z.orig;
+    zw.rgb = z.rgb;
+    zw.corner_mask = z.corner_mask;
+    zw.out_idx = z.out_idx;
+    zw.out_err = z.out_err;
+    zw.out_count = z.out_count;
+    zw.g = g_;
+    zw.t = t_;
+    zw.lookahead = lookahead;
+    zw.block_error_limit = block_error_limit;
+    launch_zeroing_orders_warp(s_, zw);
+  }
+#endif
   idx->resize(slots);
   err->resize(slots);
   count->resize(g_.nblocks);
   d2h(idx->data(), d_idx, slots, s_);
   d2h(err->data(), d_err, slots * sizeof(float), s_);
   d2h(count->data(), d_cnt, sizeof(int) * g_.nblocks, s_);
+  // compact (block, slot) list of all candidates for the order-key kernels
+  std::vector<int> eb;
+  std::vector<uint8_t> es;
+  for (int b = 0; b < g_.nblocks; ++b)
+    for (int i = 0; i < (*count)[b]; ++i) {
+      eb.push_back(b);
+      es.push_back(static_cast<uint8_t>(i));
+    }
+  num_entries_ = eb.size();
+  if (e_block_) dev_free(e_block_);
+  if (e_slot_) dev_free(e_slot_);
+  e_block_ = static_cast<int*>(dev_alloc(sizeof(int) * (num_entries_ + 1)));
+  e_slot_ = static_cast<uint8_t*>(dev_alloc(num_entries_ + 1));
+  if (num_entries_) {
+    h2d(e_block_, eb.data(), sizeof(int) * num_entries_, s_);
+    h2d(e_slot_, es.data(), num_entries_, s_);
+    stream_sync(s_);
+  }
 }
 
 size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_index,
@@ -402,14 +444,15 @@ size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_
   h2d(st, &init, sizeof(init), s_);
   OrderKeyCommon c;
   c.err = z_err_;
-  c.count = z_cnt_;
+  c.entry_block = e_block_;
+  c.entry_slot = e_slot_;
   c.last_index = d_last_index_;
   c.max_err = d_max_err_;
   c.weight = weights_;
   c.direction = direction;
   // bin the keys, find the bin of the k-th smallest, entirely on the device
   dev_zero(d_hist_, sizeof(unsigned int) * kOrderBins, s_);
-  launch_2d(s_, OrderKeyHist{c, d_hist_}, 192, g_.nblocks, "order_key_hist");
+  launch_1d(s_, OrderKeyHist{c, d_hist_}, static_cast<int>(num_entries_), "order_key_hist");
 #if defined(GB200_HOSTSIM)
   launch_1d(s_, OrderSelectBin{d_hist_, st}, 1, "order_select_bin");
 #else
@@ -425,8 +468,8 @@ size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_
     d_sel_val_ = static_cast<float*>(dev_alloc(sel_cap_ * sizeof(float)));
     d_sel_block_ = static_cast<int*>(dev_alloc(sel_cap_ * sizeof(int)));
   }
-  launch_2d(s_, OrderKeyCompact{c, st, d_sel_val_, d_sel_block_, static_cast<unsigned int>(sel_cap_)}, 192,
-            g_.nblocks, "order_key_compact");
+  launch_1d(s_, OrderKeyCompact{c, st, d_sel_val_, d_sel_block_, static_cast<unsigned int>(sel_cap_)},
+            static_cast<int>(num_entries_), "order_key_compact");
   val->resize(kept);
   block->resize(kept);
   if (kept) {
@@ -548,9 +591,10 @@ void ImageContext::jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint1
   h2d(j_depth_, depth, 6 * 256, s_);
   h2d(j_code_, code, 6 * 256 * sizeof(uint16_t), s_);
   JpegCodes codes{j_depth_, j_code_};
-  launch_1d(s_, JpegMcuBits{d_cand_, d_q_, t_.zigzag, codes, j_bits_, g_.nblocks, ncomp}, g_.nblocks, "jpeg_mcu_bits");
+  const int units = g_.nblocks * ncomp;
+  launch_1d(s_, JpegUnitBits{d_cand_, d_q_, t_.zigzag, codes, j_bits_, g_.nblocks, ncomp}, units, "jpeg_unit_bits");
   unsigned long long total_bits = 0;
-  exclusive_scan(j_bits_, j_offset_, g_.nblocks, &total_bits);
+  exclusive_scan(j_bits_, j_offset_, units, &total_bits);
   if (total_bits >= (1ull << 32)) throw std::runtime_error("jpeg scan exceeds 2^32 bits");
   const size_t nwords = static_cast<size_t>((total_bits + 31) >> 5);
   if (nwords + 1 > j_words_cap_) {
@@ -559,7 +603,7 @@ void ImageContext::jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint1
     j_words_ = static_cast<unsigned int*>(dev_alloc(j_words_cap_ * sizeof(unsigned int)));
   }
   dev_zero(j_words_, (nwords + 1) * sizeof(unsigned int), s_);
-  launch_1d(s_, JpegEmit{d_cand_, d_q_, t_.zigzag, codes, j_offset_, j_words_, g_.nblocks, ncomp}, g_.nblocks,
+  launch_1d(s_, JpegEmit{d_cand_, d_q_, t_.zigzag, codes, j_offset_, j_words_, g_.nblocks, ncomp}, units,
             "jpeg_emit");
   unsigned int* counter = j_hist_ + static_cast<size_t>(kHistCopies + 1) * kHistStride + 1;
   dev_zero(counter, sizeof(unsigned int), s_);

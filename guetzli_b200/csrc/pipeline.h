@@ -146,6 +146,9 @@ class ImageContext {
   float* d_sel_val_;
   int* d_sel_block_;
   size_t sel_cap_;
+  int* e_block_;      // [entries] block of every candidate (compact list)
+  uint8_t* e_slot_;   // [entries] its slot
+  size_t num_entries_;
   int* d_edit_i_;
   int16_t* d_edit_v_;
   size_t edit_cap_;
@@ -155,8 +158,8 @@ class ImageContext {
   std::vector<char> dirty_flag_;
   std::vector<int> dirty_list_;
   unsigned int* j_hist_;      // [kHistCopies][6][257] + [6][257] + flag + ff counter
-  unsigned int* j_bits_;      // [nblocks] MCU bit lengths
-  unsigned int* j_offset_;    // [nblocks] exclusive scan
+  unsigned int* j_bits_;      // [3*nblocks] unit bit lengths (scan order)
+  unsigned int* j_offset_;    // [3*nblocks] exclusive scan
   unsigned int* j_sums_;      // scan scratch
   uint8_t* j_depth_;          // [6][256]
   uint16_t* j_code_;          // [6][256]

@@ -140,9 +140,25 @@ __global__ void __launch_bounds__(256) k_blur_x(BlurArgs a, BlurTaps<R> taps) {
   const int w = a.g.w;
   const float* srow = tile[ry];
   float* orow = a.out + static_cast<size_t>(row) * a.g.pitch;
-  // outputs xb + lane-strided: thread handles x = x0 + threadIdx.x + 32*o (o < 8) so that
-  // shared-memory reads of a warp are consecutive (no bank conflicts)
+  // thread handles x = x0 + threadIdx.x + 32*o (o < 8): a warp reads consecutive
+  // shared-memory words (no bank conflicts)
+  if (x0 >= R && x0 + GB_BLURX_TW - 1 + R < w) {
+    // whole tile interior: eight independent accumulation chains per thread, each
+    // adding its products in ascending tap order
+    float acc[GB_BLURX_PT];
 #pragma unroll
+    for (int o = 0; o < GB_BLURX_PT; ++o) acc[o] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < LEN; ++j) {
+      const float tap = taps.n[j];
+#pragma unroll
+      for (int o = 0; o < GB_BLURX_PT; ++o) acc[o] += srow[threadIdx.x + 32 * o + j] * tap;
+    }
+#pragma unroll
+    for (int o = 0; o < GB_BLURX_PT; ++o) orow[x0 + threadIdx.x + 32 * o] = acc[o];
+    return;
+  }
+#pragma unroll 1
   for (int o = 0; o < GB_BLURX_PT; ++o) {
     const int xl = threadIdx.x + 32 * o;  // position inside the tile
     const int x = x0 + xl;
@@ -161,9 +177,9 @@ __global__ void __launch_bounds__(256) k_blur_x(BlurArgs a, BlurTaps<R> taps) {
   }
 }
 
-// y pass: a thread owns one column and makes 8 consecutive rows, streaming the
-// 8 + 2R input rows once (coalesced across the warp) into 8 accumulators.
-#define GB_BLURY_R 8
+// y pass: a thread owns one column and makes GB_BLURY_R consecutive rows, streaming the
+// GB_BLURY_R + 2R input rows once (coalesced across the warp) into that many accumulators.
+#define GB_BLURY_R 16
 template <int R>
 __global__ void __launch_bounds__(128) k_blur_y(BlurArgs a, BlurTaps<R> taps) {
   constexpr int LEN = 2 * R + 1;
@@ -247,34 +263,32 @@ inline void launch_blur_tiled(Stream s, const float* in, float* tmp, float* out,
 }
 
 // ---------------------------------------------------------------------------
-// Parallel form of OrderSelectBin (kernels.h): one CTA of 1024 threads, each owning
-// kOrderBins/1024 consecutive bins; block-wide scan of the per-thread sums, then the
-// owning thread walks its bins.  Same result as the serial functor.
+// Parallel form of OrderSelectBin (kernels.h): one CTA of 32 warps.  Warp w owns the
+// contiguous chunk of kOrderBins/32 bins; it sums the chunk with coalesced loads,
+// the 32 chunk totals are scanned, and the warp whose chunk contains the wanted rank
+// re-reads it 32 bins at a time (warp-inclusive scan) to find the bin.  Same result
+// as the serial functor.
 __global__ void __launch_bounds__(1024) k_order_select_bin(const unsigned int* hist, OrderSelectState* st) {
-  constexpr int PER = kOrderBins / 1024;
-  __shared__ unsigned int warp_tot[32];
-  const int t = threadIdx.x;
+  constexpr int CHUNK = kOrderBins / 32;
+  __shared__ unsigned int chunk_tot[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int* h = hist + warp * CHUNK;
   unsigned int local = 0;
-  for (int i = 0; i < PER; ++i) local += hist[t * PER + i];
-  unsigned int incl = local;
-  const int lane = t & 31, warp = t >> 5;
+#pragma unroll 8
+  for (int i = 0; i < CHUNK / 32; ++i) local += h[i * 32 + lane];
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
-  }
-  if (lane == 31) warp_tot[warp] = incl;
+  for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+  if (lane == 0) chunk_tot[warp] = local;
   __syncthreads();
-  unsigned int base = 0, total = 0;
+  unsigned int before = 0, total = 0;
   for (int k = 0; k < 32; ++k) {
-    if (k < warp) base += warp_tot[k];
-    total += warp_tot[k];
+    if (k < warp) before += chunk_tot[k];
+    total += chunk_tot[k];
   }
-  const unsigned int excl = base + incl - local;  // entries in bins before this thread's range
   const unsigned int want = st->want;
   const unsigned int shift = 32 - kOrderBinBits;
   if (total < want || want == 0) {
-    if (t == 0) {
+    if (threadIdx.x == 0) {
       // serial loop: want == 0 is reached at bin 0; an unreachable rank keeps everything
       const unsigned int bin = (want == 0) ? 0u : static_cast<unsigned int>(kOrderBins - 1);
       st->threshold = (bin << shift) | ((1u << shift) - 1u);
@@ -284,18 +298,28 @@ __global__ void __launch_bounds__(1024) k_order_select_bin(const unsigned int* h
     }
     return;
   }
-  if (excl < want && excl + local >= want) {  // exactly one thread
-    unsigned int cum = excl;
-    for (int i = 0; i < PER; ++i) {
-      cum += hist[t * PER + i];
-      if (cum >= want) {
-        st->threshold = (static_cast<unsigned int>(t * PER + i) << shift) | ((1u << shift) - 1u);
-        st->kept = cum;
-        break;
-      }
+  if (!(before < want && before + chunk_tot[warp] >= want)) return;  // exactly one warp continues
+  unsigned int cum = before;
+  for (int i = 0; i < CHUNK / 32; ++i) {
+    const unsigned int v = h[i * 32 + lane];
+    unsigned int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned int u = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += u;
     }
-    st->total = total;
-    st->counter = 0;
+    const unsigned int reach = __ballot_sync(0xffffffffu, cum + incl >= want);
+    if (reach) {
+      const int first = __ffs(reach) - 1;
+      if (lane == first) {
+        st->threshold = (static_cast<unsigned int>(warp * CHUNK + i * 32 + lane) << shift) | ((1u << shift) - 1u);
+        st->kept = cum + incl;
+        st->total = total;
+        st->counter = 0;
+      }
+      return;
+    }
+    cum += __shfl_sync(0xffffffffu, incl, 31);
   }
 }
 
