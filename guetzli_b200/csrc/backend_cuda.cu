@@ -21,14 +21,68 @@ void cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   throw std::runtime_error(buf);
 }
 
+// Caching device allocator.  cudaMalloc takes a process-wide lock and cudaFree
+// synchronises the whole device; with one image context per host thread (dozens of
+// planes each, created and destroyed per image) that serialises the threads and
+// stalls every stream.  Freed blocks are kept in per-(device, size) free lists and
+// handed out again; callers only free memory whose stream work has completed
+// (contexts synchronise their stream before releasing anything).
+namespace {
+struct DevCache {
+  std::mutex mu;
+  std::map<std::pair<int, size_t>, std::vector<void*> > free_list;
+  std::map<void*, std::pair<int, size_t> > live;
+};
+DevCache& dev_cache() {
+  static DevCache c;
+  return c;
+}
+}  // namespace
+
 void* dev_alloc(size_t bytes) {
+  const size_t size = ((bytes ? bytes : 1) + 511) & ~static_cast<size_t>(511);
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  DevCache& c = dev_cache();
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    std::vector<void*>& fl = c.free_list[std::make_pair(dev, size)];
+    if (!fl.empty()) {
+      void* p = fl.back();
+      fl.pop_back();
+      c.live[p] = std::make_pair(dev, size);
+      return p;
+    }
+  }
   void* p = nullptr;
-  GB_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+  cudaError_t e = cudaMalloc(&p, size);
+  if (e != cudaSuccess) {
+    // out of memory: drop the cache and retry once
+    cudaGetLastError();
+    {
+      std::lock_guard<std::mutex> lock(c.mu);
+      for (std::map<std::pair<int, size_t>, std::vector<void*> >::iterator it = c.free_list.begin();
+           it != c.free_list.end(); ++it) {
+        if (it->first.first != dev) continue;
+        for (size_t i = 0; i < it->second.size(); ++i) cudaFree(it->second[i]);
+        it->second.clear();
+      }
+    }
+    GB_CUDA(cudaMalloc(&p, size));
+  }
+  std::lock_guard<std::mutex> lock(c.mu);
+  c.live[p] = std::make_pair(dev, size);
   return p;
 }
 
 void dev_free(void* p) {
-  if (p) cudaFree(p);
+  if (!p) return;
+  DevCache& c = dev_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  std::map<void*, std::pair<int, size_t> >::iterator it = c.live.find(p);
+  if (it == c.live.end()) return;
+  c.free_list[it->second].push_back(p);
+  c.live.erase(it);
 }
 
 static std::atomic<long long> g_h2d_bytes(0), g_d2h_bytes(0);

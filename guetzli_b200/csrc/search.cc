@@ -602,7 +602,7 @@ class Search {
         // the smallest keys from the device, sort those, and fall back to the complete
         // reference-ordered sort whenever the result could depend on how std::sort
         // places equal keys of different blocks, or the prefix runs out.
-        if (direction < 0 && order_size > 16384 && !getenv("GB200_NO_PARTIAL_ORDER")) {
+        if (direction < 0 && order_size > 16384) {
           // the walk usually stops right after min_coeffs_to_change entries
           size_t want = std::max<size_t>(last_consumed, static_cast<size_t>(min_coeffs_to_change)) * 5 / 4 + 512;
           while (!done && want < order_size / 2) {
@@ -611,7 +611,6 @@ class Search {
             std::vector<int> blk;
             const size_t total = ctx_->order_smallest(direction, m.last_indexes, m.max_block_error, want, &val, &blk);
             if (total != order_size) throw std::runtime_error("order_smallest: entry count mismatch");
-            if (getenv("GB200_DEBUG_ORDER")) fprintf(stderr, "[order] size %zu want %zu got %zu\n", order_size, want, val.size());
             if (val.size() >= order_size) break;
             order.resize(val.size());
             for (size_t i = 0; i < val.size(); ++i) order[i] = std::make_pair(blk[i], val[i]);
@@ -644,11 +643,6 @@ class Search {
             // usable only if the walk stopped strictly inside the fetched prefix
             if (out.stopped && out.consumed < order.size()) {
               ++st_->order_partial;
-              if (getenv("GB200_DUMP_ITER") && st_->iterations + 1 == atoi(getenv("GB200_DUMP_ITER"))) {
-                fprintf(stderr, "[partial] consumed %zu min %d\n", out.consumed, min_coeffs_to_change);
-                for (size_t i = 0; i < out.consumed + 3 && i < order.size(); ++i)
-                  fprintf(stderr, "[partial] %zu block %d key %.9g\n", i, order[i].first, order[i].second);
-              }
               done = true;
               break;
             }

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) k_blur_x(BlurArgs a, BlurTaps<R> taps) {
 
 // y pass: a thread owns one column and makes GB_BLURY_R consecutive rows, streaming the
 // GB_BLURY_R + 2R input rows once (coalesced across the warp) into that many accumulators.
-#define GB_BLURY_R 16
+#define GB_BLURY_R 8
 template <int R>
 __global__ void __launch_bounds__(128) k_blur_y(BlurArgs a, BlurTaps<R> taps) {
   constexpr int LEN = 2 * R + 1;
