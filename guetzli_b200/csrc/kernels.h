@@ -622,66 +622,76 @@ struct OrderKeyCommon {
   }
 };
 
-// Device-resident state of the key selection.  Keys are binned by the upper
-// kOrderBinBits bits of their order-preserving 32-bit image (sign, exponent and the
-// top mantissa bits: relative resolution 2^-9); every entry whose bin is <= the bin
-// in which the cumulative count reaches `want` is kept -- a superset of the `want`
-// smallest keys that is a prefix of the sorted order (all ties included).
-static const int kOrderBinBits = 18;
-static const int kOrderBins = 1 << kOrderBinBits;
+// Device-resident state of the key selection: a two-level radix select on the
+// order-preserving 32-bit image of the keys.  Level 0 bins bits 31..21 (sign,
+// exponent, 2 mantissa bits), level 1 bins bits 20..10 of the keys that fell into the
+// level-0 bin of the wanted rank; every entry with image <= threshold (22 significant
+// bits) is kept -- a superset of the `want` smallest keys that is a prefix of the
+// sorted order (equal keys are never separated).
+static const int kOrderBins = 2048;
 
 struct OrderSelectState {
   unsigned int want;       // rank wanted (number of smallest keys)
+  unsigned int bin0;       // level-0 bin of that rank
+  unsigned int below0;     // entries in level-0 bins < bin0
   unsigned int threshold;  // entries with sortable key <= threshold are kept
   unsigned int kept;       // number of such entries
   unsigned int total;      // all entries
   unsigned int counter;    // compaction cursor
 };
 
-GB_HD void order_hist_add(unsigned int* hist, unsigned int bin) {
-#if defined(__CUDA_ARCH__)
-  // warp-aggregated: one atomic per distinct bin per warp
-  const unsigned int active = __activemask();
-  const unsigned int peers = __match_any_sync(active, bin);
-  const int leader = __ffs(peers) - 1;
-  if ((threadIdx.y * blockDim.x + threadIdx.x) % 32 == leader) atomicAdd(&hist[bin], __popc(peers));
-#else
-  hd_atomic_add(&hist[bin], 1u);
-#endif
+GB_HD bool order_bin(const OrderSelectState* st, int level, unsigned int u, unsigned int* bin) {
+  if (level == 0) {
+    *bin = u >> 21;
+    return true;
+  }
+  if ((u >> 21) != st->bin0) return false;
+  *bin = (u >> 10) & 0x7ffu;
+  return true;
 }
 
-struct OrderKeyHist {
+struct OrderKeyHist {  // generic form (CPU port); the CUDA build uses k_order_hist
   OrderKeyCommon c;
   unsigned int* hist;  // [kOrderBins]
+  const OrderSelectState* st;
+  int level;
   GB_HD void operator()(int entry) const {
     float v;
     int b;
     if (!c.key(entry, &b, &v)) return;
-    order_hist_add(hist, hd_float_sortable(v) >> (32 - kOrderBinBits));
+    unsigned int bin;
+    if (order_bin(st, level, hd_float_sortable(v), &bin)) hd_atomic_add(&hist[bin], 1u);
   }
 };
 
-// One invocation (launch_1d over 1 element): scans the histogram for the bin where
-// the cumulative count reaches the wanted rank.
+// One invocation: scans the 2048-bin histogram for the bin where the cumulative
+// count reaches the wanted rank (level 0), resp. the residual rank (level 1).
 struct OrderSelectBin {
   const unsigned int* hist;
   OrderSelectState* st;
+  int level;
   GB_HD void operator()(int) const {
-    unsigned int cum = 0, bin = kOrderBins - 1, kept = 0;
+    const unsigned int want = level == 0 ? st->want : (st->want > st->below0 ? st->want - st->below0 : 0u);
+    unsigned int cum = 0, bin = kOrderBins - 1, at = 0;
     bool found = false;
     for (int i = 0; i < kOrderBins; ++i) {
-      cum += hist[i];
-      if (!found && cum >= st->want) {
+      if (!found && cum + hist[i] >= want) {
         bin = static_cast<unsigned int>(i);
-        kept = cum;
+        at = cum;
         found = true;
       }
+      cum += hist[i];
     }
-    if (!found) kept = cum;
-    st->threshold = (bin << (32 - kOrderBinBits)) | ((1u << (32 - kOrderBinBits)) - 1u);
-    st->kept = kept;
-    st->total = cum;
-    st->counter = 0;
+    if (!found) at = cum - hist[kOrderBins - 1];
+    if (level == 0) {
+      st->bin0 = bin;
+      st->below0 = at;
+      st->total = cum;
+    } else {
+      st->threshold = (st->bin0 << 21) | (bin << 10) | 0x3ffu;
+      st->kept = st->below0 + at + hist[bin];
+      st->counter = 0;
+    }
   }
 };
 

@@ -450,14 +450,17 @@ size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_
   c.max_err = d_max_err_;
   c.weight = weights_;
   c.direction = direction;
-  // bin the keys, find the bin of the k-th smallest, entirely on the device
-  dev_zero(d_hist_, sizeof(unsigned int) * kOrderBins, s_);
-  launch_1d(s_, OrderKeyHist{c, d_hist_}, static_cast<int>(num_entries_), "order_key_hist");
+  // two-level radix select of the k-th smallest key, entirely on the device
+  for (int level = 0; level < 2; ++level) {
+    dev_zero(d_hist_, sizeof(unsigned int) * kOrderBins, s_);
 #if defined(GB200_HOSTSIM)
-  launch_1d(s_, OrderSelectBin{d_hist_, st}, 1, "order_select_bin");
+    launch_1d(s_, OrderKeyHist{c, d_hist_, st, level}, static_cast<int>(num_entries_), "order_key_hist");
+    launch_1d(s_, OrderSelectBin{d_hist_, st, level}, 1, "order_select_bin");
 #else
-  launch_order_select_bin(s_, d_hist_, st);
+    launch_order_hist(s_, c, d_hist_, st, level, static_cast<int>(num_entries_));
+    launch_order_select_bin(s_, d_hist_, st, level);
 #endif
+  }
   OrderSelectState got;
   d2h(&got, st, sizeof(got), s_);
   const size_t kept = got.kept;

@@ -263,69 +263,110 @@ inline void launch_blur_tiled(Stream s, const float* in, float* tmp, float* out,
 }
 
 // ---------------------------------------------------------------------------
-// Parallel form of OrderSelectBin (kernels.h): one CTA of 32 warps.  Warp w owns the
-// contiguous chunk of kOrderBins/32 bins; it sums the chunk with coalesced loads,
-// the 32 chunk totals are scanned, and the warp whose chunk contains the wanted rank
-// re-reads it 32 bins at a time (warp-inclusive scan) to find the bin.  Same result
-// as the serial functor.
-__global__ void __launch_bounds__(1024) k_order_select_bin(const unsigned int* hist, OrderSelectState* st) {
-  constexpr int CHUNK = kOrderBins / 32;
-  __shared__ unsigned int chunk_tot[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned int* h = hist + warp * CHUNK;
-  unsigned int local = 0;
-#pragma unroll 8
-  for (int i = 0; i < CHUNK / 32; ++i) local += h[i * 32 + lane];
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
-  if (lane == 0) chunk_tot[warp] = local;
+// a16 key histograms with a per-CTA shared-memory histogram (keys cluster in a few
+// bins: global atomics would serialise), flushed once per CTA; and the matching
+// single-CTA bin search.  Same results as OrderKeyHist / OrderSelectBin (kernels.h).
+__global__ void __launch_bounds__(256) k_order_hist(OrderKeyCommon c, unsigned int* hist, const OrderSelectState* st,
+                                                    int level, int entries) {
+  __shared__ unsigned int sh[kOrderBins];
+  for (int i = threadIdx.x; i < kOrderBins; i += 256) sh[i] = 0;
   __syncthreads();
-  unsigned int before = 0, total = 0;
-  for (int k = 0; k < 32; ++k) {
-    if (k < warp) before += chunk_tot[k];
-    total += chunk_tot[k];
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < entries; e += gridDim.x * 256) {
+    float v;
+    int b;
+    if (!c.key(e, &b, &v)) continue;
+    unsigned int bin;
+    if (order_bin(st, level, hd_float_sortable(v), &bin)) atomicAdd(&sh[bin], 1u);
   }
-  const unsigned int want = st->want;
-  const unsigned int shift = 32 - kOrderBinBits;
-  if (total < want || want == 0) {
-    if (threadIdx.x == 0) {
-      // serial loop: want == 0 is reached at bin 0; an unreachable rank keeps everything
-      const unsigned int bin = (want == 0) ? 0u : static_cast<unsigned int>(kOrderBins - 1);
-      st->threshold = (bin << shift) | ((1u << shift) - 1u);
-      st->kept = (want == 0) ? hist[0] : total;
-      st->total = total;
-      st->counter = 0;
-    }
-    return;
-  }
-  if (!(before < want && before + chunk_tot[warp] >= want)) return;  // exactly one warp continues
-  unsigned int cum = before;
-  for (int i = 0; i < CHUNK / 32; ++i) {
-    const unsigned int v = h[i * 32 + lane];
-    unsigned int incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned int u = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += u;
-    }
-    const unsigned int reach = __ballot_sync(0xffffffffu, cum + incl >= want);
-    if (reach) {
-      const int first = __ffs(reach) - 1;
-      if (lane == first) {
-        st->threshold = (static_cast<unsigned int>(warp * CHUNK + i * 32 + lane) << shift) | ((1u << shift) - 1u);
-        st->kept = cum + incl;
-        st->total = total;
-        st->counter = 0;
-      }
-      return;
-    }
-    cum += __shfl_sync(0xffffffffu, incl, 31);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kOrderBins; i += 256) {
+    const unsigned int n = sh[i];
+    if (n) atomicAdd(&hist[i], n);
   }
 }
 
-inline void launch_order_select_bin(Stream s, const unsigned int* hist, OrderSelectState* st) {
+__global__ void __launch_bounds__(1024) k_order_select_bin(const unsigned int* hist, OrderSelectState* st, int level) {
+  __shared__ unsigned int warp_tot[32];
+  const int t = threadIdx.x;
+  const unsigned int h0 = hist[2 * t], h1 = hist[2 * t + 1];
+  const unsigned int local = h0 + h1;
+  unsigned int incl = local;
+  const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  unsigned int base = 0, total = 0;
+  for (int k = 0; k < 32; ++k) {
+    if (k < warp) base += warp_tot[k];
+    total += warp_tot[k];
+  }
+  const unsigned int excl = base + incl - local;
+  const unsigned int want = level == 0 ? st->want : (st->want > st->below0 ? st->want - st->below0 : 0u);
+  // serial semantics: first bin i with cum_before(i) + hist[i] >= want; none -> last bin
+  unsigned int bin = 0xffffffffu, at = 0;
+  if (excl + h0 >= want) {
+    if (t == 0 || excl < want || want == 0) {
+      // candidate: bin 2t, valid only if no earlier bin qualifies
+      bin = 2 * t;
+      at = excl;
+    }
+  } else if (excl + local >= want) {
+    bin = 2 * t + 1;
+    at = excl + h0;
+  }
+  // the first qualifying bin overall = minimum candidate
+  __shared__ unsigned int best_bin;
+  if (t == 0) best_bin = 0xffffffffu;
+  __syncthreads();
+  if (bin != 0xffffffffu) atomicMin(&best_bin, bin);
+  __syncthreads();
+  const unsigned int chosen = best_bin;
+  if (chosen == 0xffffffffu) {
+    if (t == 0) {
+      const unsigned int last = kOrderBins - 1;
+      const unsigned int before = total - hist[last];
+      if (level == 0) {
+        st->bin0 = last;
+        st->below0 = before;
+        st->total = total;
+      } else {
+        st->threshold = (st->bin0 << 21) | (last << 10) | 0x3ffu;
+        st->kept = st->below0 + before + hist[last];
+        st->counter = 0;
+      }
+    }
+    return;
+  }
+  if (bin == chosen) {
+    if (level == 0) {
+      st->bin0 = chosen;
+      st->below0 = at;
+      st->total = total;
+    } else {
+      st->threshold = (st->bin0 << 21) | (chosen << 10) | 0x3ffu;
+      st->kept = st->below0 + at + hist[chosen];
+      st->counter = 0;
+    }
+  }
+}
+
+inline void launch_order_hist(Stream s, const OrderKeyCommon& c, unsigned int* hist, const OrderSelectState* st,
+                              int level, int entries) {
+  int ctas = (entries + 256 * 8 - 1) / (256 * 8);
+  if (ctas < 1) ctas = 1;
+  if (ctas > 1184) ctas = 1184;  // 148 SMs x 8 resident CTAs
+  note_launch("order_key_hist", s, entries);
+  k_order_hist<<<ctas, 256, 0, s>>>(c, hist, st, level, entries);
+  note_launch_end("order_key_hist", s);
+}
+
+inline void launch_order_select_bin(Stream s, const unsigned int* hist, OrderSelectState* st, int level) {
   note_launch("order_select_bin", s, kOrderBins);
-  k_order_select_bin<<<1, 1024, 0, s>>>(hist, st);
+  k_order_select_bin<<<1, 1024, 0, s>>>(hist, st, level);
   note_launch_end("order_select_bin", s);
 }
 
