@@ -45,7 +45,7 @@ ALG_BYTES = {
     "malta_channel": 28, "blur_x": 8, "blur_y": 8, "sub_planes": 12, "opsin_px": 36, "split_mf_hf": 44, "split_hf_uhf": 68,
     "malta_pre": 12, "malta_acc_hf": 8, "malta_acc_lf": 12, "noise_pre": 12, "noise_asym_acc": 20,
     "mask_diff_pre": 40, "combine_sqrt": 44, "diffmap_mix": 12, "render_blocks": 1152,
-    "block_max": 260, "jpeg_unit_bits": 128, "jpeg_emit": 140, "jpeg_hist_acc": 128, "linearize_rgb": 15, "quantize_coeffs": 4, "fdct_blocks": 576,
+    "block_max": 260, "jpeg_unit_bits": 128, "jpeg_emit": 140, "jpeg_hist_acc": 128, "jpeg_hist": 128, "linearize_rgb": 15, "quantize_coeffs": 4, "fdct_blocks": 576,
 }
 
 

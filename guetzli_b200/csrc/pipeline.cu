@@ -579,10 +579,18 @@ void ImageContext::exclusive_scan(const unsigned int* in, unsigned int* out, int
 
 void ImageContext::jpeg_histograms(unsigned int* hist, bool* chroma_nonzero) {
   const size_t priv = static_cast<size_t>(kHistCopies) * kHistStride;
+#if defined(GB200_HOSTSIM)
   dev_zero(j_hist_, sizeof(unsigned int) * (priv + kHistStride + 2), s_);
+#else
+  dev_zero(j_hist_ + priv, sizeof(unsigned int) * (kHistStride + 2), s_);
+#endif
   unsigned int* flag = j_hist_ + priv + kHistStride;
+#if defined(GB200_HOSTSIM)
   launch_1d(s_, JpegHistAcc{d_cand_, d_q_, t_.zigzag, j_hist_, flag, g_.nblocks}, 3 * g_.nblocks, "jpeg_hist_acc");
   launch_1d(s_, JpegHistSum{j_hist_, j_hist_ + priv}, kHistStride, "jpeg_hist_sum");
+#else
+  launch_jpeg_hist(s_, d_cand_, d_q_, t_.zigzag, j_hist_ + priv, flag, g_.nblocks);
+#endif
   std::vector<unsigned int> buf(kHistStride + 2);
   d2h(buf.data(), j_hist_ + priv, sizeof(unsigned int) * (kHistStride + 2), s_);
   memcpy(hist, buf.data(), sizeof(unsigned int) * kHistStride);

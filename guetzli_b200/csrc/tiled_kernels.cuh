@@ -9,6 +9,7 @@
 #include <stdexcept>
 
 #include "ba_math.h"
+#include "jpeg_dev.h"
 #include "kernels.h"
 #include "malta_unrolled.inc"
 
@@ -260,6 +261,48 @@ inline void launch_blur_tiled(Stream s, const float* in, float* tmp, float* out,
     case 24: launch_blur_r<24>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
     default: throw std::runtime_error("blur radius without a compiled kernel");
   }
+}
+
+// ---------------------------------------------------------------------------
+// a11 symbol histograms with a per-CTA shared-memory histogram (same counts as
+// JpegHistAcc + JpegHistSum in jpeg_dev.h): out[6][257] = dc0 dc1 dc2 ac0 ac1 ac2.
+__global__ void __launch_bounds__(256) k_jpeg_hist(const int16_t* cand, const int* q, const int* zigzag,
+                                                   unsigned int* out, unsigned int* chroma_nonzero, int nblocks) {
+  __shared__ unsigned int sh[kHistStride];
+  __shared__ int sq[192];
+  __shared__ int szz[64];
+  for (int i = threadIdx.x; i < kHistStride; i += 256) sh[i] = 0;
+  if (threadIdx.x < 192) sq[threadIdx.x] = q[threadIdx.x];
+  if (threadIdx.x < 64) szz[threadIdx.x] = zigzag[threadIdx.x];
+  __syncthreads();
+  const int units = 3 * nblocks;
+  bool chroma = false;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < units; i += gridDim.x * 256) {
+    const int c = i / nblocks, b = i - c * nblocks;
+    const int16_t* blk = cand + static_cast<size_t>(i) * 64;
+    const int* qc = sq + 64 * c;
+    const int prev = b > 0 ? (blk - 64)[0] / qc[0] : 0;
+    JpegHistAcc::Visitor v{sh + c * 257, sh + (3 + c) * 257};
+    visit_block_symbols(blk, qc, prev, szz, v);
+    if (c > 0) {
+      for (int k = 0; k < 64; ++k) chroma = chroma || (blk[k] != 0);
+    }
+  }
+  if (chroma) *chroma_nonzero = 1u;
+  __syncthreads();
+  for (int i = threadIdx.x; i < kHistStride; i += 256) {
+    const unsigned int n = sh[i];
+    if (n) atomicAdd(&out[i], n);
+  }
+}
+
+inline void launch_jpeg_hist(Stream s, const int16_t* cand, const int* q, const int* zigzag, unsigned int* out,
+                             unsigned int* chroma_nonzero, int nblocks) {
+  int ctas = (3 * nblocks + 255) / 256;
+  if (ctas > 592) ctas = 592;  // 148 SMs x 4
+  note_launch("jpeg_hist", s, 3.0 * nblocks);
+  k_jpeg_hist<<<ctas, 256, 0, s>>>(cand, q, zigzag, out, chroma_nonzero, nblocks);
+  note_launch_end("jpeg_hist", s);
 }
 
 // ---------------------------------------------------------------------------
