@@ -294,6 +294,8 @@ def main():
         kernels.sort(key=lambda k: -k["ms"])
         gpu_ms = sum(k["ms"] for k in kernels)
     barrier_sync(dist)
+    if dist is not None:
+        dist.destroy_process_group()
     if rank != 0:
         return
 
