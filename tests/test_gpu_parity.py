@@ -81,3 +81,31 @@ def test_full_size_properties_1080p(cuda_lib):
     a.scatter(nz, flat[nz])
     assert a.compare() == dm2[0] and parity.bits_equal(a.distmap(), dm2[1])
     a.close()
+
+
+def _large_cases():
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_large.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
+@pytest.mark.parametrize("name", sorted(_large_cases()))
+def test_process_matches_golden_full_size(cuda_lib, name):
+    """BASELINE.json full-size configurations against the reference's own answers
+    (tests/golden/make_golden_large.py: minutes to tens of minutes of CPU each)."""
+    import hashlib
+    g = _large_cases()[name]
+    gens = {
+        "noise1080p_s1234_q95": lambda: synth.noise(1080, 1920, 1234),
+        "gradnoise4k_s4321_q90": lambda: synth.gradnoise(2160, 3840, 4321),
+        "gradnoise1024_s1000_q84": lambda: synth.gradnoise(1024, 1024, 1000),
+    }
+    rgb = gens[name]()
+    assert synth.sha256(rgb) == g["input_sha256"]
+    ok, jpeg, trace, st = parity.run_process(cuda_lib, rgb, g["quality"])
+    assert ok and len(jpeg) == g["jpeg_size"]
+    assert hashlib.sha256(jpeg).hexdigest() == g["jpeg_sha256"]
+    assert hashlib.sha256(trace.encode()).hexdigest() == g["trace_sha256"]
+    assert [st.counters["number of iterations"], st.counters["number of iterations up"],
+            st.counters["number of iterations down"]] == g["iterations"]
