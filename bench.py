@@ -28,7 +28,7 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     # BASELINE.json configs[1] -- the single-GPU configuration the metric is quoted on
     "noise1080p_q95": dict(gen="noise", h=1080, w=1920, seed=1234, quality=95,
-                           cpu_sample=dict(gen="noise", h=192, w=192, seed=1234)),
+                           cpu_sample=dict(gen="noise", h=160, w=160, seed=1234)),
     "gradnoise4k_q90": dict(gen="gradnoise", h=2160, w=3840, seed=4321, quality=90,
                             cpu_sample=dict(gen="gradnoise", h=320, w=320, seed=4321)),
     "gradnoise1024_q84": dict(gen="gradnoise", h=1024, w=1024, seed=1000, quality=84,
