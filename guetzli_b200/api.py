@@ -58,6 +58,12 @@ def load_library(path=None):
     lib.gb200_process_rgb.argtypes = [P(_CParams), C.c_void_p, C.c_int, C.c_int, C.c_int, _LOG_FN,
                                       C.c_void_p, P(P(C.c_uint8)), P(C.c_size_t), P(_CStats)]
     lib.gb200_free.argtypes = [C.c_void_p]
+    lib.gb200_process_rgb_tiled_threads.argtypes = [P(_CParams), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                    P(P(C.c_uint8)), P(C.c_size_t), P(_CStats)]
+    lib.gb200_process_rgb_tiled.argtypes = [P(_CParams), C.c_void_p, C.c_int, C.c_int, _LOG_FN, C.c_void_p,
+                                            P(P(C.c_uint8)), P(C.c_size_t), P(_CStats)]
+    lib.gb200_dist_unique_id.argtypes = [C.c_void_p]
+    lib.gb200_dist_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.gb200_image_create.restype = C.c_void_p
     lib.gb200_image_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.gb200_image_create2.restype = C.c_void_p
@@ -168,6 +174,66 @@ def counters(lib=None):
     n, a, b = C.c_long(), C.c_longlong(), C.c_longlong()
     lib.gb200_counters(C.byref(n), C.byref(a), C.byref(b))
     return n.value, a.value, b.value
+
+
+def _cparams(params):
+    return _CParams(params.butteraugli_target, int(params.clear_metadata), int(params.try_420),
+                    int(params.force_420), int(params.use_silver_screen),
+                    int(params.zeroing_greedy_lookahead), int(params.new_zeroing_model))
+
+
+def _take(lib, out, out_len):
+    data = C.string_at(out, out_len.value) if out_len.value else b""
+    if out:
+        lib.gb200_free(out)
+    return data
+
+
+def process_tiled_threads(params, rgb, w, h, world, device=0, lib=None):
+    """One image decomposed into `world` row strips handled by `world` host threads
+    on one device (test entry of the strip mode) -> (ok, jpeg)."""
+    lib = lib or load_library()
+    buf = np.ascontiguousarray(np.asarray(rgb, dtype=np.uint8)).reshape(-1)
+    cp, cs = _cparams(params), _CStats()
+    out, out_len = C.POINTER(C.c_uint8)(), C.c_size_t()
+    ok = lib.gb200_process_rgb_tiled_threads(C.byref(cp), buf.ctypes.data, w, h, device, world,
+                                             C.byref(out), C.byref(out_len), C.byref(cs))
+    data = _take(lib, out, out_len)
+    if not ok and not data:
+        raise RuntimeError(_err(lib))
+    return bool(ok), data
+
+
+def dist_unique_id(lib=None):
+    lib = lib or load_library()
+    buf = (C.c_uint8 * 128)()
+    if not lib.gb200_dist_unique_id(buf):
+        raise RuntimeError(_err(lib))
+    return bytes(buf)
+
+
+def dist_init(uid, rank, world, device, lib=None):
+    lib = lib or load_library()
+    buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+    if not lib.gb200_dist_init(buf, rank, world, device):
+        raise RuntimeError(_err(lib))
+
+
+def process_tiled(params, stats, rgb, w, h, lib=None):
+    """Collective: every rank (after dist_init) passes the same image -> (ok, jpeg)."""
+    lib = lib or load_library()
+    buf = np.ascontiguousarray(np.asarray(rgb, dtype=np.uint8)).reshape(-1)
+    cp, cs = _cparams(params), _CStats()
+    out, out_len = C.POINTER(C.c_uint8)(), C.c_size_t()
+    ok = lib.gb200_process_rgb_tiled(C.byref(cp), buf.ctypes.data, w, h, C.cast(None, _LOG_FN), None,
+                                     C.byref(out), C.byref(out_len), C.byref(cs))
+    data = _take(lib, out, out_len)
+    if stats is not None:
+        stats.counters["number of iterations"] = cs.iterations
+        stats.device = {k: getattr(cs, k) for k, _ in _CStats._fields_}
+    if not ok and not data:
+        raise RuntimeError(_err(lib))
+    return bool(ok), data
 
 
 def write_jpeg(coeffs, w, h, q, lib=None):

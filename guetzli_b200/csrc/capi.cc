@@ -6,11 +6,13 @@
 
 #include <exception>
 #include <stdexcept>
+#include <thread>
 #include <string>
 #include <vector>
 
 #include <algorithm>
 
+#include "comm.h"
 #include "exact_sort.h"
 #include "jpeg_out.h"
 #include "pipeline.h"
@@ -18,6 +20,15 @@
 #include "tables.h"
 
 namespace gb200 {
+struct ThreadGroup;
+ThreadGroup* thread_group_create(int world);
+void thread_group_destroy(ThreadGroup* g);
+Comm* thread_comm_create(ThreadGroup* g, int rank);
+#if !defined(GB200_HOSTSIM)
+void nccl_unique_id(uint8_t out[128]);
+Comm* nccl_comm_create(const uint8_t id[128], int rank, int world);
+void select_device(int device);
+#endif
 long total_launches();
 long long h2d_bytes_total();
 long long d2h_bytes_total();
@@ -140,6 +151,114 @@ int gb200_image_process(gb200_image* img, const gb200_params* params, gb200_log_
     fill_stats(st, stats);
   });
   return (guarded_ok && ok) ? 1 : 0;
+}
+
+// ---- row-strip mode -------------------------------------------------------
+namespace {
+gb200::Comm* g_comm = nullptr;
+int g_comm_device = 0;
+}  // namespace
+
+int gb200_dist_unique_id(uint8_t* out128) {
+#if defined(GB200_HOSTSIM)
+  (void)out128;
+  g_err = "the CPU port has no NCCL";
+  return 0;
+#else
+  return guarded([&]() { gb200::nccl_unique_id(out128); });
+#endif
+}
+
+int gb200_dist_init(const uint8_t* id128, int rank, int world, int device) {
+#if defined(GB200_HOSTSIM)
+  (void)id128; (void)rank; (void)world; (void)device;
+  g_err = "the CPU port has no NCCL";
+  return 0;
+#else
+  return guarded([&]() {
+    gb200::select_device(device);
+    delete g_comm;
+    g_comm = gb200::nccl_comm_create(id128, rank, world);
+    g_comm_device = device;
+  });
+#endif
+}
+
+void gb200_dist_shutdown(void) {
+  guarded([&]() {
+    delete g_comm;
+    g_comm = nullptr;
+  });
+}
+
+int gb200_process_rgb_tiled(const gb200_params* params, const uint8_t* rgb, int w, int h, gb200_log_fn log,
+                            void* log_user, uint8_t** out, size_t* out_len, gb200_stats* stats) {
+  *out = nullptr;
+  *out_len = 0;
+  bool ok = false;
+  int guarded_ok = guarded([&]() {
+    if (!g_comm) throw std::runtime_error("gb200_dist_init has not been called");
+    gb200::SearchParams sp = to_search_params(params);
+    gb200::SearchStats st;
+    std::string jpeg, err;
+    ok = gb200::process_rgb_tiled(sp, rgb, w, h, g_comm_device, g_comm, log, log_user, &jpeg, &st, &err);
+    if (!ok) g_err = err;
+    if (!jpeg.empty()) {
+      *out = static_cast<uint8_t*>(malloc(jpeg.size()));
+      memcpy(*out, jpeg.data(), jpeg.size());
+      *out_len = jpeg.size();
+    }
+    fill_stats(st, stats);
+  });
+  return (guarded_ok && ok) ? 1 : 0;
+}
+
+// The same strip decomposition with `world` host threads of this process sharing one
+// device (test entry: exercises the strip kernels and the exchange without NCCL).
+int gb200_process_rgb_tiled_threads(const gb200_params* params, const uint8_t* rgb, int w, int h, int device,
+                                    int world, uint8_t** out, size_t* out_len, gb200_stats* stats) {
+  *out = nullptr;
+  *out_len = 0;
+  bool all_ok = true;
+  int guarded_ok = guarded([&]() {
+    if (world < 1 || world > 64) throw std::runtime_error("bad world size");
+    gb200::ThreadGroup* group = gb200::thread_group_create(world);
+    std::vector<std::string> jpegs(world), errs(world);
+    std::vector<gb200::SearchStats> sts(world);
+    std::vector<int> oks(world, 0);
+    std::vector<std::string> what(world);
+    std::vector<std::thread> threads;
+    gb200::SearchParams sp = to_search_params(params);
+    for (int r = 0; r < world; ++r) {
+      threads.emplace_back([&, r]() {
+        gb200::Comm* comm = gb200::thread_comm_create(group, r);
+        try {
+          oks[r] = gb200::process_rgb_tiled(sp, rgb, w, h, device, comm, nullptr, nullptr, &jpegs[r], &sts[r], &errs[r]);
+        } catch (const std::exception& e) {
+          what[r] = e.what();
+          oks[r] = -1;
+        }
+        delete comm;
+      });
+    }
+    for (auto& t : threads) t.join();
+    gb200::thread_group_destroy(group);
+    for (int r = 0; r < world; ++r) {
+      if (oks[r] < 0) throw std::runtime_error("rank " + std::to_string(r) + ": " + what[r]);
+      if (!oks[r]) {
+        all_ok = false;
+        g_err = errs[r];
+      }
+      if (jpegs[r] != jpegs[0]) throw std::runtime_error("ranks disagree on the output");
+    }
+    if (!jpegs[0].empty()) {
+      *out = static_cast<uint8_t*>(malloc(jpegs[0].size()));
+      memcpy(*out, jpegs[0].data(), jpegs[0].size());
+      *out_len = jpegs[0].size();
+    }
+    fill_stats(sts[0], stats);
+  });
+  return (guarded_ok && all_ok) ? 1 : 0;
 }
 
 void gb200_free(void* p) { free(p); }

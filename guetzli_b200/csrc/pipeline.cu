@@ -38,6 +38,60 @@ std::vector<KernelStat> profiling_snapshot();
 void profiling_reset();
 #endif
 
+namespace {
+// Runs a per-pixel functor written for "tall image" row indices (plane * h + y) on
+// the rows [y0, y0 + nrows) of each plane only.
+template <class F>
+struct RowsOf {
+  F f;
+  int y0, nrows, h;
+  GB_HD void operator()(int x, int yy) const {
+    const int pl = yy / nrows;
+    f(x, pl * h + y0 + (yy - pl * nrows));
+  }
+};
+template <class F>
+struct OffsetOf {
+  F f;
+  int i0;
+  GB_HD void operator()(int i) const { f(i0 + i); }
+};
+}  // namespace
+
+template <class F>
+void ImageContext::px(const F& f, const char* name, int nplanes) {
+  const int nrows = cr_hi_ - cr_lo_;
+  if (cr_lo_ == 0 && nrows == g_.h) {
+    launch_2d(s_, f, g_.w, g_.h * nplanes, name);
+  } else {
+    launch_2d(s_, RowsOf<F>{f, cr_lo_, nrows, g_.h}, g_.w, nrows * nplanes, name);
+  }
+}
+
+template <class F>
+void ImageContext::block_rows(const F& f, const char* name, int by_lo, int by_hi) {
+  const int n = (by_hi - by_lo) * g_.bw;
+  if (by_lo == 0) {
+    launch_1d(s_, f, n, name);
+  } else {
+    launch_1d(s_, OffsetOf<F>{f, by_lo * g_.bw}, n, name);
+  }
+}
+
+// In-place all-gather of a per-block array: every rank owns the blocks of its strip.
+void ImageContext::gather_blocks(void* dev_buf, size_t elem_bytes_per_block) {
+  if (!comm_ || comm_->world() == 1) return;
+  const int W = comm_->world();
+  std::vector<size_t> off(W), cnt(W);
+  for (int r = 0; r < W; ++r) {
+    int lo, hi;
+    strip_of(g_.bh, r, W, &lo, &hi);
+    off[r] = static_cast<size_t>(lo) * g_.bw;
+    cnt[r] = static_cast<size_t>(hi - lo) * g_.bw;
+  }
+  comm_->allgather_inplace(dev_buf, elem_bytes_per_block, off, cnt, s_);
+}
+
 float* ImageContext::planes(int n) {
   void* p = dev_alloc(sizeof(float) * g_.plane * n);
   dev_zero(p, sizeof(float) * g_.plane * n, s_);
@@ -45,8 +99,14 @@ float* ImageContext::planes(int n) {
   return static_cast<float*>(p);
 }
 
-ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device, bool prepare_now)
-    : g_(make_geom(w, h)), device_(device) {
+ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device, bool prepare_now, Comm* comm)
+    : g_(make_geom(w, h)), device_(device), comm_(comm) {
+  by_lo_ = 0;
+  by_hi_ = g_.bh;
+  if (comm_ && comm_->world() > 1) strip_of(g_.bh, comm_->rank(), comm_->world(), &by_lo_, &by_hi_);
+  // rows whose distmap this rank must produce, widened by the metric's receptive field
+  cr_lo_ = std::max(0, 8 * by_lo_ - 56);
+  cr_hi_ = std::min(g_.h, 8 * by_hi_ + 56);
   select_device(device);
   s_ = make_stream();
   t_ = build_tables(w, h, s_, &owned_, &ht_);
@@ -164,17 +224,17 @@ void ImageContext::prepare() {
     return;
   }
   // a3: PsychoImage of the original (pi0_), resident for the whole search.
-  launch_2d(s_, LinearizeRgb{d_rgb_, lin_, g_, t_.srgb_lin}, g_.w, g_.h, "linearize_rgb");
+  px(LinearizeRgb{d_rgb_, lin_, g_, t_.srgb_lin}, "linearize_rgb");
   opsin(lin_, xyb_);
   separate(xyb_, ps0_);
 
   // a13: mask_xyz_ = Mask(xyb0, xyb0), only its block-corner samples are ever read.
-  launch_2d(s_, MaskDiffPreSelf{xyb_, mpre_, g_}, g_.w, g_.h, "mask_diff_pre_self");
+  px(MaskDiffPreSelf{xyb_, mpre_, g_}, "mask_diff_pre_self");
   blur(mpre_, sact_, 1, kBlurMaskX);
   blur(mpre_ + g_.plane, sact_ + g_.plane, 1, kBlurMaskY0);
   blur(mpre_ + g_.plane, sact_ + 2 * g_.plane, 1, kBlurMaskY1);
-  launch_1d(s_, BlockCornerMask{sact_, sact_ + g_.plane, sact_ + 2 * g_.plane, corner_mask_, g_, t_.mask_lut},
-            g_.nblocks, "block_corner_mask");
+  block_rows(BlockCornerMask{sact_, sact_ + g_.plane, sact_ + 2 * g_.plane, corner_mask_, g_, t_.mask_lut},
+             "block_corner_mask", by_lo_, by_hi_);
   stream_sync(s_);
 }
 
@@ -193,25 +253,25 @@ ImageContext::~ImageContext() {
 
 void ImageContext::blur(const float* in, float* out, int nplanes, int id) {
 #if defined(GB200_HOSTSIM)
-  launch_2d(s_, BlurX{in, tmp_, t_.blur[id], g_}, g_.w, g_.h * nplanes, "blur_x");
-  launch_2d(s_, BlurY{tmp_, out, t_.blur[id], g_}, g_.w, g_.h * nplanes, "blur_y");
+  px(BlurX{in, tmp_, t_.blur[id], g_}, "blur_x", nplanes);
+  px(BlurY{tmp_, out, t_.blur[id], g_}, "blur_y", nplanes);
 #else
-  launch_blur_tiled(s_, in, tmp_, out, nplanes, t_.blur[id], ht_.blur_taps_n[id].data(), g_);
+  launch_blur_tiled(s_, in, tmp_, out, nplanes, t_.blur[id], ht_.blur_taps_n[id].data(), g_, cr_lo_, cr_hi_ - cr_lo_);
 #endif
 }
 
 void ImageContext::opsin(const float* lin, float* xyb) {
   blur(lin, blr_, 3, kBlurOpsin);
-  launch_2d(s_, OpsinPx{lin, blr_, xyb, g_}, g_.w, g_.h, "opsin_px");
+  px(OpsinPx{lin, blr_, xyb, g_}, "opsin_px");
 }
 
 void ImageContext::separate(const float* xyb, float* ps) {
   blur(xyb, lf_, 3, kBlurLf);
-  launch_2d(s_, SubPlanes{xyb, lf_, mf_in_, g_}, g_.w, 3 * g_.h, "sub_planes");
+  px(SubPlanes{xyb, lf_, mf_in_, g_}, "sub_planes", 3);
   blur(mf_in_, mf_blr_, 3, kBlurMf);
-  launch_2d(s_, SplitMfHf{mf_in_, mf_blr_, ps, hf_raw_, g_}, g_.w, g_.h, "split_mf_hf");
+  px(SplitMfHf{mf_in_, mf_blr_, ps, hf_raw_, g_}, "split_mf_hf");
   blur(hf_raw_, hf_blr_, 2, kBlurHf);
-  launch_2d(s_, SplitHfUhf{hf_raw_, hf_blr_, lf_, ps, g_}, g_.w, g_.h, "split_hf_uhf");
+  px(SplitHfUhf{hf_raw_, hf_blr_, lf_, ps, g_}, "split_hf_uhf");
 }
 
 void ImageContext::apply_global_quant(const int q[192]) {
@@ -262,8 +322,20 @@ void ImageContext::download_candidate(int16_t* coeffs) {
 float ImageContext::compare() {
   const size_t P = g_.plane;
   // S0 render (only blocks edited since the last render), S1 opsin, S2-S6 frequency split
-  if (render_all_ || dirty_list_.size() > static_cast<size_t>(g_.nblocks) / 2) {
-    launch_1d(s_, RenderBlocks{d_cand_, lin_, g_, t_}, g_.nblocks, "render_blocks");
+  const int rb_lo = cr_lo_ / 8, rb_hi = (cr_hi_ + 7) / 8;  // block rows that intersect the computed rows
+  if (comm_ && comm_->world() > 1 && !render_all_) {
+    // strip mode: only edited blocks inside the computed rows need new pixels
+    size_t keep = 0;
+    for (size_t i = 0; i < dirty_list_.size(); ++i) {
+      const int by = dirty_list_[i] / g_.bw;
+      dirty_flag_[dirty_list_[i]] = 0;
+      if (by >= rb_lo && by < rb_hi) dirty_list_[keep++] = dirty_list_[i];
+    }
+    dirty_list_.resize(keep);
+    for (size_t i = 0; i < keep; ++i) dirty_flag_[dirty_list_[i]] = 1;
+  }
+  if (render_all_ || dirty_list_.size() > static_cast<size_t>(rb_hi - rb_lo) * g_.bw / 2) {
+    block_rows(RenderBlocks{d_cand_, lin_, g_, t_}, "render_blocks", rb_lo, rb_hi);
   } else if (!dirty_list_.empty()) {
     const int nd = static_cast<int>(dirty_list_.size());
     h2d(d_dirty_, dirty_list_.data(), sizeof(int) * nd, s_);
@@ -280,7 +352,7 @@ float ImageContext::compare() {
   static const int kMaltaAcc[6] = {1, 0, 1, 0, 1, 0};
   for (int i = 0; i < 6; ++i) {
     const int pl = kMaltaPlane[i];
-    launch_2d(s_, MaltaPre{ps0_ + pl * P, ps1_ + pl * P, diffs_, malta_[i], g_}, g_.w, g_.h, "malta_pre");
+    px(MaltaPre{ps0_ + pl * P, ps1_ + pl * P, diffs_, malta_[i], g_}, "malta_pre");
     MaltaAcc acc;
     acc.diffs = diffs_;
     acc.acc = ac_ + kMaltaAcc[i] * P;
@@ -289,7 +361,7 @@ float ImageContext::compare() {
     acc.stride = i < 2 ? 9 : 5;
     acc.first = i < 2 ? 1 : 0;
     acc.g = g_;
-    launch_2d(s_, acc, g_.w, g_.h, i < 2 ? "malta_acc_hf" : "malta_acc_lf");
+    px(acc, i < 2 ? "malta_acc_hf" : "malta_acc_lf");
   }
 #else
   for (int ch = 0; ch < 2; ++ch) {  // 0 = X, 1 = Y
@@ -303,26 +375,28 @@ float ImageContext::compare() {
     }
     a.acc = ac_ + ch * P;
     a.g = g_;
+    a.y0 = cr_lo_;
+    a.nrows = cr_hi_ - cr_lo_;
     launch_malta_channel(s_, a);
   }
 #endif
   // S8 + S9 on block_diff_ac[Y]
-  launch_2d(s_, NoisePre{ps0_ + kHfY * P, ps1_ + kHfY * P, noise_, g_}, g_.w, g_.h, "noise_pre");
+  px(NoisePre{ps0_ + kHfY * P, ps1_ + kHfY * P, noise_, g_}, "noise_pre");
   blur(noise_, noise_ + P, 1, kBlurNoise);
-  launch_2d(s_, NoiseAndAsymAcc{noise_ + P, ps0_ + kHfY * P, ps1_ + kHfY * P, ac_ + P, asym_w0_, asym_w1_, g_},
-            g_.w, g_.h, "noise_asym_acc");
+  px(NoiseAndAsymAcc{noise_ + P, ps0_ + kHfY * P, ps1_ + kHfY * P, ac_ + P, asym_w0_, asym_w1_, g_},
+     "noise_asym_acc");
   // S10 mask
-  launch_2d(s_, MaskDiffPre{ps0_, ps1_, mpre_, g_}, g_.w, g_.h, "mask_diff_pre");
+  px(MaskDiffPre{ps0_, ps1_, mpre_, g_}, "mask_diff_pre");
   blur(mpre_, sact_, 1, kBlurMaskX);
   blur(mpre_ + P, sact_ + P, 1, kBlurMaskY0);
   blur(mpre_ + P, sact_ + 2 * P, 1, kBlurMaskY1);
   // S11 + S12
-  launch_2d(s_, CombineAndSqrt{ps0_, ps1_, ac_, sact_, sact_ + P, sact_ + 2 * P, dm_, g_, t_.mask_lut}, g_.w,
-            g_.h, "combine_sqrt");
+  px(CombineAndSqrt{ps0_, ps1_, ac_, sact_, sact_ + P, sact_ + 2 * P, dm_, g_, t_.mask_lut}, "combine_sqrt");
   blur(dm_, dm_ + P, 1, kBlurFinal);
-  launch_2d(s_, DiffmapMix{dm_ + P, dm_, g_}, g_.w, g_.h, "diffmap_mix");
+  px(DiffmapMix{dm_ + P, dm_, g_}, "diffmap_mix");
   // S13 + a15 first half
-  launch_1d(s_, BlockMax{dm_, block_max_, g_}, g_.nblocks, "block_max");
+  block_rows(BlockMax{dm_, block_max_, g_}, "block_max", by_lo_, by_hi_);
+  gather_blocks(block_max_, sizeof(float));  // strip mode: one float per block crosses NVLink
   const int lanes = 1024;
   launch_1d(s_, PartialMax{block_max_, partial_, g_.nblocks, lanes}, lanes, "partial_max");
   float part[1024];
@@ -388,7 +462,7 @@ void ImageContext::zeroing_orders(float block_error_limit, int lookahead, std::v
   z.lookahead = lookahead;
   z.block_error_limit = block_error_limit;
 #if defined(GB200_HOSTSIM)
-  launch_1d(s_, z, g_.nblocks, "zeroing_orders");
+  block_rows(z, "zeroing_orders", by_lo_, by_hi_);
 #else
   {
     ZeroingWarpArgs zw;
@@ -403,9 +477,15 @@ void ImageContext::zeroing_orders(float block_error_limit, int lookahead, std::v
     zw.t = t_;
     zw.lookahead = lookahead;
     zw.block_error_limit = block_error_limit;
+    zw.b0 = by_lo_ * g_.bw;
+    zw.nb = (by_hi_ - by_lo_) * g_.bw;
     launch_zeroing_orders_warp(s_, zw);
   }
 #endif
+  // strip mode: the lists of the other strips
+  gather_blocks(d_idx, 192);
+  gather_blocks(d_err, 192 * sizeof(float));
+  gather_blocks(d_cnt, sizeof(int));
   idx->resize(slots);
   err->resize(slots);
   count->resize(g_.nblocks);

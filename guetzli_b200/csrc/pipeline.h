@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "comm.h"
 #include "kernels.h"
 #include "tables.h"
 
@@ -23,7 +24,9 @@ class ImageContext {
  public:
   // Uploads the image, runs the one-time kernels (a2 FDCT, a3 PsychoImage of the
   // original, a13 block-corner masks).  rgb: interleaved sRGB u8, w*h*3.
-  ImageContext(const uint8_t* rgb, int w, int h, int device, bool prepare_now = true);
+  // comm != nullptr: row-strip mode, this context computes block rows strip_of(rank)
+  // of the image-plane work and all-gathers the per-block results (comm.h).
+  ImageContext(const uint8_t* rgb, int w, int h, int device, bool prepare_now = true, Comm* comm = nullptr);
   // the one-time kernels (idempotent); split from the upload so that a caller can
   // time the job with the image already resident in HBM
   void prepare();
@@ -94,6 +97,11 @@ class ImageContext {
 
  private:
   void blur(const float* in, float* out, int nplanes, int id);
+  template <class F>
+  void px(const F& f, const char* name, int nplanes = 1);  // rows [cr_lo_, cr_hi_) of nplanes planes
+  template <class F>
+  void block_rows(const F& f, const char* name, int by_lo, int by_hi);  // blocks of block rows [by_lo, by_hi)
+  void gather_blocks(void* dev_buf, size_t elem_bytes_per_block);
   void opsin(const float* lin, float* xyb);
   void separate(const float* xyb, float* ps);
   void upload_planes(const float* packed, float* dst, int n);
@@ -103,6 +111,9 @@ class ImageContext {
   Geom g_;
   int device_;
   bool metric_;
+  Comm* comm_;
+  int by_lo_, by_hi_;  // owned block rows
+  int cr_lo_, cr_hi_;  // pixel rows computed by the image-plane kernels (strip + 56-row halo)
   bool prepared_;
   Stream s_;
   Tables t_;

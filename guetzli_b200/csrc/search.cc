@@ -805,6 +805,11 @@ bool process_resident(const SearchParams& params, ImageContext* ctx, LogSink log
 
 bool process_rgb(const SearchParams& params, const uint8_t* rgb, int w, int h, int device, LogSink log,
                  void* log_user, std::string* jpeg_out, SearchStats* stats, std::string* err) {
+  return process_rgb_tiled(params, rgb, w, h, device, nullptr, log, log_user, jpeg_out, stats, err);
+}
+
+bool process_rgb_tiled(const SearchParams& params, const uint8_t* rgb, int w, int h, int device, Comm* comm,
+                       LogSink log, void* log_user, std::string* jpeg_out, SearchStats* stats, std::string* err) {
   SearchStats local;
   SearchStats* st = stats ? stats : &local;
   *st = SearchStats();
@@ -822,7 +827,7 @@ bool process_rgb(const SearchParams& params, const uint8_t* rgb, int w, int h, i
   }
   Clock::time_point t0 = Clock::now();
   const long long h2d0 = h2d_bytes_total();
-  ImageContext ctx(rgb, w, h, device, false);
+  ImageContext ctx(rgb, w, h, device, false, comm);
   st->ms_device_setup = ms_since(t0);
   const bool ok = process_resident(params, &ctx, log, log_user, jpeg_out, st, err);
   st->h2d_bytes = h2d_bytes_total() - h2d0;

@@ -41,6 +41,13 @@ class ImageContext;
 bool process_resident(const SearchParams& params, ImageContext* ctx, LogSink log, void* log_user,
                       std::string* jpeg_out, SearchStats* stats, std::string* err);
 
+class Comm;
+// Row-strip mode: a collective call, every rank passes the same image and
+// parameters and receives the same JPEG; rank r computes the image-plane kernels of
+// block rows strip_of(r) (comm.h).  The scalar search runs redundantly on every rank.
+bool process_rgb_tiled(const SearchParams& params, const uint8_t* rgb, int w, int h, int device, Comm* comm,
+                       LogSink log, void* log_user, std::string* jpeg_out, SearchStats* stats, std::string* err);
+
 // Returns true on success; *jpeg_out receives the best JPEG found (possibly
 // empty on failure), error text goes to err (and stderr, like the reference).
 bool process_rgb(const SearchParams& params, const uint8_t* rgb, int w, int h, int device, LogSink log,

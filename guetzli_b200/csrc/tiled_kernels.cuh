@@ -29,6 +29,7 @@ struct MaltaChannelArgs {
   MaltaParams mp[3];
   float* acc;            // block_diff_ac plane of this channel (overwritten)
   Geom g;
+  int y0, nrows;         // rows [y0, y0 + nrows) are produced
 };
 
 #define GB_MALTA_TILE_W 32
@@ -39,7 +40,8 @@ struct MaltaChannelArgs {
 __global__ void __launch_bounds__(256) k_malta_channel(MaltaChannelArgs a) {
   __shared__ float tile[GB_MALTA_SH * GB_MALTA_SW];
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
-  const int x0 = blockIdx.x * GB_MALTA_TILE_W, y0 = blockIdx.y * GB_MALTA_TILE_H;
+  const int x0 = blockIdx.x * GB_MALTA_TILE_W, y0 = a.y0 + blockIdx.y * GB_MALTA_TILE_H;
+  const int y_end = a.y0 + a.nrows < a.g.h ? a.y0 + a.nrows : a.g.h;
   const int tid = ty * 32 + tx;
   float r0 = 0.0f, r1 = 0.0f;
 #pragma unroll 1
@@ -79,14 +81,14 @@ __global__ void __launch_bounds__(256) k_malta_channel(MaltaChannelArgs a) {
   const int x = x0 + tx;
   if (x < a.g.w) {
     const int ya = y0 + ty, yb = y0 + ty + 8;
-    if (ya < a.g.h) a.acc[static_cast<size_t>(ya) * a.g.pitch + x] = r0;
-    if (yb < a.g.h) a.acc[static_cast<size_t>(yb) * a.g.pitch + x] = r1;
+    if (ya < y_end) a.acc[static_cast<size_t>(ya) * a.g.pitch + x] = r0;
+    if (yb < y_end) a.acc[static_cast<size_t>(yb) * a.g.pitch + x] = r1;
   }
 }
 
 inline void launch_malta_channel(Stream s, const MaltaChannelArgs& a) {
-  dim3 block(32, 8), grid((a.g.w + GB_MALTA_TILE_W - 1) / GB_MALTA_TILE_W, (a.g.h + GB_MALTA_TILE_H - 1) / GB_MALTA_TILE_H);
-  note_launch("malta_channel", s, static_cast<double>(a.g.w) * a.g.h);
+  dim3 block(32, 8), grid((a.g.w + GB_MALTA_TILE_W - 1) / GB_MALTA_TILE_W, (a.nrows + GB_MALTA_TILE_H - 1) / GB_MALTA_TILE_H);
+  note_launch("malta_channel", s, static_cast<double>(a.g.w) * a.nrows);
   k_malta_channel<<<grid, block, 0, s>>>(a);
   note_launch_end("malta_channel", s);
 }
@@ -107,7 +109,9 @@ struct BlurArgs {
   float* out;
   BlurTab tab;
   Geom g;
-  int rows;  // total rows = nplanes * h
+  int rows;   // rows to produce = nplanes * nrows
+  int y0;     // first row of every plane
+  int nrows;  // rows per plane
 };
 
 template <int R>
@@ -131,7 +135,11 @@ __global__ void __launch_bounds__(256) k_blur_x(BlurArgs a, BlurTaps<R> taps) {
     const int ry = i / SPAN, sx = i - ry * SPAN;
     const int x = x0 - R + sx, row = row0 + ry;
     float v = 0.0f;
-    if (row < a.rows && x >= 0 && x < a.g.w) v = a.in[static_cast<size_t>(row) * a.g.pitch + x];
+    if (row < a.rows && x >= 0 && x < a.g.w) {
+      const int pl = row / a.nrows;
+      const size_t grow = static_cast<size_t>(pl) * a.g.h + a.y0 + (row - pl * a.nrows);
+      v = a.in[grow * a.g.pitch + x];
+    }
     tile[ry][sx] = v;
   }
   __syncthreads();
@@ -140,7 +148,8 @@ __global__ void __launch_bounds__(256) k_blur_x(BlurArgs a, BlurTaps<R> taps) {
   if (row >= a.rows) return;
   const int w = a.g.w;
   const float* srow = tile[ry];
-  float* orow = a.out + static_cast<size_t>(row) * a.g.pitch;
+  const int opl = row / a.nrows;
+  float* orow = a.out + (static_cast<size_t>(opl) * a.g.h + a.y0 + (row - opl * a.nrows)) * a.g.pitch;
   // thread handles x = x0 + threadIdx.x + 32*o (o < 8): a warp reads consecutive
   // shared-memory words (no bank conflicts)
   if (x0 >= R && x0 + GB_BLURX_TW - 1 + R < w) {
@@ -187,13 +196,14 @@ __global__ void __launch_bounds__(128) k_blur_y(BlurArgs a, BlurTaps<R> taps) {
   const int x = blockIdx.x * 128 + threadIdx.x;
   if (x >= a.g.w) return;
   const int h = a.g.h;
-  const int strips = (h + GB_BLURY_R - 1) / GB_BLURY_R;
+  const int y_end = a.y0 + a.nrows < h ? a.y0 + a.nrows : h;
+  const int strips = (a.nrows + GB_BLURY_R - 1) / GB_BLURY_R;
   const int pl = blockIdx.y / strips;
-  const int yb = (blockIdx.y - pl * strips) * GB_BLURY_R;
+  const int yb = a.y0 + (blockIdx.y - pl * strips) * GB_BLURY_R;
   const float* col = a.in + static_cast<size_t>(pl) * a.g.plane + x;
   float* ocol = a.out + static_cast<size_t>(pl) * a.g.plane + x;
   const size_t pitch = a.g.pitch;
-  const bool interior = (yb >= R) && (yb + GB_BLURY_R - 1 + R < h);
+  const bool interior = (yb >= R) && (yb + GB_BLURY_R - 1 + R < h) && (yb + GB_BLURY_R <= y_end);
   if (interior) {
     float acc[GB_BLURY_R];
 #pragma unroll
@@ -213,7 +223,7 @@ __global__ void __launch_bounds__(128) k_blur_y(BlurArgs a, BlurTaps<R> taps) {
   } else {
     for (int o = 0; o < GB_BLURY_R; ++o) {
       const int y = yb + o;
-      if (y >= h) break;
+      if (y >= y_end) break;
       float sum = 0.0f;
       if (y < R || y + R >= h) {
         const int lo = y < R ? 0 : y - R;
@@ -230,35 +240,38 @@ __global__ void __launch_bounds__(128) k_blur_y(BlurArgs a, BlurTaps<R> taps) {
 
 template <int R>
 inline void launch_blur_r(Stream s, const float* in, float* tmp, float* out, int nplanes, const BlurTab& tab,
-                          const float* host_taps_n, const Geom& g) {
+                          const float* host_taps_n, const Geom& g, int y0, int nrows) {
   BlurTaps<R> taps;
   for (int j = 0; j < 2 * R + 1; ++j) taps.n[j] = host_taps_n[j];
-  BlurArgs ax{in, tmp, tab, g, nplanes * g.h};
-  dim3 bx(32, 8), gx((g.w + GB_BLURX_TW - 1) / GB_BLURX_TW, (nplanes * g.h + 7) / 8);
-  note_launch("blur_x", s, static_cast<double>(g.w) * g.h * nplanes);
+  // strip mode: the y pass reads x-pass rows outside [y0, y0+nrows) that are stale; the
+  // outputs they reach lie in the halo margin that the next stage no longer needs
+  const int xy0 = y0, xy1 = y0 + nrows;
+  BlurArgs ax{in, tmp, tab, g, nplanes * (xy1 - xy0), xy0, xy1 - xy0};
+  dim3 bx(32, 8), gx((g.w + GB_BLURX_TW - 1) / GB_BLURX_TW, (nplanes * (xy1 - xy0) + 7) / 8);
+  note_launch("blur_x", s, static_cast<double>(g.w) * (xy1 - xy0) * nplanes);
   k_blur_x<R><<<gx, bx, 0, s>>>(ax, taps);
   note_launch_end("blur_x", s);
-  BlurArgs ay{tmp, out, tab, g, nplanes * g.h};
-  const int strips = (g.h + GB_BLURY_R - 1) / GB_BLURY_R;
+  BlurArgs ay{tmp, out, tab, g, nplanes * nrows, y0, nrows};
+  const int strips = (nrows + GB_BLURY_R - 1) / GB_BLURY_R;
   dim3 gy((g.w + 127) / 128, strips * nplanes);
-  note_launch("blur_y", s, static_cast<double>(g.w) * g.h * nplanes);
+  note_launch("blur_y", s, static_cast<double>(g.w) * nrows * nplanes);
   k_blur_y<R><<<gy, 128, 0, s>>>(ay, taps);
   note_launch_end("blur_y", s);
 }
 
 // host_taps_n: the interior kernel (taps * 1/sum) as built by tables.cc.
 inline void launch_blur_tiled(Stream s, const float* in, float* tmp, float* out, int nplanes, const BlurTab& tab,
-                              const float* host_taps_n, const Geom& g) {
+                              const float* host_taps_n, const Geom& g, int y0, int nrows) {
   switch (tab.r) {
-    case 2: launch_blur_r<2>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
-    case 3: launch_blur_r<3>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
-    case 4: launch_blur_r<4>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
-    case 5: launch_blur_r<5>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
-    case 8: launch_blur_r<8>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
-    case 16: launch_blur_r<16>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
-    case 20: launch_blur_r<20>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
-    case 23: launch_blur_r<23>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
-    case 24: launch_blur_r<24>(s, in, tmp, out, nplanes, tab, host_taps_n, g); break;
+    case 2: launch_blur_r<2>(s, in, tmp, out, nplanes, tab, host_taps_n, g, y0, nrows); break;
+    case 3: launch_blur_r<3>(s, in, tmp, out, nplanes, tab, host_taps_n, g, y0, nrows); break;
+    case 4: launch_blur_r<4>(s, in, tmp, out, nplanes, tab, host_taps_n, g, y0, nrows); break;
+    case 5: launch_blur_r<5>(s, in, tmp, out, nplanes, tab, host_taps_n, g, y0, nrows); break;
+    case 8: launch_blur_r<8>(s, in, tmp, out, nplanes, tab, host_taps_n, g, y0, nrows); break;
+    case 16: launch_blur_r<16>(s, in, tmp, out, nplanes, tab, host_taps_n, g, y0, nrows); break;
+    case 20: launch_blur_r<20>(s, in, tmp, out, nplanes, tab, host_taps_n, g, y0, nrows); break;
+    case 23: launch_blur_r<23>(s, in, tmp, out, nplanes, tab, host_taps_n, g, y0, nrows); break;
+    case 24: launch_blur_r<24>(s, in, tmp, out, nplanes, tab, host_taps_n, g, y0, nrows); break;
     default: throw std::runtime_error("blur radius without a compiled kernel");
   }
 }

@@ -98,6 +98,7 @@ struct ZeroingWarpArgs {
   Tables t;
   int lookahead;
   float block_error_limit;
+  int b0, nb;  // blocks [b0, b0 + nb) are processed
 };
 
 // CompareBlock for the current pixel state: comp c uses `pc` (its trial pixels),
@@ -193,8 +194,9 @@ __device__ __forceinline__ float warp_compare_block(ZWarpState& s, const Zeroing
 __global__ void __launch_bounds__(32 * GB_ZW_WARPS) k_zeroing_orders_warp(ZeroingWarpArgs a) {
   __shared__ ZWarpState smem[GB_ZW_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.x * GB_ZW_WARPS + warp;
-  if (b >= a.g.nblocks) return;
+  const int bl = blockIdx.x * GB_ZW_WARPS + warp;
+  if (bl >= a.nb) return;
+  const int b = a.b0 + bl;
   ZWarpState& s = smem[warp];
   const Geom& g = a.g;
   const Tables& t = a.t;
@@ -308,8 +310,9 @@ __global__ void __launch_bounds__(32 * GB_ZW_WARPS) k_zeroing_orders_warp(Zeroin
 }
 
 inline void launch_zeroing_orders_warp(Stream s, const ZeroingWarpArgs& a) {
-  const int ctas = (a.g.nblocks + GB_ZW_WARPS - 1) / GB_ZW_WARPS;
-  note_launch("zeroing_orders", s, a.g.nblocks);
+  const int ctas = (a.nb + GB_ZW_WARPS - 1) / GB_ZW_WARPS;
+  if (ctas <= 0) return;
+  note_launch("zeroing_orders", s, a.nb);
   k_zeroing_orders_warp<<<ctas, 32 * GB_ZW_WARPS, 0, s>>>(a);
   note_launch_end("zeroing_orders", s);
 }

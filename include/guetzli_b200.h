@@ -69,6 +69,22 @@ int gb200_process_rgb(const gb200_params* params, const uint8_t* rgb, int w, int
                       gb200_log_fn log, void* log_user, uint8_t** out, size_t* out_len,
                       gb200_stats* stats);
 
+/* ---- one image tiled over the GPUs of a node (BASELINE configs[3]) ------------
+ * One process per GPU.  Rank 0 obtains an id, the host application distributes it
+ * (e.g. torch.distributed broadcast), every rank calls gb200_dist_init once, then
+ * gb200_process_rgb_tiled collectively with the SAME image and parameters; every
+ * rank receives the same JPEG.  Rank r runs the image-plane kernels for its strip of
+ * block rows (+56-row halo, the metric's receptive field); the per-block results
+ * cross NVLink through NCCL (in-place all-gather).  Same bytes as gb200_process_rgb. */
+int gb200_dist_unique_id(uint8_t* out128);
+int gb200_dist_init(const uint8_t* id128, int rank, int world, int device);
+void gb200_dist_shutdown(void);
+int gb200_process_rgb_tiled(const gb200_params* params, const uint8_t* rgb, int w, int h, gb200_log_fn log,
+                            void* log_user, uint8_t** out, size_t* out_len, gb200_stats* stats);
+/* test entry: the same decomposition with `world` host threads sharing one device */
+int gb200_process_rgb_tiled_threads(const gb200_params* params, const uint8_t* rgb, int w, int h, int device,
+                                    int world, uint8_t** out, size_t* out_len, gb200_stats* stats);
+
 void gb200_free(void* p);
 const char* gb200_last_error(void);
 const char* gb200_backend_name(void); /* "cuda-sm_100a" for the product library */

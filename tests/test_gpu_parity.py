@@ -109,3 +109,17 @@ def test_process_matches_golden_full_size(cuda_lib, name):
     assert hashlib.sha256(trace.encode()).hexdigest() == g["trace_sha256"]
     assert [st.counters["number of iterations"], st.counters["number of iterations up"],
             st.counters["number of iterations down"]] == g["iterations"]
+
+
+@pytest.mark.parametrize("name,world", [("bees_444x258_q95", 3), ("odd_70x51_s3_q88", 2)])
+def test_strip_mode_on_one_gpu_matches_golden(cuda_lib, name, world):
+    """Row-strip mode with the CUDA strip kernels (row-range launches, per-block
+    exchange) driven by host threads that share this GPU: same bytes as untiled."""
+    import hashlib
+    import guetzli_b200 as gb
+    g = parity.GOLDEN[name]
+    rgb = parity.golden_input(name)
+    h, w, _ = rgb.shape
+    p = gb.Params(butteraugli_target=gb.butteraugli_score_for_quality(g["quality"], lib=cuda_lib))
+    ok, jpeg = gb.process_tiled_threads(p, rgb, w, h, world, lib=cuda_lib)
+    assert ok and hashlib.sha256(jpeg).hexdigest() == g["jpeg_sha256"]
