@@ -121,6 +121,15 @@ class NcclComm : public Comm {
     ncclUniqueId uid;
     memcpy(uid.internal, id, 128);
     nccl_check(nccl().CommInitRank(&comm_, world, uid, rank), "ncclCommInitRank");
+    // NCCL sets up its channels lazily at the first collective (seconds): pay that here,
+    // not inside the first image
+    std::vector<size_t> off(world), cnt(world, 1);
+    for (int r = 0; r < world; ++r) off[r] = r;
+    void* tmp = dev_alloc(static_cast<size_t>(world) * 4);
+    dev_zero(tmp, static_cast<size_t>(world) * 4, nullptr);
+    allgather_inplace(tmp, 4, off, cnt, nullptr);
+    stream_sync(nullptr);
+    dev_free(tmp);
   }
   ~NcclComm() override {
     if (comm_) nccl().CommDestroy(comm_);
