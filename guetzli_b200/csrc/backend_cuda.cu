@@ -75,6 +75,21 @@ void* dev_alloc(size_t bytes) {
   return p;
 }
 
+// Returns every cached (currently unused) block of all devices to the driver.
+void dev_trim() {
+  DevCache& c = dev_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (std::map<std::pair<int, size_t>, std::vector<void*> >::iterator it = c.free_list.begin();
+       it != c.free_list.end(); ++it) {
+    cudaSetDevice(it->first.first);
+    for (size_t i = 0; i < it->second.size(); ++i) cudaFree(it->second[i]);
+    it->second.clear();
+  }
+  cudaSetDevice(cur);
+}
+
 void dev_free(void* p) {
   if (!p) return;
   DevCache& c = dev_cache();

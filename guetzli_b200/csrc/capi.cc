@@ -28,6 +28,7 @@ Comm* thread_comm_create(ThreadGroup* g, int rank);
 void nccl_unique_id(uint8_t out[128]);
 Comm* nccl_comm_create(const uint8_t id[128], int rank, int world);
 void select_device(int device);
+void dev_trim();
 #endif
 long total_launches();
 long long h2d_bytes_total();
@@ -398,6 +399,12 @@ void gb200_debug_std_sort(int* block, float* key, size_t n) {
     block[i] = v[i].first;
     key[i] = v[i].second;
   }
+}
+
+void gb200_trim_memory(void) {
+#if !defined(GB200_HOSTSIM)
+  guarded([&]() { gb200::dev_trim(); });
+#endif
 }
 
 void gb200_counters(long* launches, long long* h2d_bytes, long long* d2h_bytes) {

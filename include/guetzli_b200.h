@@ -139,6 +139,10 @@ int gb200_write_jpeg(const int16_t* coeffs, int w, int h, const int* q, uint8_t*
 size_t gb200_debug_partial_sort(int* block, float* key, size_t n, size_t want);
 void gb200_debug_std_sort(int* block, float* key, size_t n);
 
+/* The library keeps freed device blocks in a size-bucketed cache (cudaMalloc/cudaFree
+ * would serialise concurrent image contexts); this returns the cache to the driver. */
+void gb200_trim_memory(void);
+
 /* process-wide running totals: kernels launched, bytes copied host->device and
  * device->host by this library (all threads, all contexts) */
 void gb200_counters(long* launches, long long* h2d_bytes, long long* d2h_bytes);
