@@ -151,35 +151,28 @@ __global__ void __launch_bounds__(256) k_blur_x(BlurArgs a, BlurTaps<R> taps) {
   const int opl = row / a.nrows;
   float* orow = a.out + (static_cast<size_t>(opl) * a.g.h + a.y0 + (row - opl * a.nrows)) * a.g.pitch;
   // thread handles x = x0 + threadIdx.x + 32*o (o < 8): a warp reads consecutive
-  // shared-memory words (no bank conflicts)
-  if (x0 >= R && x0 + GB_BLURX_TW - 1 + R < w) {
-    // whole tile interior: eight independent accumulation chains per thread, each
-    // adding its products in ascending tap order
-    float acc[GB_BLURX_PT];
+  // shared-memory words (no bank conflicts).  Eight independent accumulation chains
+  // per thread, each adding its products in ascending tap order; outputs that need the
+  // border rule (only in the first / last tile of a row) are recomputed afterwards.
+  float acc[GB_BLURX_PT];
 #pragma unroll
-    for (int o = 0; o < GB_BLURX_PT; ++o) acc[o] = 0.0f;
+  for (int o = 0; o < GB_BLURX_PT; ++o) acc[o] = 0.0f;
 #pragma unroll
-    for (int j = 0; j < LEN; ++j) {
-      const float tap = taps.n[j];
+  for (int j = 0; j < LEN; ++j) {
+    const float tap = taps.n[j];
 #pragma unroll
-      for (int o = 0; o < GB_BLURX_PT; ++o) acc[o] += srow[threadIdx.x + 32 * o + j] * tap;
-    }
-#pragma unroll
-    for (int o = 0; o < GB_BLURX_PT; ++o) orow[x0 + threadIdx.x + 32 * o] = acc[o];
-    return;
+    for (int o = 0; o < GB_BLURX_PT; ++o) acc[o] += srow[threadIdx.x + 32 * o + j] * tap;
   }
-#pragma unroll 1
-  for (int o = 0; o < GB_BLURX_PT; ++o) {
-    const int xl = threadIdx.x + 32 * o;  // position inside the tile
-    const int x = x0 + xl;
-    if (x >= w) continue;
-    float sum = 0.0f;
-    if (x >= R && x + R < w) {
+  const bool tile_interior = x0 >= R && x0 + GB_BLURX_TW - 1 + R < w;
 #pragma unroll
-      for (int j = 0; j < LEN; ++j) sum += srow[xl + j] * taps.n[j];
-    } else {
+  for (int o = 0; o < GB_BLURX_PT; ++o) {
+    const int x = x0 + threadIdx.x + 32 * o;
+    if (x >= w) continue;
+    float sum = acc[o];
+    if (!tile_interior && (x < R || x + R >= w)) {
       const int lo = x < R ? 0 : x - R;
       const int hi = (x + R < w - 1) ? x + R : w - 1;
+      sum = 0.0f;
       for (int j = lo; j <= hi; ++j) sum += srow[j - x0 + R] * a.tab.taps[j - x + R];
       sum = sum * a.tab.scale_x[x];
     }
@@ -211,7 +204,8 @@ __global__ void __launch_bounds__(128) k_blur_y(BlurArgs a, BlurTaps<R> taps) {
     const float* p = col + static_cast<size_t>(yb - R) * pitch;
 #pragma unroll
     for (int t = 0; t < LEN + GB_BLURY_R - 1; ++t) {
-      const float v = p[static_cast<size_t>(t) * pitch];
+      const float v = *p;
+      p += pitch;
 #pragma unroll
       for (int o = 0; o < GB_BLURY_R; ++o) {
         const int j = t - o;  // compile-time after unrolling
