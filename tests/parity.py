@@ -40,6 +40,9 @@ def golden_input(name):
         "odd_70x51_s3_q88": lambda: synth.gradnoise(70, 51, 3),
         "gray_64x64_s9_q90": lambda: gray(64, 64, 9),
         "gradnoise_128x128_s11_q84": lambda: synth.gradnoise(128, 128, 11),
+        "min_32x32_s2_q90": lambda: synth.noise(32, 32, 2),
+        "small_33x47_s4_q95": lambda: synth.gradnoise(33, 47, 4),
+        "wide_32x200_s6_q88": lambda: synth.gradnoise(32, 200, 6),
         "flat_40x40_q95": lambda: np.full((40, 40, 3), 77, dtype=np.uint8),
     }
     return table[name]()
