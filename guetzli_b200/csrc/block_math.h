@@ -285,6 +285,16 @@ GB_HD void std_sort_replay(SortItem* a, int n) {
   }
 }
 
+// Score that orders the candidate coefficients of a block (g/processor.cc:369-393):
+// the regression tables of order.inc (new_zeroing_model, the default) or the legacy
+// formula (|orig| - zigzag_pos/64) * weight[c] / oldCsf[k].
+GB_HD float zeroing_score(int abs_orig, int idx, bool new_model, const Tables& t) {
+  if (new_model) return abs_orig * t.order_csf[idx] + t.order_bias[idx];
+  const int c = idx >> 6, k = idx & 63;
+  const double weight = c == 0 ? 1.0 : (c == 1 ? 0.22 : 0.20);
+  return static_cast<float>((abs_orig - t.nat2zz[k] / 64.0) * weight / t.order_old_csf[k]);
+}
+
 // ---------------------------------------------------------------------------
 struct ZeroingOrders {
   const int16_t* cand;   // [3][nblocks][64] after global quantisation
@@ -299,6 +309,7 @@ struct ZeroingOrders {
   const float* scale8;   // border scales of the sigma-1.2 blur on an 8-long axis
   int lookahead;         // Params::zeroing_greedy_lookahead (3)
   float block_error_limit;
+  int new_model;         // Params::new_zeroing_model
 
   // CompareBlock: pixels (YCbCr u8, full 8x8 IDCT output) -> error.
   GB_HD float compare_block(const uint8_t px[3][64], int xlast, int ylast, const float xyb0[3][64],
@@ -349,7 +360,7 @@ struct ZeroingOrders {
         const int idx = 64 * c + k;
         if (cb[k] != 0) {
           const int a = ob[k] < 0 ? -ob[k] : ob[k];
-          order[n].key = a * t.order_csf[idx] + t.order_bias[idx];
+          order[n].key = zeroing_score(a, idx, new_model != 0, t);
           order[n].id = idx;
           ++n;
         }

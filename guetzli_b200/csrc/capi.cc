@@ -337,7 +337,7 @@ int gb200_image_zeroing_orders(gb200_image* img, float block_error_limit, int lo
     std::vector<float> ve;
     std::vector<int> vc;
     img->ctx->bind();
-    img->ctx->zeroing_orders(block_error_limit, lookahead, &vi, &ve, &vc);
+    img->ctx->zeroing_orders(block_error_limit, lookahead, true, &vi, &ve, &vc);
     memcpy(idx, vi.data(), vi.size());
     memcpy(err, ve.data(), ve.size() * sizeof(float));
     memcpy(count, vc.data(), vc.size() * sizeof(int));

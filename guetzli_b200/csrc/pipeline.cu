@@ -442,7 +442,7 @@ void ImageContext::block_weights(int direction, int radius, double target_distan
   d2h(out, weights_, sizeof(float) * g_.nblocks, s_);
 }
 
-void ImageContext::zeroing_orders(float block_error_limit, int lookahead, std::vector<uint8_t>* idx,
+void ImageContext::zeroing_orders(float block_error_limit, int lookahead, bool new_model, std::vector<uint8_t>* idx,
                                   std::vector<float>* err, std::vector<int>* count) {
   const size_t slots = static_cast<size_t>(g_.nblocks) * 192;
   uint8_t* d_idx = z_idx_;
@@ -461,6 +461,7 @@ void ImageContext::zeroing_orders(float block_error_limit, int lookahead, std::v
   z.scale8 = t_.opsin_scale8;
   z.lookahead = lookahead;
   z.block_error_limit = block_error_limit;
+  z.new_model = new_model ? 1 : 0;
 #if defined(GB200_HOSTSIM)
   block_rows(z, "zeroing_orders", by_lo_, by_hi_);
 #else
@@ -477,6 +478,7 @@ void ImageContext::zeroing_orders(float block_error_limit, int lookahead, std::v
     zw.t = t_;
     zw.lookahead = lookahead;
     zw.block_error_limit = block_error_limit;
+    zw.new_model = new_model ? 1 : 0;
     zw.b0 = by_lo_ * g_.bw;
     zw.nb = (by_hi_ - by_lo_) * g_.bw;
     launch_zeroing_orders_warp(s_, zw);

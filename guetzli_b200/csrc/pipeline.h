@@ -62,7 +62,7 @@ class ImageContext {
 
   // a13+a14: greedy zeroing order of every block of the current candidate.
   // idx/err are [nblocks][192] slots, count[nblocks] valid entries each.
-  void zeroing_orders(float block_error_limit, int lookahead, std::vector<uint8_t>* idx,
+  void zeroing_orders(float block_error_limit, int lookahead, bool new_model, std::vector<uint8_t>* idx,
                       std::vector<float>* err, std::vector<int>* count);
 
   // a16: the entries of the walk order whose keys are among (at least) the k

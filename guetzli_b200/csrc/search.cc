@@ -531,7 +531,8 @@ class Search {
       Clock::time_point t0 = Clock::now();
       std::vector<uint8_t> idx;
       std::vector<float> err;
-      ctx_->zeroing_orders(params_.butteraugli_target, params_.zeroing_greedy_lookahead, &idx, &err, &count);
+      ctx_->zeroing_orders(params_.butteraugli_target, params_.zeroing_greedy_lookahead, params_.new_zeroing_model, &idx, &err,
+                           &count);
       size_t total = 0;
       for (int b = 0; b < num_blocks; ++b) total += count[b];
       m.cand_idx.reserve(total);
@@ -752,8 +753,8 @@ static bool check_params(const SearchParams& params, std::string* err) {
     fputs(err->c_str(), stderr);
     return false;
   }
-  if (params.try_420 || params.force_420 || !params.new_zeroing_model) {
-    *err = "guetzli_b200: YUV420 and the legacy zeroing model are outside the B200 hot path (DESIGN.md)\n";
+  if (params.try_420 || params.force_420) {
+    *err = "guetzli_b200: YUV420 is outside the B200 hot path (DESIGN.md)\n";
     fputs(err->c_str(), stderr);
     return false;
   }

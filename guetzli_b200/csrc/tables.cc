@@ -159,6 +159,8 @@ Tables build_tables(int w, int h, Stream s, std::vector<void*>* owned, HostTable
   }
   t.order_csf = upload(csf, s, owned);
   t.order_bias = upload(bias, s, owned);
+  t.order_old_csf = upload(std::vector<unsigned char>(kOrderOldCsf, kOrderOldCsf + 64), s, owned);
+  t.nat2zz = upload(std::vector<int>(natural_to_zigzag(), natural_to_zigzag() + 64), s, owned);
   t.block_csf = upload(std::vector<double>(kBlockCsf, kBlockCsf + 37), s, owned);
 
   // MaskX / MaskY / MaskDcX / MaskDcY (butteraugli.cc:1655-1697)

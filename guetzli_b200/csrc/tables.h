@@ -41,6 +41,8 @@ struct Tables {
   const int* zigzag;         // [64]  zig-zag scan position -> natural index
   const float* order_csf;    // [192] order.inc
   const float* order_bias;   // [192]
+  const unsigned char* order_old_csf;  // [64] legacy zeroing model, processor.cc:369
+  const int* nat2zz;         // [64] natural index -> zig-zag position
   const double* block_csf;   // [37]  butteraugli_comparator.cc:94
   const double* mask_lut;    // [4][512] MaskX, MaskY, MaskDcX, MaskDcY  butteraugli.cc:1655-1697
   const unsigned char* malta_lf;      // [16][5]

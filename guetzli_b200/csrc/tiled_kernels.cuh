@@ -163,20 +163,27 @@ __global__ void __launch_bounds__(256) k_blur_x(BlurArgs a, BlurTaps<R> taps) {
 #pragma unroll
     for (int o = 0; o < GB_BLURX_PT; ++o) acc[o] += srow[threadIdx.x + 32 * o + j] * tap;
   }
-  const bool tile_interior = x0 >= R && x0 + GB_BLURX_TW - 1 + R < w;
+  if (x0 >= R && x0 + GB_BLURX_TW - 1 + R < w) {  // whole tile interior (all but the first / last tile of a row)
+#pragma unroll
+    for (int o = 0; o < GB_BLURX_PT; ++o) orow[x0 + threadIdx.x + 32 * o] = acc[o];
+    return;
+  }
 #pragma unroll
   for (int o = 0; o < GB_BLURX_PT; ++o) {
     const int x = x0 + threadIdx.x + 32 * o;
-    if (x >= w) continue;
-    float sum = acc[o];
-    if (!tile_interior && (x < R || x + R >= w)) {
-      const int lo = x < R ? 0 : x - R;
-      const int hi = (x + R < w - 1) ? x + R : w - 1;
-      sum = 0.0f;
-      for (int j = lo; j <= hi; ++j) sum += srow[j - x0 + R] * a.tab.taps[j - x + R];
-      sum = sum * a.tab.scale_x[x];
-    }
-    orow[x] = sum;
+    if (x < w && x >= R && x + R < w) orow[x] = acc[o];
+  }
+  // border rule (blur_tap_sum's clamped window and per-column scale) for the few outputs that need it
+#pragma unroll 1
+  for (int o = 0; o < GB_BLURX_PT; ++o) {
+    const int x = x0 + threadIdx.x + 32 * o;
+    if (x >= w || (x >= R && x + R < w)) continue;
+    const int lo = x < R ? 0 : x - R;
+    const int hi = (x + R < w - 1) ? x + R : w - 1;
+    float sum = 0.0f;
+#pragma unroll 1
+    for (int j = lo; j <= hi; ++j) sum += srow[j - x0 + R] * a.tab.taps[j - x + R];
+    orow[x] = sum * a.tab.scale_x[x];
   }
 }
 

@@ -99,6 +99,7 @@ struct ZeroingWarpArgs {
   int lookahead;
   float block_error_limit;
   int b0, nb;  // blocks [b0, b0 + nb) are processed
+  int new_model;
 };
 
 // CompareBlock for the current pixel state: comp c uses `pc` (its trial pixels),
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(32 * GB_ZW_WARPS) k_zeroing_orders_warp(Zeroin
         const int idx = 64 * c + k;
         if (s.blk[idx] != 0) {
           const int v = ob[k] < 0 ? -ob[k] : ob[k];
-          s.order[n].key = v * t.order_csf[idx] + t.order_bias[idx];
+          s.order[n].key = zeroing_score(v, idx, a.new_model != 0, t);
           s.order[n].id = idx;
           ++n;
         }

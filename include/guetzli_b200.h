@@ -38,7 +38,7 @@ typedef struct gb200_params {
   int force_420;                /* 0; unsupported when set */
   int use_silver_screen;        /* 0 */
   int zeroing_greedy_lookahead; /* 3 */
-  int new_zeroing_model;        /* 1; the legacy model is unsupported */
+  int new_zeroing_model;        /* 1 = csf/bias score, 0 = legacy score (processor.cc:388-393) */
 } gb200_params;
 
 /* guetzli::ProcessStats counters (guetzli/stats.h:29-40) + device accounting. */

@@ -82,11 +82,14 @@ double gref_target_for_quality(double q) {
 void gref_free(void* p) { free(p); }
 
 // guetzli::Process(RGB) (processor.cc:926). counters = {iterations, up, down}.
-int gref_process_rgb(const uint8_t* rgb, int w, int h, float butteraugli_target,
-                     uint8_t** out, size_t* out_len, char** trace,
-                     size_t* trace_len, int* counters, double* seconds) {
+// _ex: also sets Params::zeroing_greedy_lookahead / new_zeroing_model (processor.h:35-36).
+int gref_process_rgb_ex(const uint8_t* rgb, int w, int h, float butteraugli_target, int lookahead, int new_model,
+                        uint8_t** out, size_t* out_len, char** trace, size_t* trace_len, int* counters,
+                        double* seconds) {
   guetzli::Params params;
   params.butteraugli_target = butteraugli_target;
+  params.zeroing_greedy_lookahead = lookahead;
+  params.new_zeroing_model = new_model != 0;
   guetzli::ProcessStats stats;
   std::string dbg;
   if (trace) stats.debug_output = &dbg;
@@ -111,6 +114,14 @@ int gref_process_rgb(const uint8_t* rgb, int w, int h, float butteraugli_target,
     counters[2] = stats.counters[guetzli::kNumItersDownCnt];
   }
   return ok ? 1 : 0;
+}
+
+int gref_process_rgb(const uint8_t* rgb, int w, int h, float butteraugli_target,
+                     uint8_t** out, size_t* out_len, char** trace,
+                     size_t* trace_len, int* counters, double* seconds) {
+  const guetzli::Params d;
+  return gref_process_rgb_ex(rgb, w, h, butteraugli_target, d.zeroing_greedy_lookahead, d.new_zeroing_model ? 1 : 0, out,
+                             out_len, trace, trace_len, counters, seconds);
 }
 
 // EncodeRGBToJpeg (jpeg_data_encoder.cc:66): coeffs = 3 planes of B*64 int16.

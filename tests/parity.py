@@ -115,10 +115,10 @@ def check_compare_and_blocks(lib, ref, rgb, target=0.9):
     img.close()
 
 
-def run_process(lib, rgb, quality, device=0):
+def run_process(lib, rgb, quality, device=0, **params):
     h, w, _ = rgb.shape
     st = gb.ProcessStats(debug_output=[])
-    p = gb.Params(butteraugli_target=gb.butteraugli_score_for_quality(quality, lib=lib))
+    p = gb.Params(butteraugli_target=gb.butteraugli_score_for_quality(quality, lib=lib), **params)
     ok, jpeg = gb.process(p, st, rgb, w, h, device=device, lib=lib)
     return ok, jpeg, "".join(st.debug_output), st
 
@@ -138,9 +138,11 @@ def check_golden(lib, name):
     return st
 
 
-def check_process_vs_ref(lib, ref, rgb, quality):
-    ok, jpeg, trace, st = run_process(lib, rgb, quality)
-    rok, rjpeg, rtrace, rcnt, _ = ref.process_rgb(rgb, quality)
+def check_process_vs_ref(lib, ref, rgb, quality, lookahead=3, new_zeroing_model=True):
+    ok, jpeg, trace, st = run_process(lib, rgb, quality, zeroing_greedy_lookahead=lookahead,
+                                      new_zeroing_model=new_zeroing_model)
+    rok, rjpeg, rtrace, rcnt, _ = ref.process_rgb(rgb, quality, lookahead=lookahead,
+                                                  new_zeroing_model=new_zeroing_model)
     assert ok == rok
     if trace != rtrace:
         a, b = trace.split("\n"), rtrace.split("\n")

@@ -34,7 +34,7 @@ def target_for_quality(q):
     return float(np.float32(lib().gref_target_for_quality(float(q))))
 
 
-def process_rgb(rgb, quality=95.0, trace=True):
+def process_rgb(rgb, quality=95.0, trace=True, lookahead=3, new_zeroing_model=True):
     """-> (ok, jpeg bytes, trace str, counters[3], seconds)"""
     rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
     h, w, _ = rgb.shape
@@ -44,8 +44,8 @@ def process_rgb(rgb, quality=95.0, trace=True):
     tr_len = C.c_size_t()
     counters = (C.c_int * 3)()
     secs = C.c_double()
-    ok = lib().gref_process_rgb(
-        _p(rgb, C.c_uint8), w, h, C.c_float(target_for_quality(quality)),
+    ok = lib().gref_process_rgb_ex(
+        _p(rgb, C.c_uint8), w, h, C.c_float(target_for_quality(quality)), int(lookahead), int(new_zeroing_model),
         C.byref(out), C.byref(out_len),
         C.byref(tr) if trace else None, C.byref(tr_len), counters, C.byref(secs))
     data = C.string_at(out, out_len.value)

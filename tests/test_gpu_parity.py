@@ -40,6 +40,13 @@ def test_process_matches_reference_256(cuda_lib, ref):
     assert st.device["gpu_launches"] > 0
 
 
+@pytest.mark.parametrize("lookahead,new_model", [(3, False), (1, True), (5, False)])
+def test_process_other_zeroing_params(cuda_lib, ref, lookahead, new_model):
+    """zeroing_greedy_lookahead and the legacy zeroing score (processor.cc:391)."""
+    parity.check_process_vs_ref(cuda_lib, ref, synth.gradnoise(96, 120, 12), 90, lookahead=lookahead,
+                                new_zeroing_model=new_model)
+
+
 def test_product_equals_port_on_512(cuda_lib, port_lib):
     """A larger case where the reference takes too long for a test: the CUDA
     product against the CPU restatement (itself pinned to the reference)."""

@@ -72,6 +72,14 @@ def test_rejects_low_quality_and_bad_sizes(port_lib):
     assert not ok                            # YUV420 is out of scope
 
 
+@pytest.mark.parametrize("lookahead,new_model", [(3, False), (1, True), (5, True), (2, False)])
+def test_port_process_other_zeroing_params(port_lib, ref, lookahead, new_model):
+    """Params::zeroing_greedy_lookahead / new_zeroing_model (processor.h:35-36; the
+    legacy score of processor.cc:391-392) against the reference itself."""
+    rgb = synth.gradnoise(48, 56, 11)
+    parity.check_process_vs_ref(port_lib, ref, rgb, 90, lookahead=lookahead, new_zeroing_model=new_model)
+
+
 def test_partial_order_is_arrangement_independent(port_lib, ref, monkeypatch):
     """The device returns the smallest walk-order keys in arbitrary order and equal
     keys may be arranged differently from the reference's std::sort.  The result must
