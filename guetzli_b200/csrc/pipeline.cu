@@ -377,7 +377,7 @@ float ImageContext::compare() {
     a.g = g_;
     a.y0 = cr_lo_;
     a.nrows = cr_hi_ - cr_lo_;
-    launch_malta_channel(s_, a);
+    launch_malta_channel(s_, a, tmp_);  // tmp_ (blur x-pass scratch) is free here
   }
 #endif
   // S8 + S9 on block_diff_ac[Y]

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <stdexcept>
 
 #include "ba_math.h"
@@ -32,15 +33,17 @@ struct MaltaChannelArgs {
   int y0, nrows;         // rows [y0, y0 + nrows) are produced
 };
 
-#define GB_MALTA_TILE_W 32
-#define GB_MALTA_TILE_H 16
-#define GB_MALTA_SW (GB_MALTA_TILE_W + 8)
-#define GB_MALTA_SH (GB_MALTA_TILE_H + 8)
+// Variant 0: tile 32 x 16, a thread makes the two pixels (tx, ty) and (tx, ty + 8) and
+// reads every line-sum term from shared memory.
+#define GB_MALTA0_TILE_W 32
+#define GB_MALTA0_TILE_H 16
+#define GB_MALTA0_SW (GB_MALTA0_TILE_W + 8)
+#define GB_MALTA0_SH (GB_MALTA0_TILE_H + 8)
 
-__global__ void __launch_bounds__(256) k_malta_channel(MaltaChannelArgs a) {
-  __shared__ float tile[GB_MALTA_SH * GB_MALTA_SW];
+__global__ void __launch_bounds__(256) k_malta_channel_v0(MaltaChannelArgs a) {
+  __shared__ float tile[GB_MALTA0_SH * GB_MALTA0_SW];
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
-  const int x0 = blockIdx.x * GB_MALTA_TILE_W, y0 = a.y0 + blockIdx.y * GB_MALTA_TILE_H;
+  const int x0 = blockIdx.x * GB_MALTA0_TILE_W, y0 = a.y0 + blockIdx.y * GB_MALTA0_TILE_H;
   const int y_end = a.y0 + a.nrows < a.g.h ? a.y0 + a.nrows : a.g.h;
   const int tid = ty * 32 + tx;
   float r0 = 0.0f, r1 = 0.0f;
@@ -50,8 +53,8 @@ __global__ void __launch_bounds__(256) k_malta_channel(MaltaChannelArgs a) {
     const float* l1 = a.lum1[band];
     const MaltaParams mp = a.mp[band];
     __syncthreads();
-    for (int i = tid; i < GB_MALTA_SH * GB_MALTA_SW; i += 256) {
-      const int sy = i / GB_MALTA_SW, sx = i - sy * GB_MALTA_SW;
+    for (int i = tid; i < GB_MALTA0_SH * GB_MALTA0_SW; i += 256) {
+      const int sy = i / GB_MALTA0_SW, sx = i - sy * GB_MALTA0_SW;
       const int x = x0 + sx - 4, y = y0 + sy - 4;
       float v = 0.0f;
       if (x >= 0 && x < a.g.w && y >= 0 && y < a.g.h) {
@@ -62,10 +65,10 @@ __global__ void __launch_bounds__(256) k_malta_channel(MaltaChannelArgs a) {
     }
     __syncthreads();
     float u0 = 0.0f, u1 = 0.0f;
-    const float* c0 = tile + (ty + 4) * GB_MALTA_SW + tx + 4;
-    const float* c1 = c0 + 8 * GB_MALTA_SW;
-#define GB_T0(dx, dy) c0[(dy) * GB_MALTA_SW + (dx)]
-#define GB_T1(dx, dy) c1[(dy) * GB_MALTA_SW + (dx)]
+    const float* c0 = tile + (ty + 4) * GB_MALTA0_SW + tx + 4;
+    const float* c1 = c0 + 8 * GB_MALTA0_SW;
+#define GB_T0(dx, dy) c0[(dy) * GB_MALTA0_SW + (dx)]
+#define GB_T1(dx, dy) c1[(dy) * GB_MALTA0_SW + (dx)]
     if (band == 0) {
       GB_MALTA_HF_SUMS(GB_T0, u0)
       GB_MALTA_HF_SUMS(GB_T1, u1)
@@ -86,10 +89,200 @@ __global__ void __launch_bounds__(256) k_malta_channel(MaltaChannelArgs a) {
   }
 }
 
-inline void launch_malta_channel(Stream s, const MaltaChannelArgs& a) {
-  dim3 block(32, 8), grid((a.g.w + GB_MALTA_TILE_W - 1) / GB_MALTA_TILE_W, (a.nrows + GB_MALTA_TILE_H - 1) / GB_MALTA_TILE_H);
+
+// Variants 1 and 2: tile 64 x 32 outputs per CTA (256 threads = 16 column groups x 16
+// rows); a thread makes 4 ADJACENT pixels of a row, for rows ty and ty + 16.  Its 9 x 12
+// sample window comes from shared memory as 27 float4 loads and then lives in registers:
+// every sample is loaded once per 4 pixels instead of once per line-sum term.
+#define GB_MALTA_TILE_W 64
+#define GB_MALTA_TILE_H 32
+#define GB_MALTA_SW (GB_MALTA_TILE_W + 8)
+#define GB_MALTA_SH (GB_MALTA_TILE_H + 8)
+
+// Line sums of the thread's 2 x 4 pixels for one band from the diffs tile; r += sums.
+__device__ __forceinline__ void malta_window_sums(const float* tile, int tx, int ty, bool hf, float r[2][4]) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    // window rows ty + 16k .. +8, columns 4tx .. 4tx + 11 of the tile (pixel p of the
+    // thread is at window column 4 + p, window row 4)
+    float win[9][12];
+    const float4* src = reinterpret_cast<const float4*>(tile + (ty + 16 * k) * GB_MALTA_SW + 4 * tx);
+#pragma unroll
+    for (int wy = 0; wy < 9; ++wy) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 v = src[wy * (GB_MALTA_SW / 4) + q];
+        win[wy][4 * q + 0] = v.x;
+        win[wy][4 * q + 1] = v.y;
+        win[wy][4 * q + 2] = v.z;
+        win[wy][4 * q + 3] = v.w;
+      }
+    }
+    float u0 = 0.0f, u1 = 0.0f, u2 = 0.0f, u3 = 0.0f;
+#define GB_T0(dx, dy) win[(dy) + 4][(dx) + 4]
+#define GB_T1(dx, dy) win[(dy) + 4][(dx) + 5]
+#define GB_T2(dx, dy) win[(dy) + 4][(dx) + 6]
+#define GB_T3(dx, dy) win[(dy) + 4][(dx) + 7]
+    if (hf) {
+      GB_MALTA_HF_SUMS(GB_T0, u0)
+      GB_MALTA_HF_SUMS(GB_T1, u1)
+      GB_MALTA_HF_SUMS(GB_T2, u2)
+      GB_MALTA_HF_SUMS(GB_T3, u3)
+    } else {
+      GB_MALTA_LF_SUMS(GB_T0, u0)
+      GB_MALTA_LF_SUMS(GB_T1, u1)
+      GB_MALTA_LF_SUMS(GB_T2, u2)
+      GB_MALTA_LF_SUMS(GB_T3, u3)
+    }
+#undef GB_T0
+#undef GB_T1
+#undef GB_T2
+#undef GB_T3
+    r[k][0] = r[k][0] + u0;
+    r[k][1] = r[k][1] + u1;
+    r[k][2] = r[k][2] + u2;
+    r[k][3] = r[k][3] + u3;
+  }
+}
+
+__device__ __forceinline__ void malta_store(const MaltaChannelArgs& a, int x0, int y0, int y_end, int tx, int ty,
+                                            const float r[2][4]) {
+  const int xb = x0 + 4 * tx;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int y = y0 + ty + 16 * k;
+    if (y >= y_end || xb >= a.g.w) continue;
+    float* orow = a.acc + static_cast<size_t>(y) * a.g.pitch + xb;
+    if (xb + 3 < a.g.w) {
+      *reinterpret_cast<float4*>(orow) = make_float4(r[k][0], r[k][1], r[k][2], r[k][3]);
+    } else {
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (xb + p < a.g.w) orow[p] = r[k][p];
+    }
+  }
+}
+
+// Variant 1: pre-pass fused (diffs computed into the tile by the CTA itself).
+__global__ void __launch_bounds__(256, 2) k_malta_channel_v1(MaltaChannelArgs a) {
+  __shared__ __align__(16) float tile[GB_MALTA_SH * GB_MALTA_SW];
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 16 x 16
+  const int x0 = blockIdx.x * GB_MALTA_TILE_W, y0 = a.y0 + blockIdx.y * GB_MALTA_TILE_H;
+  const int y_end = a.y0 + a.nrows < a.g.h ? a.y0 + a.nrows : a.g.h;
+  const int tid = ty * 16 + tx;
+  float r[2][4];
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) r[k][p] = 0.0f;
+#pragma unroll 1
+  for (int band = 0; band < 3; ++band) {
+    const float* l0 = a.lum0[band];
+    const float* l1 = a.lum1[band];
+    const MaltaParams mp = a.mp[band];
+    __syncthreads();
+    for (int i = tid; i < GB_MALTA_SH * GB_MALTA_SW; i += 256) {
+      const int sy = i / GB_MALTA_SW, sx = i - sy * GB_MALTA_SW;
+      const int x = x0 + sx - 4, y = y0 + sy - 4;
+      float v = 0.0f;
+      if (x >= 0 && x < a.g.w && y >= 0 && y < a.g.h) {
+        const size_t o = static_cast<size_t>(y) * a.g.pitch + x;
+        v = malta_diff(l0[o], l1[o], mp);
+      }
+      tile[i] = v;
+    }
+    __syncthreads();
+    malta_window_sums(tile, tx, ty, band == 0, r);
+  }
+  malta_store(a, x0, y0, y_end, tx, ty, r);
+}
+
+// Variant 2: the pre-pass is its own elementwise kernel (three diffs planes, zero in
+// the pad columns), and the line-sum kernel only copies tiles (cp.async, double
+// buffered over the bands, zero fill outside the plane).
+__global__ void __launch_bounds__(256) k_malta_pre3(MaltaChannelArgs a, float* diffs, int r0) {
+  const int x = blockIdx.x * 256 + threadIdx.x;
+  if (x >= a.g.pitch) return;
+  const int y = r0 + blockIdx.y, band = blockIdx.z;
+  const size_t o = static_cast<size_t>(y) * a.g.pitch + x;
+  float v = 0.0f;
+  if (x < a.g.w) v = malta_diff(a.lum0[band][o], a.lum1[band][o], a.mp[band]);
+  diffs[band * a.g.plane + o] = v;
+}
+
+__device__ __forceinline__ void cp_async16_zfill(float* smem, const float* gmem, bool valid) {
+  const unsigned int sa = static_cast<unsigned int>(__cvta_generic_to_shared(smem));
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes));
+}
+
+__device__ __forceinline__ void malta_stage_async(float* tile, const float* plane, const Geom& g, int x0, int y0,
+                                                  int tid) {
+  constexpr int Q = GB_MALTA_SW / 4;
+  for (int i = tid; i < GB_MALTA_SH * Q; i += 256) {
+    const int sy = i / Q, q = i - sy * Q;
+    const int x = x0 - 4 + 4 * q, y = y0 + sy - 4;
+    const bool valid = x >= 0 && x < g.pitch && y >= 0 && y < g.h;
+    const float* src = valid ? plane + static_cast<size_t>(y) * g.pitch + x : plane;
+    cp_async16_zfill(tile + sy * GB_MALTA_SW + 4 * q, src, valid);
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+}
+
+__global__ void __launch_bounds__(256, 2) k_malta_sums(MaltaChannelArgs a, const float* diffs) {
+  __shared__ __align__(16) float tile[2][GB_MALTA_SH * GB_MALTA_SW];
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 16 x 16
+  const int x0 = blockIdx.x * GB_MALTA_TILE_W, y0 = a.y0 + blockIdx.y * GB_MALTA_TILE_H;
+  const int y_end = a.y0 + a.nrows < a.g.h ? a.y0 + a.nrows : a.g.h;
+  const int tid = ty * 16 + tx;
+  float r[2][4];
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) r[k][p] = 0.0f;
+  malta_stage_async(tile[0], diffs, a.g, x0, y0, tid);
+#pragma unroll 1
+  for (int band = 0; band < 3; ++band) {
+    if (band + 1 < 3) {
+      malta_stage_async(tile[(band + 1) & 1], diffs + (band + 1) * a.g.plane, a.g, x0, y0, tid);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::);
+    }
+    __syncthreads();
+    malta_window_sums(tile[band & 1], tx, ty, band == 0, r);
+    __syncthreads();  // the buffer is refilled two bands later
+  }
+  malta_store(a, x0, y0, y_end, tx, ty, r);
+}
+
+// GB200_MALTA = 0 | 1 | 2 selects the variant (measurement aid; all three produce the same bits).
+inline int malta_variant() {
+  static const int v = [] {
+    const char* e = getenv("GB200_MALTA");
+    return e ? atoi(e) : 2;
+  }();
+  return v;
+}
+
+inline void launch_malta_channel(Stream s, const MaltaChannelArgs& a, float* scratch3) {
+  const int variant = malta_variant();
   note_launch("malta_channel", s, static_cast<double>(a.g.w) * a.nrows);
-  k_malta_channel<<<grid, block, 0, s>>>(a);
+  if (variant == 0) {
+    dim3 block(32, 8), grid((a.g.w + GB_MALTA0_TILE_W - 1) / GB_MALTA0_TILE_W, (a.nrows + GB_MALTA0_TILE_H - 1) / GB_MALTA0_TILE_H);
+    k_malta_channel_v0<<<grid, block, 0, s>>>(a);
+  } else {
+    dim3 block(16, 16), grid((a.g.w + GB_MALTA_TILE_W - 1) / GB_MALTA_TILE_W, (a.nrows + GB_MALTA_TILE_H - 1) / GB_MALTA_TILE_H);
+    if (variant == 1) {
+      k_malta_channel_v1<<<grid, block, 0, s>>>(a);
+    } else {
+      const int r0 = a.y0 - 4 > 0 ? a.y0 - 4 : 0;
+      const int r1 = a.y0 + a.nrows + 4 < a.g.h ? a.y0 + a.nrows + 4 : a.g.h;
+      dim3 pgrid((a.g.pitch + 255) / 256, r1 - r0, 3);
+      k_malta_pre3<<<pgrid, 256, 0, s>>>(a, scratch3, r0);
+      k_malta_sums<<<grid, block, 0, s>>>(a, scratch3);
+    }
+  }
   note_launch_end("malta_channel", s);
 }
 
@@ -119,70 +312,77 @@ struct BlurTaps {
   float n[2 * R + 1];  // taps * (1/sum)
 };
 
-// x pass: a CTA stages [8 rows][256 + 2R] samples in shared memory; a thread makes
-// 8 adjacent outputs of one row.
+// x pass: a warp owns one row segment of 256 outputs.  It stages the 256 + 2R input
+// samples in shared memory (its private row: only __syncwarp), then every lane makes 8
+// ADJACENT outputs, streaming its 8 + 2R samples once through registers into eight
+// accumulators (one shared-memory load per sample instead of one per product).  The
+// row is stored with one pad word per 8 samples, so lane l reads word 9l + const:
+// conflict-free for a fixed stream position.
 #define GB_BLURX_TW 256
 #define GB_BLURX_PT 8
 template <int R>
 __global__ void __launch_bounds__(256) k_blur_x(BlurArgs a, BlurTaps<R> taps) {
   constexpr int LEN = 2 * R + 1;
   constexpr int SPAN = GB_BLURX_TW + 2 * R;
-  __shared__ float tile[8][SPAN + 1];
-  const int tid = threadIdx.y * 32 + threadIdx.x;
+  constexpr int SROW = SPAN + SPAN / 8 + 1;
+  __shared__ float tile[8][SROW];
+  const int lane = threadIdx.x;
   const int x0 = blockIdx.x * GB_BLURX_TW;
-  const int row0 = blockIdx.y * 8;
-  for (int i = tid; i < 8 * SPAN; i += 256) {
-    const int ry = i / SPAN, sx = i - ry * SPAN;
-    const int x = x0 - R + sx, row = row0 + ry;
-    float v = 0.0f;
-    if (row < a.rows && x >= 0 && x < a.g.w) {
-      const int pl = row / a.nrows;
-      const size_t grow = static_cast<size_t>(pl) * a.g.h + a.y0 + (row - pl * a.nrows);
-      v = a.in[grow * a.g.pitch + x];
-    }
-    tile[ry][sx] = v;
-  }
-  __syncthreads();
-  const int ry = threadIdx.y;
-  const int row = row0 + ry;
-  if (row >= a.rows) return;
+  const int row = blockIdx.y * 8 + threadIdx.y;
+  if (row >= a.rows) return;  // whole warp; no block-wide barrier below
   const int w = a.g.w;
-  const float* srow = tile[ry];
-  const int opl = row / a.nrows;
-  float* orow = a.out + (static_cast<size_t>(opl) * a.g.h + a.y0 + (row - opl * a.nrows)) * a.g.pitch;
-  // thread handles x = x0 + threadIdx.x + 32*o (o < 8): a warp reads consecutive
-  // shared-memory words (no bank conflicts).  Eight independent accumulation chains
-  // per thread, each adding its products in ascending tap order; outputs that need the
-  // border rule (only in the first / last tile of a row) are recomputed afterwards.
+  const int pl = row / a.nrows;
+  const size_t grow = (static_cast<size_t>(pl) * a.g.h + a.y0 + (row - pl * a.nrows)) * a.g.pitch;
+  const float* irow = a.in + grow;
+  float* orow = a.out + grow;
+  float* srow = tile[threadIdx.y];
+#pragma unroll 4
+  for (int sx = lane; sx < SPAN; sx += 32) {
+    const int x = x0 - R + sx;
+    srow[sx + (sx >> 3)] = (x >= 0 && x < w) ? irow[x] : 0.0f;
+  }
+  __syncwarp();
+  // outputs x0 + 8*lane + o, o < 8; sample t of the lane sits at tile column 8*lane + t
   float acc[GB_BLURX_PT];
 #pragma unroll
   for (int o = 0; o < GB_BLURX_PT; ++o) acc[o] = 0.0f;
+  const float* sl = srow + 9 * lane;
 #pragma unroll
-  for (int j = 0; j < LEN; ++j) {
-    const float tap = taps.n[j];
+  for (int t = 0; t < LEN + GB_BLURX_PT - 1; ++t) {
+    const float v = sl[t + (t >> 3)];
 #pragma unroll
-    for (int o = 0; o < GB_BLURX_PT; ++o) acc[o] += srow[threadIdx.x + 32 * o + j] * tap;
+    for (int o = 0; o < GB_BLURX_PT; ++o) {
+      const int j = t - o;  // compile-time after unrolling; ascending for every output
+      if (j >= 0 && j < LEN) acc[o] += v * taps.n[j];
+    }
   }
+  const int xb = x0 + 8 * lane;
   if (x0 >= R && x0 + GB_BLURX_TW - 1 + R < w) {  // whole tile interior (all but the first / last tile of a row)
-#pragma unroll
-    for (int o = 0; o < GB_BLURX_PT; ++o) orow[x0 + threadIdx.x + 32 * o] = acc[o];
+    float4* o4 = reinterpret_cast<float4*>(orow + xb);  // pitch, x0 multiples of 32 floats; 256-byte aligned planes
+    o4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     return;
   }
 #pragma unroll
   for (int o = 0; o < GB_BLURX_PT; ++o) {
-    const int x = x0 + threadIdx.x + 32 * o;
+    const int x = xb + o;
     if (x < w && x >= R && x + R < w) orow[x] = acc[o];
   }
-  // border rule (blur_tap_sum's clamped window and per-column scale) for the few outputs that need it
+  // border rule (blur_tap_sum's clamped window and per-column scale): at most R outputs at
+  // either end of the row, one per lane so that their serial sums run side by side
 #pragma unroll 1
-  for (int o = 0; o < GB_BLURX_PT; ++o) {
-    const int x = x0 + threadIdx.x + 32 * o;
-    if (x >= w || (x >= R && x + R < w)) continue;
+  for (int side = 0; side < 2; ++side) {
+    const int x = side == 0 ? lane : w - R + lane;
+    if (lane >= R || x < x0 || x >= x0 + GB_BLURX_TW || x >= w || (side == 1 && x < R)) continue;
     const int lo = x < R ? 0 : x - R;
     const int hi = (x + R < w - 1) ? x + R : w - 1;
+    const float* tp = a.tab.taps + (R - x);
     float sum = 0.0f;
-#pragma unroll 1
-    for (int j = lo; j <= hi; ++j) sum += srow[j - x0 + R] * a.tab.taps[j - x + R];
+#pragma unroll 4
+    for (int j = lo; j <= hi; ++j) {
+      const int c = j - x0 + R;
+      sum += srow[c + (c >> 3)] * tp[j];
+    }
     orow[x] = sum * a.tab.scale_x[x];
   }
 }
@@ -222,19 +422,52 @@ __global__ void __launch_bounds__(128) k_blur_y(BlurArgs a, BlurTaps<R> taps) {
 #pragma unroll
     for (int o = 0; o < GB_BLURY_R; ++o) ocol[static_cast<size_t>(yb + o) * pitch] = acc[o];
   } else {
+    // strip that touches the top / bottom of the plane (or the end of the row range):
+    // same streaming pass with rows outside the plane read as zero -- exact for every
+    // row whose 2R+1 taps lie inside the plane -- then the border rows are recomputed
+    // with the border rule, all (up to 8) of them in one pass over the column so that
+    // their serial sums overlap.
+    float acc[GB_BLURY_R];
+#pragma unroll
+    for (int o = 0; o < GB_BLURY_R; ++o) acc[o] = 0.0f;
+#pragma unroll
+    for (int t = 0; t < LEN + GB_BLURY_R - 1; ++t) {
+      const int yi = yb - R + t;
+      const float v = (yi >= 0 && yi < h) ? col[static_cast<size_t>(yi) * pitch] : 0.0f;
+#pragma unroll
+      for (int o = 0; o < GB_BLURY_R; ++o) {
+        const int j = t - o;
+        if (j >= 0 && j < LEN) acc[o] += v * taps.n[j];
+      }
+    }
+    bool any_border = false;
+#pragma unroll
     for (int o = 0; o < GB_BLURY_R; ++o) {
       const int y = yb + o;
-      if (y >= y_end) break;
-      float sum = 0.0f;
-      if (y < R || y + R >= h) {
-        const int lo = y < R ? 0 : y - R;
-        const int hi = (y + R < h - 1) ? y + R : h - 1;
-        for (int j = lo; j <= hi; ++j) sum += col[static_cast<size_t>(j) * pitch] * a.tab.taps[j - y + R];
-        sum = sum * a.tab.scale_y[y];
-      } else {
-        for (int j = 0; j < LEN; ++j) sum += col[static_cast<size_t>(y - R + j) * pitch] * a.tab.taps_n[j];
+      const bool border = y < R || y + R >= h;
+      any_border = any_border || (border && y < y_end);
+      if (y < y_end && !border) ocol[static_cast<size_t>(y) * pitch] = acc[o];
+    }
+    if (any_border) {  // uniform over the CTA
+#pragma unroll
+      for (int o = 0; o < GB_BLURY_R; ++o) acc[o] = 0.0f;
+      const int j_lo = yb - R > 0 ? yb - R : 0;
+      const int j_hi = yb + GB_BLURY_R - 1 + R < h - 1 ? yb + GB_BLURY_R - 1 + R : h - 1;
+      const float* raw = a.tab.taps;
+#pragma unroll 2
+      for (int j = j_lo; j <= j_hi; ++j) {
+        const float v = col[static_cast<size_t>(j) * pitch];
+#pragma unroll
+        for (int o = 0; o < GB_BLURY_R; ++o) {
+          const int k = j - (yb + o) + R;  // ascending with j for every output, as in blur_tap_sum
+          if (k >= 0 && k < LEN) acc[o] += v * raw[k];
+        }
       }
-      ocol[static_cast<size_t>(y) * pitch] = sum;
+#pragma unroll
+      for (int o = 0; o < GB_BLURY_R; ++o) {
+        const int y = yb + o;
+        if (y < y_end && (y < R || y + R >= h)) ocol[static_cast<size_t>(y) * pitch] = acc[o] * a.tab.scale_y[y];
+      }
     }
   }
 }

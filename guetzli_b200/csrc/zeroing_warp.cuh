@@ -12,19 +12,31 @@
 
 namespace gb200 {
 
+// Per-warp block state in shared memory.  Arrays whose lifetimes do not overlap share
+// storage (7.1 KB per warp instead of 11 KB: seven CTAs of four warps per SM instead of five):
+//   sort   (only while the order is built)          over  f
+//   d      (written after opsin_pixel has read lin) over  lin + tmp
+//   pw     (written after the row transforms)       over  d
 struct ZWarpState {
-  SortItem order[192];
+  uint8_t order_id[192];  // sorted candidate coefficients (component * 64 + natural index)
   int16_t blk[192];
   int16_t col[64];
   uint8_t px[3][64];
   uint8_t trial[64];
   float xyb0[3][64];
-  float lin[3][64];
-  float tmp[3][64];
+  union {
+    struct {
+      float lin[3][64];
+      float tmp[3][64];
+    };
+    double d[3][64];
+    double pw[3][40];
+  };
   float blr[3][64];
-  double d[3][64];
-  Cplx f[3][64];
-  double pw[3][40];
+  union {
+    Cplx f[3][64];
+    SortItem sort[192];
+  };
 };
 
 #define GB_ZW_WARPS 4
@@ -84,6 +96,7 @@ __device__ __forceinline__ void warp_opsin8(ZWarpState& s, const BlurTab& tab, c
     opsin_pixel(s.lin[0][i], s.lin[1][i], s.lin[2][i], s.blr[0][i], s.blr[1][i], s.blr[2][i], &out[k][0],
                 &out[k][1], &out[k][2]);
   }
+  __syncwarp();  // lin / tmp are dead from here on: the caller may overwrite them (d shares their storage)
 }
 
 struct ZeroingWarpArgs {
@@ -192,7 +205,7 @@ __device__ __forceinline__ float warp_compare_block(ZWarpState& s, const Zeroing
   return static_cast<float>(sqrt(diff));
 }
 
-__global__ void __launch_bounds__(32 * GB_ZW_WARPS) k_zeroing_orders_warp(ZeroingWarpArgs a) {
+__global__ void __launch_bounds__(32 * GB_ZW_WARPS, 7) k_zeroing_orders_warp(ZeroingWarpArgs a) {
   __shared__ ZWarpState smem[GB_ZW_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int bl = blockIdx.x * GB_ZW_WARPS + warp;
@@ -219,15 +232,23 @@ __global__ void __launch_bounds__(32 * GB_ZW_WARPS) k_zeroing_orders_warp(Zeroin
         const int idx = 64 * c + k;
         if (s.blk[idx] != 0) {
           const int v = ob[k] < 0 ? -ob[k] : ob[k];
-          s.order[n].key = zeroing_score(v, idx, a.new_model != 0, t);
-          s.order[n].id = idx;
+          s.sort[n].key = zeroing_score(v, idx, a.new_model != 0, t);
+          s.sort[n].id = idx;
           ++n;
         }
       }
     }
-    std_sort_replay(s.order, n);
+    std_sort_replay(s.sort, n);
   }
   n = __shfl_sync(0xffffffffu, n, 0);
+  __syncwarp();
+  {
+    int ids[6];
+    for (int k = 0; k < 6; ++k) ids[k] = lane + 32 * k < n ? s.sort[lane + 32 * k].id : 0;
+    __syncwarp();
+    for (int k = 0; k < 6; ++k) s.order_id[lane + 32 * k] = static_cast<uint8_t>(ids[k]);
+  }
+  __syncwarp();
   // SwitchBlock: original tile (edge-replicated) -> linear -> opsin
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
@@ -258,7 +279,7 @@ __global__ void __launch_bounds__(32 * GB_ZW_WARPS) k_zeroing_orders_warp(Zeroin
     int best_i = 0;
     const int tries = a.lookahead < n ? a.lookahead : n;
     for (int i = 0; i < tries; ++i) {
-      const int idx = s.order[i].id;
+      const int idx = s.order_id[i];
       const int c = idx >> 6;
       const int16_t saved = s.blk[idx];
       __syncwarp();
@@ -276,18 +297,18 @@ __global__ void __launch_bounds__(32 * GB_ZW_WARPS) k_zeroing_orders_warp(Zeroin
       if (lane == 0) s.blk[idx] = saved;
       __syncwarp();
     }
-    const int idx = s.order[best_i].id;
+    const int idx = s.order_id[best_i];
     __syncwarp();
     if (lane == 0) s.blk[idx] = 0;
     __syncwarp();
     warp_idct(t.idct, s.blk + 64 * (idx >> 6), s.col, s.px[idx >> 6], lane);
     // erase order[best_i]
-    SortItem moved[6];
+    uint8_t moved[6];
     int cnt = 0;
-    for (int i = best_i + lane; i + 1 < n; i += 32) moved[cnt++] = s.order[i + 1];
+    for (int i = best_i + lane; i + 1 < n; i += 32) moved[cnt++] = s.order_id[i + 1];
     __syncwarp();
     cnt = 0;
-    for (int i = best_i + lane; i + 1 < n; i += 32) s.order[i] = moved[cnt++];
+    for (int i = best_i + lane; i + 1 < n; i += 32) s.order_id[i] = moved[cnt++];
     __syncwarp();
     --n;
     if (lane == 0) {
