@@ -390,6 +390,7 @@ __global__ void __launch_bounds__(256) k_blur_x(BlurArgs a, BlurTaps<R> taps) {
 // y pass: a thread owns one column and makes GB_BLURY_R consecutive rows, streaming the
 // GB_BLURY_R + 2R input rows once (coalesced across the warp) into that many accumulators.
 #define GB_BLURY_R 8
+#define GB_BLURY_CH 16
 template <int R>
 __global__ void __launch_bounds__(128) k_blur_y(BlurArgs a, BlurTaps<R> taps) {
   constexpr int LEN = 2 * R + 1;
@@ -405,18 +406,40 @@ __global__ void __launch_bounds__(128) k_blur_y(BlurArgs a, BlurTaps<R> taps) {
   const size_t pitch = a.g.pitch;
   const bool interior = (yb >= R) && (yb + GB_BLURY_R - 1 + R < h) && (yb + GB_BLURY_R <= y_end);
   if (interior) {
+    // The GB_BLURY_R + 2R input rows are fetched in batches of GB_BLURY_CH loads that are
+    // all in flight together, one batch ahead of the arithmetic (register double buffer).
+    constexpr int NT = LEN + GB_BLURY_R - 1;
+    constexpr int NCH = (NT + GB_BLURY_CH - 1) / GB_BLURY_CH;
     float acc[GB_BLURY_R];
 #pragma unroll
     for (int o = 0; o < GB_BLURY_R; ++o) acc[o] = 0.0f;
     const float* p = col + static_cast<size_t>(yb - R) * pitch;
+    float buf[2][GB_BLURY_CH];
 #pragma unroll
-    for (int t = 0; t < LEN + GB_BLURY_R - 1; ++t) {
-      const float v = *p;
+    for (int i = 0; i < GB_BLURY_CH; ++i) {
+      if (i < NT) buf[0][i] = *p;
       p += pitch;
+    }
 #pragma unroll
-      for (int o = 0; o < GB_BLURY_R; ++o) {
-        const int j = t - o;  // compile-time after unrolling
-        if (j >= 0 && j < LEN) acc[o] += v * taps.n[j];
+    for (int c = 0; c < NCH; ++c) {
+      if (c + 1 < NCH) {
+#pragma unroll
+        for (int i = 0; i < GB_BLURY_CH; ++i) {
+          if ((c + 1) * GB_BLURY_CH + i < NT) buf[(c + 1) & 1][i] = *p;
+          p += pitch;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < GB_BLURY_CH; ++i) {
+        const int t = c * GB_BLURY_CH + i;
+        if (t < NT) {
+          const float v = buf[c & 1][i];
+#pragma unroll
+          for (int o = 0; o < GB_BLURY_R; ++o) {
+            const int j = t - o;  // compile-time after unrolling
+            if (j >= 0 && j < LEN) acc[o] += v * taps.n[j];
+          }
+        }
       }
     }
 #pragma unroll

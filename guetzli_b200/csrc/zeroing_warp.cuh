@@ -8,6 +8,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <stdexcept>
+
 #include "block_math.h"
 
 namespace gb200 {
@@ -74,20 +76,56 @@ __device__ __forceinline__ void warp_idct(const int* basis, const int16_t* blk, 
   __syncwarp();
 }
 
+// The 8-wide opsin blur (sigma 1.2: radius 2) as a fixed 5-term sum.  For output
+// position p the weights are the raw taps (border rule, p < 2 or p > 5), or the
+// normalised taps (interior); terms whose sample lies outside 0..7 get weight 0 and a
+// clamped (finite) sample: they add +-0 to a sum that starts at +0, which leaves every
+// partial sum bit-identical to blur_tap_sum's shorter loop.  sc = 1/weight for border
+// positions, 1 for interior ones (x * 1 == x).
+struct Blur8W {
+  float w[5];
+  float sc;
+};
+__device__ __forceinline__ Blur8W blur8_weights(const BlurTab& tab, const float* scale8, int p) {
+  Blur8W b;
+  const bool border = p < 2 || p + 2 >= 8;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int q = p + j - 2;
+    b.w[j] = (q < 0 || q > 7) ? 0.0f : (border ? tab.taps[j] : tab.taps_n[j]);
+  }
+  b.sc = border ? scale8[p] : 1.0f;
+  return b;
+}
+// in[stride * q], q = 0..7, is the line through the output; p its position on the line.
+__device__ __forceinline__ float blur8(const float* in, int stride, int p, const Blur8W& b) {
+  float sum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    int q = p + j - 2;
+    q = q < 0 ? 0 : (q > 7 ? 7 : q);
+    sum += in[stride * q] * b.w[j];
+  }
+  return sum * b.sc;
+}
+
+// Both passes give a lane outputs at position lane & 7 of their line (the row pass
+// x = lane & 7, the column pass y = lane & 7), so one weight set per lane serves both.
+typedef Blur8W Blur8Lane;
+
 // 8x8 linear RGB tile -> XYB (OpsinDynamicsImage on 8x8), two pixels per lane.
-__device__ __forceinline__ void warp_opsin8(ZWarpState& s, const BlurTab& tab, const float* scale8, int lane,
-                                            float out[2][3]) {
-  // row pass: 192 outputs, six per lane
+__device__ __forceinline__ void warp_opsin8(ZWarpState& s, const Blur8Lane& bw, int lane, float out[2][3]) {
+  // row pass: 192 outputs, six per lane (x = lane & 7 for all of them)
+#pragma unroll
   for (int k = 0; k < 6; ++k) {
     const int o = lane + 32 * k, c = o >> 6, i = o & 63, y = i >> 3, x = i & 7;
-    SmemRow at{s.lin[c] + 8 * y};
-    s.tmp[c][i] = blur_tap_sum(at, tab.taps, tab.taps_n, scale8, tab.r, x, 8);
+    s.tmp[c][i] = blur8(s.lin[c] + 8 * y, 1, x, bw);
   }
   __syncwarp();
+#pragma unroll
   for (int k = 0; k < 6; ++k) {
-    const int o = lane + 32 * k, c = o >> 6, i = o & 63, y = i >> 3, x = i & 7;
-    SmemCol at{s.tmp[c] + x};
-    s.blr[c][i] = blur_tap_sum(at, tab.taps, tab.taps_n, scale8, tab.r, y, 8);
+    const int c = k >> 1, y = lane & 7, x = (lane >> 3) + 4 * (k & 1);
+    s.blr[c][8 * y + x] = blur8(s.tmp[c] + x, 8, y, bw);
   }
   __syncwarp();
 #pragma unroll
@@ -117,9 +155,9 @@ struct ZeroingWarpArgs {
 
 // CompareBlock for the current pixel state: comp c uses `pc` (its trial pixels),
 // the others s.px.  Returns the error in every lane.
-__device__ __forceinline__ float warp_compare_block(ZWarpState& s, const ZeroingWarpArgs& a, int c_changed,
-                                                    const uint8_t* pc, int xlast, int ylast, const float* mask,
-                                                    int lane) {
+__device__ __forceinline__ float warp_compare_block(ZWarpState& s, const ZeroingWarpArgs& a, const Blur8Lane& bw,
+                                                    int c_changed, const uint8_t* pc, int xlast, int ylast,
+                                                    const float* mask, int lane) {
   const Tables& t = a.t;
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
@@ -137,7 +175,7 @@ __device__ __forceinline__ float warp_compare_block(ZWarpState& s, const Zeroing
   }
   __syncwarp();
   float xyb1[2][3];
-  warp_opsin8(s, t.blur[kBlurOpsin], t.opsin_scale8, lane, xyb1);
+  warp_opsin8(s, bw, lane, xyb1);
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int i = lane + 32 * k;
@@ -205,7 +243,7 @@ __device__ __forceinline__ float warp_compare_block(ZWarpState& s, const Zeroing
   return static_cast<float>(sqrt(diff));
 }
 
-__global__ void __launch_bounds__(32 * GB_ZW_WARPS, 7) k_zeroing_orders_warp(ZeroingWarpArgs a) {
+__global__ void __launch_bounds__(32 * GB_ZW_WARPS, 6) k_zeroing_orders_warp(ZeroingWarpArgs a) {
   __shared__ ZWarpState smem[GB_ZW_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int bl = blockIdx.x * GB_ZW_WARPS + warp;
@@ -260,9 +298,10 @@ __global__ void __launch_bounds__(32 * GB_ZW_WARPS, 7) k_zeroing_orders_warp(Zer
     s.lin[2][i] = t.srgb_lin[p[2]];
   }
   __syncwarp();
+  const Blur8Lane bw = blur8_weights(t.blur[kBlurOpsin], t.opsin_scale8, lane & 7);
   {
     float x0[2][3];
-    warp_opsin8(s, t.blur[kBlurOpsin], t.opsin_scale8, lane, x0);
+    warp_opsin8(s, bw, lane, x0);
 #pragma unroll
     for (int k = 0; k < 2; ++k)
 #pragma unroll
@@ -286,7 +325,7 @@ __global__ void __launch_bounds__(32 * GB_ZW_WARPS, 7) k_zeroing_orders_warp(Zer
       if (lane == 0) s.blk[idx] = 0;
       __syncwarp();
       warp_idct(t.idct, s.blk + 64 * c, s.col, s.trial, lane);
-      const float err = warp_compare_block(s, a, c, s.trial, xlast, ylast, mask, lane);
+      const float err = warp_compare_block(s, a, bw, c, s.trial, xlast, ylast, mask, lane);
       float max_err = 0;
       max_err = hd_max(max_err, err);
       if (max_err < best_err) {
@@ -332,6 +371,7 @@ __global__ void __launch_bounds__(32 * GB_ZW_WARPS, 7) k_zeroing_orders_warp(Zer
 }
 
 inline void launch_zeroing_orders_warp(Stream s, const ZeroingWarpArgs& a) {
+  if (a.t.blur[kBlurOpsin].r != 2) throw std::runtime_error("zeroing kernel: the opsin blur radius must be 2");
   const int ctas = (a.nb + GB_ZW_WARPS - 1) / GB_ZW_WARPS;
   if (ctas <= 0) return;
   note_launch("zeroing_orders", s, a.nb);
