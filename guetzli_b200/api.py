@@ -57,6 +57,8 @@ def load_library(path=None):
     lib.gb200_backend_name.restype = C.c_char_p
     lib.gb200_process_rgb.argtypes = [P(_CParams), C.c_void_p, C.c_int, C.c_int, C.c_int, _LOG_FN,
                                       C.c_void_p, P(P(C.c_uint8)), P(C.c_size_t), P(_CStats)]
+    lib.gb200_process_jpeg.argtypes = [P(_CParams), C.c_void_p, C.c_size_t, C.c_int, _LOG_FN,
+                                       C.c_void_p, P(P(C.c_uint8)), P(C.c_size_t), P(_CStats)]
     lib.gb200_free.argtypes = [C.c_void_p]
     lib.gb200_process_rgb_tiled_threads.argtypes = [P(_CParams), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                     P(P(C.c_uint8)), P(C.c_size_t), P(_CStats)]
@@ -166,6 +168,54 @@ def process(params, stats, rgb, w, h, device=0, lib=None):
         if "CUDA" in msg or "no CUDA device" in msg:
             raise RuntimeError(msg)
     return bool(ok), data
+
+
+def process_jpeg(params, stats, jpeg_in, device=0, lib=None):
+    """guetzli::Process(params, stats, jpeg_in, &out) (processor.cc:890): JPEG input
+    (4:4:4 YCbCr).  Returns (ok, jpeg_bytes) like process()."""
+    lib = lib or load_library()
+    buf = np.frombuffer(bytes(jpeg_in), dtype=np.uint8)
+    cp, cs = _cparams(params), _CStats()
+    want_log = stats is not None and (stats.debug_output is not None or stats.debug_output_file is not None)
+
+    def _sink(_user, text):
+        s = text.decode(errors="replace")
+        if stats.debug_output is not None:
+            stats.debug_output.append(s)
+        if stats.debug_output_file is not None:
+            stats.debug_output_file.write(s)
+
+    cb = _LOG_FN(_sink) if want_log else C.cast(None, _LOG_FN)
+    out, out_len = C.POINTER(C.c_uint8)(), C.c_size_t()
+    ok = lib.gb200_process_jpeg(C.byref(cp), buf.ctypes.data if buf.size else None, buf.size, device, cb, None,
+                                C.byref(out), C.byref(out_len), C.byref(cs))
+    data = C.string_at(out, out_len.value) if out_len.value else b""
+    if out:
+        lib.gb200_free(out)
+    if stats is not None:
+        stats.counters["number of iterations"] = cs.iterations
+        stats.counters["number of iterations up"] = cs.iterations_up
+        stats.counters["number of iterations down"] = cs.iterations_down
+        stats.device = {k: getattr(cs, k) for k, _ in _CStats._fields_}
+    if not ok and not data:
+        msg = _err(lib)
+        if "CUDA" in msg or "no CUDA device" in msg:
+            raise RuntimeError(msg)
+    return bool(ok), data
+
+
+def read_jpeg(jpeg_in, lib=None):
+    """ReadJpeg alone (test hook) -> (ok, dims, quantised coefficients concatenated over components)."""
+    lib = lib or load_library()
+    buf = np.frombuffer(bytes(jpeg_in), dtype=np.uint8)
+    dims = (C.c_int * 11)()
+    cap = 1 << 24
+    out = np.zeros(cap, dtype=np.int16)
+    lib.gb200_debug_read_jpeg.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
+    ok = lib.gb200_debug_read_jpeg(buf.ctypes.data, buf.size, dims, out.ctypes.data, cap)
+    d = list(dims)
+    n = sum(d[3 + 2 * c] * d[4 + 2 * c] * 64 for c in range(d[2])) if ok else 0
+    return bool(ok), d, out[:n].copy()
 
 
 def counters(lib=None):

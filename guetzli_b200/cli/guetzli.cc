@@ -1,7 +1,7 @@
 // Drop-in `guetzli` command line (guetzli/guetzli.cc:232-326): same flags, same
 // exit codes, same messages; the work goes through guetzli::Process(RGB) of
-// include/guetzli_b200_compat.h (C ABI of libguetzli_b200.so).  JPEG *input* is
-// outside the B200 hot path and is refused with exit code 1.
+// include/guetzli_b200_compat.h (C ABI of libguetzli_b200.so).  JPEG input (4:4:4)
+// goes through guetzli::Process(jpeg bytes) of the same header.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -142,9 +142,21 @@ int main(int argc, char** argv) {
       return 1;
     }
   } else {
-    fprintf(stderr, "Error reading JPG data from input file\n");
-    fprintf(stderr, "(guetzli_b200: JPEG input is outside the B200 hot path; give a PNG)\n");
-    return 1;
+    int xsize = 0, ysize = 0;
+    if (!gb200_jpeg_dimensions(reinterpret_cast<const uint8_t*>(in_data.data()), in_data.size(), &xsize, &ysize)) {
+      fprintf(stderr, "Error reading JPG data from input file\n");
+      return 1;
+    }
+    const double pixels = static_cast<double>(xsize) * ysize;
+    if (memlimit_mb != -1 &&
+        (pixels * kBytesPerPixel / (1 << 20) > memlimit_mb || memlimit_mb < kLowestMemusageMB)) {
+      fprintf(stderr, "Memory limit would be exceeded. Failing.\n");
+      return 1;
+    }
+    if (!guetzli::Process(params, &stats, in_data, &out_data)) {
+      fprintf(stderr, "Guetzli processing failed\n");
+      return 1;
+    }
   }
   WriteFileOrDie(argv[opt_idx + 1], out_data);
   return 0;

@@ -16,6 +16,7 @@
 #include "exact_sort.h"
 #include "jpeg_out.h"
 #include "pipeline.h"
+#include "jpeg_in.h"
 #include "search.h"
 #include "tables.h"
 
@@ -131,6 +132,51 @@ int gb200_process_rgb(const gb200_params* params, const uint8_t* rgb, int w, int
     fill_stats(st, stats);
   });
   return (guarded_ok && ok) ? 1 : 0;
+}
+
+int gb200_process_jpeg(const gb200_params* params, const uint8_t* jpeg_in, size_t jpeg_len, int device,
+                       gb200_log_fn log, void* log_user, uint8_t** out, size_t* out_len, gb200_stats* stats) {
+  *out = nullptr;
+  *out_len = 0;
+  bool ok = false;
+  int guarded_ok = guarded([&]() {
+    gb200::SearchParams sp = to_search_params(params);
+    gb200::SearchStats st;
+    std::string jpeg, err;
+    ok = gb200::process_jpeg(sp, jpeg_in, jpeg_len, device, log, log_user, &jpeg, &st, &err);
+    if (!ok) g_err = err;
+    if (!jpeg.empty()) {
+      *out = static_cast<uint8_t*>(malloc(jpeg.size()));
+      memcpy(*out, jpeg.data(), jpeg.size());
+      *out_len = jpeg.size();
+    }
+    fill_stats(st, stats);
+  });
+  return (guarded_ok && ok) ? 1 : 0;
+}
+
+int gb200_jpeg_dimensions(const uint8_t* jpeg_in, size_t jpeg_len, int* width, int* height) {
+  return gb200::read_jpeg_dimensions(jpeg_in, jpeg_len, width, height) ? 1 : 0;
+}
+
+int gb200_debug_read_jpeg(const uint8_t* jpeg_in, size_t jpeg_len, int* dims, int16_t* out, size_t out_cap) {
+  gb200::JpegInput jpg;
+  std::string err;
+  if (!gb200::read_jpeg(jpeg_in, jpeg_len, &jpg, &err)) {
+    g_err = err;
+    return 0;
+  }
+  dims[0] = jpg.width;
+  dims[1] = jpg.height;
+  dims[2] = static_cast<int>(jpg.components.size());
+  size_t pos = 0;
+  for (size_t c = 0; c < jpg.components.size(); ++c) {
+    dims[3 + 2 * c] = jpg.components[c].width_in_blocks;
+    dims[4 + 2 * c] = jpg.components[c].height_in_blocks;
+    for (size_t i = 0; i < jpg.components[c].coeffs.size(); ++i, ++pos)
+      if (pos < out_cap) out[pos] = jpg.components[c].coeffs[i];
+  }
+  return pos <= out_cap ? 1 : 0;
 }
 
 int gb200_image_process(gb200_image* img, const gb200_params* params, gb200_log_fn log, void* log_user,

@@ -134,7 +134,7 @@ size_t cluster_histograms(SymbolHistogram* h, size_t* num, int* index, uint8_t* 
 }
 
 int num_output_components(const CoeffImage& img) {
-  if (img.as_encoded) return 3;
+  if (img.as_encoded || img.as_read) return 3;
   const size_t n = static_cast<size_t>(img.nblocks) * 64;
   const int16_t* p = img.coeffs + n;
   for (size_t i = 0; i < 2 * n; ++i)
@@ -213,18 +213,36 @@ void build_dc_histograms(const CoeffImage& img, int ncomp, SymbolHistogram* h) {
 // Distinct quant tables in component order (g/jpeg_data.cc:70).
 struct QuantSet {
   int num;
-  int table[3][64];
-  int precision[3];
-  int comp_idx[3];
+  int table[4][64];
+  int precision[4];
+  int index[4];     // Tq written into DQT
+  int comp_idx[3];  // table position per component
+  int comp_id[3];   // component id written into SOF / SOS
 };
 QuantSet dedup_quant(const CoeffImage& img, int ncomp) {
   QuantSet qs;
   qs.num = 0;
+  for (int c = 0; c < 3; ++c) qs.comp_id[c] = c;
+  if (img.as_read) {
+    const JpegFileLayout& f = *img.as_read;
+    qs.num = f.num_tables;
+    for (int i = 0; i < f.num_tables; ++i) {
+      memcpy(qs.table[i], f.table[i], sizeof(qs.table[i]));
+      qs.precision[i] = f.precision[i];
+      qs.index[i] = f.index[i];
+    }
+    for (int c = 0; c < 3; ++c) {
+      qs.comp_idx[c] = f.comp_table[c];
+      qs.comp_id[c] = f.comp_id[c];
+    }
+    return qs;
+  }
   if (img.as_encoded) {
     qs.num = 3;
     for (int c = 0; c < 3; ++c) {
       memcpy(qs.table[c], img.q[c], sizeof(qs.table[c]));
       qs.precision[c] = 0;
+      qs.index[c] = 0;
       qs.comp_idx[c] = c;
     }
     return qs;
@@ -241,6 +259,7 @@ QuantSet dedup_quant(const CoeffImage& img, int ncomp) {
       qs.precision[qs.num] = 0;
       for (int k = 0; k < 64; ++k)
         if (img.q[c][k] > 0xff) qs.precision[qs.num] = 1;
+      qs.index[qs.num] = qs.num;
       found = qs.num++;
     }
     qs.comp_idx[c] = found;
@@ -324,8 +343,15 @@ size_t estimate_dc_bytes(const CoeffImage& img) {
 size_t jpeg_header_bytes(const CoeffImage& img) {
   const int ncomp = num_output_components(img);
   const QuantSet qs = dedup_quant(img, ncomp);
-  size_t n = 2 + 18;  // SOI, APP0
-  n += 4;             // DQT marker + length
+  size_t n = 2;  // SOI
+  if (img.meta == nullptr || img.meta->strip) {
+    n += 18;  // APP0
+  } else {
+    for (const std::string& a : img.meta->app_data) n += 1 + a.size();
+    for (const std::string& c : img.meta->com_data) n += 2 + c.size();
+  }
+  if (img.meta) n += img.meta->tail_data.size();  // counted even when stripped (g/jpeg_data_writer.cc:291)
+  n += 4;  // DQT marker + length
   for (int i = 0; i < qs.num; ++i) n += 1 + (qs.precision[i] ? 2 : 1) * 64;
   n += 10 + 3 * ncomp;  // SOF
   n += 4;               // DHT marker + length
@@ -364,17 +390,30 @@ JpegPlan plan_jpeg(const CoeffImage& img, int ncomp, SymbolHistogram* dc_h, Symb
   std::string& out = plan.prefix;
   auto byte = [&out](int b) { out.push_back(static_cast<char>(b)); };
 
-  // SOI + JFIF APP0 (g/jpeg_data_writer.cc:52-63)
-  static const uint8_t kHead[] = {0xff, 0xd8, 0xff, 0xe0, 0x00, 0x10, 0x4a, 0x46, 0x49, 0x46,
-                                  0x00, 0x01, 0x01, 0x00, 0x00, 0x01, 0x00, 0x01, 0x00, 0x00};
-  out.append(reinterpret_cast<const char*>(kHead), sizeof(kHead));
+  // SOI + JFIF APP0, or the input's APPn / COM segments (g/jpeg_data_writer.cc:52-74)
+  byte(0xff); byte(0xd8);
+  if (img.meta == nullptr || img.meta->strip) {
+    static const uint8_t kApp0[] = {0xff, 0xe0, 0x00, 0x10, 0x4a, 0x46, 0x49, 0x46, 0x00,
+                                    0x01, 0x01, 0x00, 0x00, 0x01, 0x00, 0x01, 0x00, 0x00};
+    out.append(reinterpret_cast<const char*>(kApp0), sizeof(kApp0));
+  } else {
+    for (const std::string& a : img.meta->app_data) {
+      byte(0xff);
+      out.append(a);
+    }
+    for (const std::string& c : img.meta->com_data) {
+      byte(0xff); byte(0xfe);
+      out.append(c);
+    }
+  }
+  plan.trailer = jpeg_trailer(img);
   // DQT
   {
     int len = 2;
     for (int i = 0; i < qs.num; ++i) len += 1 + (qs.precision[i] ? 2 : 1) * 64;
     byte(0xff); byte(0xdb); byte(len >> 8); byte(len & 0xff);
     for (int i = 0; i < qs.num; ++i) {
-      byte((qs.precision[i] << 4) + (img.as_encoded ? 0 : i));
+      byte((qs.precision[i] << 4) + qs.index[i]);
       for (int k = 0; k < 64; ++k) {
         const int v = qs.table[i][zz[k]];
         if (qs.precision[i]) byte(v >> 8);
@@ -391,9 +430,9 @@ JpegPlan plan_jpeg(const CoeffImage& img, int ncomp, SymbolHistogram* dc_h, Symb
     byte(img.w >> 8); byte(img.w & 0xff);
     byte(ncomp);
     for (int c = 0; c < ncomp; ++c) {
-      byte(c);
+      byte(qs.comp_id[c]);
       byte(0x11);
-      byte(img.as_encoded ? 0 : qs.comp_idx[c]);
+      byte(qs.index[qs.comp_idx[c]]);
     }
   }
   // Huffman codes: cluster DC then AC histograms
@@ -440,7 +479,7 @@ JpegPlan plan_jpeg(const CoeffImage& img, int ncomp, SymbolHistogram* dc_h, Symb
     byte(0xff); byte(0xda); byte(len >> 8); byte(len & 0xff);
     byte(ncomp);
     for (int c = 0; c < ncomp; ++c) {
-      byte(c);
+      byte(qs.comp_id[c]);
       byte((dc_index[c] << 4) | ac_index[c]);
     }
     byte(0); byte(63); byte(0);
@@ -463,7 +502,6 @@ std::string write_jpeg(const CoeffImage& img) {
   std::string out;
   out.reserve(static_cast<size_t>(img.nblocks) * 48 + 1024);
   out = plan.prefix;
-  auto byte = [&out](int b) { out.push_back(static_cast<char>(b)); };
   // entropy-coded scan, one block of each component per MCU (444)
   {
     BitSink bw(&out);
@@ -517,7 +555,7 @@ std::string write_jpeg(const CoeffImage& img) {
     }
     bw.finish();
   }
-  byte(0xff); byte(0xd9);
+  out.append(plan.trailer);
   return out;
 }
 
@@ -530,9 +568,16 @@ std::string assemble_jpeg(const JpegPlan& plan, const uint8_t* scan, size_t nbyt
     out.push_back(static_cast<char>(scan[i]));
     if (scan[i] == 0xff) out.push_back(0);
   }
-  out.push_back(static_cast<char>(0xff));
-  out.push_back(static_cast<char>(0xd9));
+  out.append(plan.trailer);
   return out;
+}
+
+std::string jpeg_trailer(const CoeffImage& img) {
+  std::string t;
+  t.push_back(static_cast<char>(0xff));
+  t.push_back(static_cast<char>(0xd9));
+  if (img.meta && !img.meta->strip) t.append(img.meta->tail_data);
+  return t;
 }
 
 }  // namespace gb200

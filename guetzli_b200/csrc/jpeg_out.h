@@ -35,6 +35,26 @@ struct SymbolHistogram {
   }
 };
 
+// What surrounds the coded image in the output file (EncodeMetadata and the tail,
+// g/jpeg_data_writer.cc:52-74,552): Params::clear_metadata keeps only a JFIF APP0.
+struct JpegMeta {
+  bool strip = true;
+  std::vector<std::string> app_data;  // marker low byte + length + payload, as read
+  std::vector<std::string> com_data;  // length + payload
+  std::string tail_data;              // bytes after EOI
+};
+
+// Component / quant-table structure of a JPEG exactly as it was read (used for the
+// "Original Out" file of JPEG input, g/processor.cc:826: the input re-serialised).
+struct JpegFileLayout {
+  int comp_id[3];
+  int comp_table[3];  // position of the component's table in the list below
+  int num_tables;
+  int table[4][64];
+  int precision[4];
+  int index[4];  // Tq
+};
+
 // Candidate image as the host sees it: dequantised coefficients (multiples of q)
 // in [3][nblocks][64] layout plus the quant tables.
 struct CoeffImage {
@@ -45,6 +65,10 @@ struct CoeffImage {
   // g/jpeg_data.cc:48): always three components and three un-deduplicated quant tables
   // that all carry table index 0.
   bool as_encoded = false;
+  // JPEG input: the file's own structure (3 components, its tables and ids) instead of
+  // SaveToJpegData's; null otherwise.
+  const JpegFileLayout* as_read = nullptr;
+  const JpegMeta* meta = nullptr;  // null = strip (JFIF APP0 only)
   const int16_t* block(int c, int b) const { return coeffs + (static_cast<size_t>(c) * nblocks + b) * 64; }
 };
 
@@ -71,6 +95,7 @@ size_t entropy_coded_bytes(const SymbolHistogram* h3, const uint8_t* depths);  /
 // histograms (which the clustering modifies).  Slots: dc0 dc1 dc2 ac0 ac1 ac2.
 struct JpegPlan {
   std::string prefix;
+  std::string trailer;
   int ncomp;
   uint8_t depth[6][256];
   uint16_t code[6][256];
@@ -78,6 +103,8 @@ struct JpegPlan {
 JpegPlan plan_jpeg(const CoeffImage& img, int ncomp, SymbolHistogram* dc_h, SymbolHistogram* ac_h);
 void host_symbol_histograms(const CoeffImage& img, int ncomp, SymbolHistogram* dc_h, SymbolHistogram* ac_h);
 std::string assemble_jpeg(const JpegPlan& plan, const uint8_t* scan, size_t nbytes);
+// EOI plus whatever follows it (the input's tail bytes unless metadata is stripped).
+std::string jpeg_trailer(const CoeffImage& img);
 
 // SaveToJpegData + WriteJpeg (strip_metadata path): the complete JPEG file.
 std::string write_jpeg(const CoeffImage& img);

@@ -126,6 +126,37 @@ struct RenderBlocks {
   }
 };
 
+// JPEG input: sRGB bytes of the decoded original (DecodeJpegToRGB for 4:4:4 input,
+// g/jpeg_data_decoder.cc:45 -> OutputImage::ToSRGB): IDCT of the dequantised
+// coefficients and the integer colour transform, image-sized interleaved u8.
+struct RenderRgb8 {
+  const int16_t* coeffs;
+  uint8_t* rgb;  // [h][w][3]
+  Geom g;
+  Tables t;
+  GB_HD void operator()(int b) const {
+    const int bx = b % g.bw, by = b / g.bw;
+    uint8_t px[3][64];
+    for (int c = 0; c < 3; ++c)
+      idct_8x8(t.idct, coeffs + (static_cast<size_t>(c) * g.nblocks + b) * 64, px[c]);
+    for (int iy = 0; iy < 8; ++iy) {
+      const int y = 8 * by + iy;
+      if (y >= g.h) break;
+      for (int ix = 0; ix < 8; ++ix) {
+        const int x = 8 * bx + ix;
+        if (x >= g.w) break;
+        int r, gg, bb;
+        ycc_to_rgb(t.cr_r, t.cb_b, t.cr_g, t.cb_g, px[0][8 * iy + ix], px[1][8 * iy + ix],
+                   px[2][8 * iy + ix], &r, &gg, &bb);
+        uint8_t* o = rgb + 3 * (static_cast<size_t>(y) * g.w + x);
+        o[0] = static_cast<uint8_t>(r);
+        o[1] = static_cast<uint8_t>(gg);
+        o[2] = static_cast<uint8_t>(bb);
+      }
+    }
+  }
+};
+
 // The same for a list of blocks (only blocks whose coefficients changed since the
 // last render need new pixels: SetCoeffBlock's incremental update,
 // g/output_image.cc:123-145).

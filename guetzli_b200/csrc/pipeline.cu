@@ -101,6 +101,22 @@ float* ImageContext::planes(int n) {
 
 ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device, bool prepare_now, Comm* comm)
     : g_(make_geom(w, h)), device_(device), comm_(comm) {
+  init(rgb, nullptr, w, h, prepare_now);
+}
+
+ImageContext::ImageContext(const int16_t* dq_coeffs, int w, int h, int device, bool prepare_now, Comm* comm)
+    : g_(make_geom(w, h)), device_(device), comm_(comm) {
+  from_coeffs_ = true;
+  init(nullptr, dq_coeffs, w, h, prepare_now);
+}
+
+void ImageContext::download_rgb(uint8_t* rgb) {
+  bind();
+  d2h(rgb, d_rgb_, static_cast<size_t>(3) * g_.w * g_.h, s_);
+}
+
+void ImageContext::init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int h, bool prepare_now) {
+  const int device = device_;
   by_lo_ = 0;
   by_hi_ = g_.bh;
   if (comm_ && comm_->world() > 1) strip_of(g_.bh, comm_->rank(), comm_->world(), &by_lo_, &by_hi_);
@@ -195,7 +211,11 @@ ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device, bool pr
   num_dirty_ = 0;
   d_dirty_ = static_cast<int*>(dev_alloc(sizeof(int) * g_.nblocks));
   owned_.push_back(d_dirty_);
-  h2d(d_rgb_, rgb, static_cast<size_t>(3) * w * h, s_);
+  if (from_coeffs_) {
+    h2d(d_orig_, dq_coeffs, static_cast<size_t>(3) * g_.nblocks * 64 * sizeof(int16_t), s_);
+  } else {
+    h2d(d_rgb_, rgb, static_cast<size_t>(3) * w * h, s_);
+  }
   stream_sync(s_);
   if (prepare_now) prepare();
 }
@@ -208,7 +228,11 @@ void ImageContext::prepare() {
   prepared_ = true;
   const size_t ncoef = static_cast<size_t>(3) * g_.nblocks * 64;
   // a2: one-time forward DCT; the host search keeps a copy of the coefficients.
-  launch_1d(s_, FdctBlocks{d_rgb_, d_orig_, g_}, g_.nblocks, "fdct_blocks");
+  if (from_coeffs_) {
+    launch_1d(s_, RenderRgb8{d_orig_, d_rgb_, g_, t_}, g_.nblocks, "render_rgb8");
+  } else {
+    launch_1d(s_, FdctBlocks{d_rgb_, d_orig_, g_}, g_.nblocks, "fdct_blocks");
+  }
   d2d(d_cand_, d_orig_, ncoef * 2, s_);
   {
     int ones[192];

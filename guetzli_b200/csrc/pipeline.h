@@ -27,9 +27,14 @@ class ImageContext {
   // comm != nullptr: row-strip mode, this context computes block rows strip_of(rank)
   // of the image-plane work and all-gathers the per-block results (comm.h).
   ImageContext(const uint8_t* rgb, int w, int h, int device, bool prepare_now = true, Comm* comm = nullptr);
+  // JPEG input (4:4:4): the original is given as dequantised DCT coefficients
+  // [3][nblocks][64]; its pixels (DecodeJpegToRGB) are rendered on the device.
+  ImageContext(const int16_t* dq_coeffs, int w, int h, int device, bool prepare_now, Comm* comm);
   // the one-time kernels (idempotent); split from the upload so that a caller can
   // time the job with the image already resident in HBM
   void prepare();
+  // sRGB bytes of the original as the metric sees it (tests)
+  void download_rgb(uint8_t* rgb);
   // makes this context's device current for the calling host thread
   void bind();
   ~ImageContext();
@@ -139,6 +144,8 @@ class ImageContext {
   float* hf_blr_;  // [2]
   float* ps1_;     // [10]
   float* diffs_;   // [1]
+  bool from_coeffs_ = false;  // original given as coefficients (JPEG input)
+  void init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int h, bool prepare_now);
   float* ac_;      // [2]
   float* noise_;   // [2] pre, blurred
   float* mpre_;    // [2]

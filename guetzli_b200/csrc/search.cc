@@ -2,6 +2,7 @@
 // this file is scalar control flow plus the (for now host-side) sequential
 // selection walk and JPEG serialisation.
 #include "search.h"
+#include "jpeg_in.h"
 
 #include <math.h>
 #include <stdarg.h>
@@ -159,19 +160,37 @@ class Search {
       for (int k = 0; k < 64; ++k) img_.q[c][k] = 1;
   }
 
+  void set_meta(const JpegMeta* meta) { img_.meta = meta; }
+
+  // JPEG input: the original's own quant tables (q_in of g/processor.cc:825), file
+  // structure and metadata.  All pointers must outlive run().
+  void set_jpeg_source(const int q_in[3][64], const JpegFileLayout* layout, const JpegMeta* meta) {
+    memcpy(q_in_, q_in, sizeof(q_in_));
+    layout_ = layout;
+    img_.meta = meta;
+    jpeg_source_ = true;
+  }
+
   void run(std::string* best_out) {
     best_ = best_out;
     const float target = params_.butteraugli_target;
-    // the q=1 JPEG is the fallback output (g/processor.cc:826-846)
-    img_.as_encoded = true;
+    // the input itself (RGB: its q=1 encoding; JPEG: the file re-serialised) is the
+    // fallback output (g/processor.cc:826-846)
+    if (jpeg_source_) {
+      set_global_quant(q_in_);  // coefficients are multiples of q_in: values unchanged
+      img_.as_read = layout_;
+    } else {
+      img_.as_encoded = true;
+    }
     const size_t encoded = encoded_size();
     logf("Original Out[%7zd]", encoded);
     compare();
     maybe_output(encoded);
     img_.as_encoded = false;
+    img_.as_read = nullptr;
     int best_q[3][64];
     for (int c = 0; c < 3; ++c)
-      for (int k = 0; k < 64; ++k) best_q[c][k] = 1;
+      for (int k = 0; k < 64; ++k) best_q[c][k] = jpeg_source_ ? q_in_[c][k] : 1;
     if (!select_quant_matrix(best_q)) {
       for (int c = 0; c < 3; ++c)
         for (int k = 0; k < 64; ++k) best_q[c][k] = 1;
@@ -208,7 +227,7 @@ class Search {
     unsigned int hist[6][257];
     bool chroma = false;
     ctx_->jpeg_histograms(&hist[0][0], &chroma);
-    const int ncomp = img_.as_encoded ? 3 : (chroma ? 3 : 1);
+    const int ncomp = (img_.as_encoded || img_.as_read) ? 3 : (chroma ? 3 : 1);
     SymbolHistogram dc_h[3], ac_h[3];
     for (int c = 0; c < ncomp; ++c)
       for (int i = 0; i < 256; ++i) {
@@ -220,7 +239,7 @@ class Search {
     ctx_->jpeg_encode_scan(ncomp, &plan_.depth[0][0], &plan_.code[0][0], &nbytes, &num_ff);
     scan_bytes_ = nbytes;
     st_->ms_jpeg += ms_since(t0);
-    return plan_.prefix.size() + nbytes + num_ff + 2;
+    return plan_.prefix.size() + nbytes + num_ff + plan_.trailer.size();
   }
 
   std::string fetch_encoded() {
@@ -740,6 +759,9 @@ class Search {
   JpegPlan plan_;
   size_t scan_bytes_ = 0;
   int tie_fallbacks_ = 0;
+  bool jpeg_source_ = false;
+  int q_in_[3][64];
+  const JpegFileLayout* layout_ = nullptr;
 };
 
 }  // namespace
@@ -761,8 +783,25 @@ static bool check_params(const SearchParams& params, std::string* err) {
   return true;
 }
 
+namespace {
+// What process_jpeg knows about its input beyond the coefficients.
+struct JpegSource {
+  int q_in[3][64];
+  JpegFileLayout layout;
+  JpegMeta meta;
+};
+bool process_resident_impl(const SearchParams& params, ImageContext* ctx, const JpegSource* src, LogSink log,
+                           void* log_user, std::string* jpeg_out, SearchStats* stats, std::string* err);
+}  // namespace
+
 bool process_resident(const SearchParams& params, ImageContext* ctx, LogSink log, void* log_user,
                       std::string* jpeg_out, SearchStats* stats, std::string* err) {
+  return process_resident_impl(params, ctx, nullptr, log, log_user, jpeg_out, stats, err);
+}
+
+namespace {
+bool process_resident_impl(const SearchParams& params, ImageContext* ctx, const JpegSource* src, LogSink log,
+                           void* log_user, std::string* jpeg_out, SearchStats* stats, std::string* err) {
   SearchStats local;
   SearchStats* st = stats ? stats : &local;
   const double setup_ms = st->ms_device_setup;
@@ -775,6 +814,9 @@ bool process_resident(const SearchParams& params, ImageContext* ctx, LogSink log
   const long long h2d0 = h2d_bytes_total(), d2h0 = d2h_bytes_total();
   ctx->prepare();
   const int w = ctx->width(), h = ctx->height();
+  // RGB input: EncodeRGBToJpeg gives the JPEGData the same JFIF APP0 that stripping writes
+  // (g/jpeg_data_encoder.cc:53-64,73), so Params::clear_metadata makes no difference there
+  const JpegMeta* meta = src ? &src->meta : nullptr;
   if (w < 32 || h < 32) {
     // Butteraugli is skipped for tiny images (g/processor.cc:832-838,940)
     CoeffImage img;
@@ -785,8 +827,10 @@ bool process_resident(const SearchParams& params, ImageContext* ctx, LogSink log
     img.nblocks = ctx->geom().nblocks;
     img.coeffs = ctx->orig_coeffs().data();
     for (int c = 0; c < 3; ++c)
-      for (int k = 0; k < 64; ++k) img.q[c][k] = 1;
-    img.as_encoded = true;
+      for (int k = 0; k < 64; ++k) img.q[c][k] = src ? src->q_in[c][k] : 1;
+    img.as_encoded = src == nullptr;
+    img.as_read = src ? &src->layout : nullptr;
+    img.meta = meta;
     *jpeg_out = write_jpeg(img);
     if (log) {
       char buf[128];
@@ -795,6 +839,11 @@ bool process_resident(const SearchParams& params, ImageContext* ctx, LogSink log
     }
   } else {
     Search search(params, ctx, log, log_user, st);
+    if (src) {
+      search.set_jpeg_source(src->q_in, &src->layout, meta);
+    } else {
+      search.set_meta(meta);
+    }
     search.run(jpeg_out);
   }
   st->gpu_launches = total_launches() - launches0;
@@ -802,6 +851,68 @@ bool process_resident(const SearchParams& params, ImageContext* ctx, LogSink log
   st->d2h_bytes = d2h_bytes_total() - d2h0;
   st->ms_total = ms_since(t_all);
   return true;
+}
+}  // namespace
+
+// Process(jpeg bytes), g/processor.cc:890-924.
+bool process_jpeg(const SearchParams& params, const uint8_t* data, size_t len, int device, LogSink log,
+                  void* log_user, std::string* jpeg_out, SearchStats* stats, std::string* err) {
+  SearchStats local;
+  SearchStats* st = stats ? stats : &local;
+  *st = SearchStats();
+  jpeg_out->clear();
+  auto fail = [err](const char* msg) {
+    *err = msg;
+    fputs(msg, stderr);
+    return false;
+  };
+  JpegInput jpg;
+  std::string why;
+  if (data == nullptr || !read_jpeg(data, len, &jpg, &why)) return fail("Can't read jpg data from input file\n");
+  if (!check_jpeg_sanity(jpg)) return fail("Unsupported input JPEG (unexpectedly large coefficient values).\n");
+  const size_t ncomp = jpg.components.size();
+  const bool decodable = ncomp == 1 || (ncomp == 3 && has_ycbcr_color_space(jpg) && (jpg.is_420() || jpg.is_444()));
+  if (!decodable)
+    return fail(
+        "Unsupported input JPEG file (e.g. unsupported downsampling mode).\nPlease provide the input image as a PNG "
+        "file.\n");
+  if (!check_params(params, err)) return false;
+  if (ncomp != 3 || !has_ycbcr_color_space(jpg)) return fail("Only YUV color space input jpeg is supported\n");
+  if (!jpg.is_444())
+    return fail("guetzli_b200: YUV420 JPEG input is outside the B200 hot path (DESIGN.md); provide 4:4:4 or PNG\n");
+
+  Clock::time_point t0 = Clock::now();
+  const long long h2d0 = h2d_bytes_total();
+  JpegSource src;
+  const int w = jpg.width, h = jpg.height;
+  const int nblocks = jpg.components[0].width_in_blocks * jpg.components[0].height_in_blocks;
+  // RemoveOriginalQuantization (g/processor.cc:82): coefficients times their quant step
+  std::vector<int16_t> dq(static_cast<size_t>(3) * nblocks * 64);
+  for (int c = 0; c < 3; ++c) {
+    const JpegComponent& comp = jpg.components[c];
+    const int* q = jpg.quant[comp.quant_idx].values;
+    memcpy(src.q_in[c], q, sizeof(src.q_in[c]));
+    int16_t* dst = &dq[static_cast<size_t>(c) * nblocks * 64];
+    for (size_t i = 0; i < comp.coeffs.size(); ++i) dst[i] = static_cast<int16_t>(comp.coeffs[i] * q[i & 63]);
+    src.layout.comp_id[c] = comp.id;
+    src.layout.comp_table[c] = comp.quant_idx;
+  }
+  src.layout.num_tables = static_cast<int>(jpg.quant.size());
+  for (int i = 0; i < src.layout.num_tables; ++i) {
+    memcpy(src.layout.table[i], jpg.quant[i].values, sizeof(src.layout.table[i]));
+    src.layout.precision[i] = jpg.quant[i].precision;
+    src.layout.index[i] = jpg.quant[i].index;
+  }
+  src.meta.strip = params.clear_metadata;
+  src.meta.app_data = jpg.app_data;
+  src.meta.com_data = jpg.com_data;
+  src.meta.tail_data = jpg.tail_data;
+  ImageContext ctx(dq.data(), w, h, device, false, nullptr);
+  st->ms_device_setup = ms_since(t0);
+  const bool ok = process_resident_impl(params, &ctx, &src, log, log_user, jpeg_out, st, err);
+  st->h2d_bytes = h2d_bytes_total() - h2d0;
+  st->ms_total = ms_since(t0);
+  return ok;
 }
 
 bool process_rgb(const SearchParams& params, const uint8_t* rgb, int w, int h, int device, LogSink log,

@@ -50,6 +50,11 @@ bool process_rgb_tiled(const SearchParams& params, const uint8_t* rgb, int w, in
 
 // Returns true on success; *jpeg_out receives the best JPEG found (possibly
 // empty on failure), error text goes to err (and stderr, like the reference).
+// Process(jpeg bytes) (g/processor.cc:890): 4:4:4 YCbCr JPEG input; the search starts
+// from the file's own coefficients and quant tables.
+bool process_jpeg(const SearchParams& params, const uint8_t* data, size_t len, int device, LogSink log,
+                  void* log_user, std::string* jpeg_out, SearchStats* stats, std::string* err);
+
 bool process_rgb(const SearchParams& params, const uint8_t* rgb, int w, int h, int device, LogSink log,
                  void* log_user, std::string* jpeg_out, SearchStats* stats, std::string* err);
 

@@ -69,6 +69,22 @@ int gb200_process_rgb(const gb200_params* params, const uint8_t* rgb, int w, int
                       gb200_log_fn log, void* log_user, uint8_t** out, size_t* out_len,
                       gb200_stats* stats);
 
+/* guetzli::Process(params, stats, jpeg_in, &out) (guetzli/processor.h:39-41,
+ * guetzli/processor.cc:890): JPEG input.  The file is parsed on the host
+ * (ReadJpeg, guetzli/jpeg_data_reader.cc:931); its coefficients and quant tables
+ * seed the same device search.  4:4:4 YCbCr input only: 4:2:0 input needs the
+ * YUV420 path and is refused, every other rejection is the reference's. */
+int gb200_process_jpeg(const gb200_params* params, const uint8_t* jpeg_in, size_t jpeg_len, int device,
+                       gb200_log_fn log, void* log_user, uint8_t** out, size_t* out_len,
+                       gb200_stats* stats);
+
+/* ReadJpeg(JPEG_READ_HEADER) as the CLI uses it (guetzli/guetzli.cc:306): frame size only. */
+int gb200_jpeg_dimensions(const uint8_t* jpeg_in, size_t jpeg_len, int* width, int* height);
+
+/* test hook: ReadJpeg(JPEG_READ_ALL) alone.  dims = {w, h, ncomp, wb0, hb0, wb1, hb1, ...} (11 ints);
+ * out receives the quantised coefficients of all components, concatenated. */
+int gb200_debug_read_jpeg(const uint8_t* jpeg_in, size_t jpeg_len, int* dims, int16_t* out, size_t out_cap);
+
 /* ---- one image tiled over the GPUs of a node (BASELINE configs[3]) ------------
  * One process per GPU.  Rank 0 obtains an id, the host application distributes it
  * (e.g. torch.distributed broadcast), every rank calls gb200_dist_init once, then

@@ -91,6 +91,38 @@ inline bool Process(const Params& params, ProcessStats* stats, const std::vector
   return ok != 0;
 }
 
+// JPEG input (processor.h:39-41, processor.cc:890): 4:4:4 YCbCr files; the search starts
+// from the file's coefficients and quant tables.
+inline bool Process(const Params& params, ProcessStats* stats, const std::string& in_data, std::string* out) {
+  gb200_params p;
+  gb200_params_default(&p);
+  p.butteraugli_target = params.butteraugli_target;
+  p.clear_metadata = params.clear_metadata;
+  p.try_420 = params.try_420;
+  p.force_420 = params.force_420;
+  p.use_silver_screen = params.use_silver_screen;
+  p.zeroing_greedy_lookahead = params.zeroing_greedy_lookahead;
+  p.new_zeroing_model = params.new_zeroing_model;
+  ProcessStats dummy;
+  if (stats == nullptr) stats = &dummy;
+  const bool want_log = stats->debug_output || stats->debug_output_file;
+  int device = 0;
+  if (const char* e = getenv("GUETZLI_B200_DEVICE")) device = atoi(e);
+  uint8_t* buf = nullptr;
+  size_t len = 0;
+  gb200_stats st;
+  const int ok = gb200_process_jpeg(&p, reinterpret_cast<const uint8_t*>(in_data.data()), in_data.size(), device,
+                                    want_log ? b200_detail::LogSink : nullptr, stats, &buf, &len, &st);
+  out->assign(reinterpret_cast<const char*>(buf), len);
+  gb200_free(buf);
+  if (ok) {
+    stats->counters[kNumItersCnt] = st.iterations;
+    stats->counters[kNumItersUpCnt] = st.iterations_up;
+    stats->counters[kNumItersDownCnt] = st.iterations_down;
+  }
+  return ok != 0;
+}
+
 }  // namespace guetzli
 
 #endif  // GUETZLI_B200_COMPAT_H_

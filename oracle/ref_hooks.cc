@@ -82,6 +82,10 @@ double gref_target_for_quality(double q) {
 void gref_free(void* p) { free(p); }
 
 // guetzli::Process(RGB) (processor.cc:926). counters = {iterations, up, down}.
+// Params::clear_metadata for the gref_process_rgb* hooks (default: the reference's, true).
+static int g_clear_metadata = 1;
+void gref_set_clear_metadata(int on) { g_clear_metadata = on; }
+
 // _ex: also sets Params::zeroing_greedy_lookahead / new_zeroing_model (processor.h:35-36).
 int gref_process_rgb_ex(const uint8_t* rgb, int w, int h, float butteraugli_target, int lookahead, int new_model,
                         uint8_t** out, size_t* out_len, char** trace, size_t* trace_len, int* counters,
@@ -90,6 +94,7 @@ int gref_process_rgb_ex(const uint8_t* rgb, int w, int h, float butteraugli_targ
   params.butteraugli_target = butteraugli_target;
   params.zeroing_greedy_lookahead = lookahead;
   params.new_zeroing_model = new_model != 0;
+  params.clear_metadata = g_clear_metadata != 0;
   guetzli::ProcessStats stats;
   std::string dbg;
   if (trace) stats.debug_output = &dbg;
@@ -114,6 +119,55 @@ int gref_process_rgb_ex(const uint8_t* rgb, int w, int h, float butteraugli_targ
     counters[2] = stats.counters[guetzli::kNumItersDownCnt];
   }
   return ok ? 1 : 0;
+}
+
+// guetzli::Process(jpeg bytes) (processor.cc:890).  clear_metadata: Params::clear_metadata.
+int gref_process_jpeg(const uint8_t* jpeg, size_t len, float butteraugli_target, int clear_metadata,
+                      uint8_t** out, size_t* out_len, char** trace, size_t* trace_len, int* counters) {
+  guetzli::Params params;
+  params.butteraugli_target = butteraugli_target;
+  params.clear_metadata = clear_metadata != 0;
+  guetzli::ProcessStats stats;
+  std::string dbg;
+  if (trace) stats.debug_output = &dbg;
+  std::string in(reinterpret_cast<const char*>(jpeg), len), jpg;
+  bool ok = guetzli::Process(params, &stats, in, &jpg);
+  *out = (uint8_t*)malloc(jpg.size() + 1);
+  memcpy(*out, jpg.data(), jpg.size());
+  *out_len = jpg.size();
+  if (trace) {
+    *trace = (char*)malloc(dbg.size() + 1);
+    memcpy(*trace, dbg.data(), dbg.size());
+    (*trace)[dbg.size()] = 0;
+    *trace_len = dbg.size();
+  }
+  if (counters) {
+    counters[0] = stats.counters[guetzli::kNumItersCnt];
+    counters[1] = stats.counters[guetzli::kNumItersUpCnt];
+    counters[2] = stats.counters[guetzli::kNumItersDownCnt];
+  }
+  return ok ? 1 : 0;
+}
+
+// ReadJpeg(JPEG_READ_ALL) (jpeg_data_reader.cc:931): quantised coefficients of component c
+// into out (caller sizes it from dims[]).  dims = {w, h, ncomp, wb0, hb0, wb1, hb1, ...}.
+int gref_read_jpeg(const uint8_t* jpeg, size_t len, int* dims, int16_t* out, size_t out_cap) {
+  guetzli::JPEGData jpg;
+  std::string in(reinterpret_cast<const char*>(jpeg), len);
+  if (!guetzli::ReadJpeg(in, guetzli::JPEG_READ_ALL, &jpg)) return 0;
+  dims[0] = jpg.width;
+  dims[1] = jpg.height;
+  dims[2] = (int)jpg.components.size();
+  size_t pos = 0;
+  for (size_t c = 0; c < jpg.components.size(); ++c) {
+    dims[3 + 2 * c] = jpg.components[c].width_in_blocks;
+    dims[4 + 2 * c] = jpg.components[c].height_in_blocks;
+    for (size_t i = 0; i < jpg.components[c].coeffs.size(); ++i) {
+      if (pos < out_cap) out[pos] = jpg.components[c].coeffs[i];
+      ++pos;
+    }
+  }
+  return pos <= out_cap ? 1 : 0;
 }
 
 int gref_process_rgb(const uint8_t* rgb, int w, int h, float butteraugli_target,

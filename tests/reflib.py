@@ -57,6 +57,36 @@ def process_rgb(rgb, quality=95.0, trace=True, lookahead=3, new_zeroing_model=Tr
     return bool(ok), data, t, list(counters), secs.value
 
 
+def process_jpeg(jpeg_in, quality=95.0, clear_metadata=True, trace=True):
+    """guetzli::Process(jpeg bytes) -> (ok, jpeg bytes, trace str, counters[3])"""
+    buf = np.frombuffer(bytes(jpeg_in), dtype=np.uint8)
+    out, out_len = C.POINTER(C.c_uint8)(), C.c_size_t()
+    tr, tr_len = C.c_char_p(), C.c_size_t()
+    counters = (C.c_int * 3)()
+    ok = lib().gref_process_jpeg(_p(buf, C.c_uint8), C.c_size_t(buf.size), C.c_float(target_for_quality(quality)),
+                                 int(clear_metadata), C.byref(out), C.byref(out_len),
+                                 C.byref(tr) if trace else None, C.byref(tr_len), counters)
+    data = C.string_at(out, out_len.value)
+    lib().gref_free(out)
+    t = ""
+    if trace:
+        t = C.string_at(tr, tr_len.value).decode()
+        lib().gref_free(tr)
+    return bool(ok), data, t, list(counters)
+
+
+def read_jpeg(jpeg_in):
+    """ReadJpeg(JPEG_READ_ALL) -> (ok, dims, quantised coefficients of all components, concatenated)"""
+    buf = np.frombuffer(bytes(jpeg_in), dtype=np.uint8)
+    dims = (C.c_int * 11)()
+    cap = 1 << 24
+    out = np.zeros(cap, dtype=np.int16)
+    ok = lib().gref_read_jpeg(_p(buf, C.c_uint8), C.c_size_t(buf.size), dims, _p(out, C.c_int16), C.c_size_t(cap))
+    d = list(dims)
+    n = sum(d[3 + 2 * c] * d[4 + 2 * c] * 64 for c in range(d[2])) if ok else 0
+    return bool(ok), d, out[:n].copy()
+
+
 def nblocks(w, h):
     return ((w + 7) // 8) * ((h + 7) // 8)
 

@@ -14,6 +14,7 @@ import parity
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PNG_DUMP = os.path.join(ROOT, "oracle", "_build", "png_dump")
 CLI = os.path.join(ROOT, "guetzli_b200", "guetzli")
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def blend_on_black(rgb, a):
@@ -87,6 +88,18 @@ def test_cli_smoke_matrix(tmp_path, cuda_lib):
     for flags in (["--nomemlimit"], ["--memlimit", "100"], ["--quality", "85"]):
         r = subprocess.run([CLI] + flags + [small, out], stderr=subprocess.PIPE)
         assert r.returncode == 0 and open(out, "rb").read()[:2] == b"\xff\xd8", flags
+    # jpeg input, file and stdin (tests/smoke_test.sh "run_test jpeg ..."): fixture + reference answer
+    import json
+    gj = json.load(open(os.path.join(HERE, "golden", "golden_jpeg.json")))["base444_q90"]
+    jpg_in = os.path.join(HERE, "golden", "jpeg", "base444_q90.jpg")
+    r = subprocess.run([CLI, "--quality", str(gj["quality"]), jpg_in, out], stderr=subprocess.PIPE)
+    assert r.returncode == 0
+    assert hashlib.sha256(open(out, "rb").read()).hexdigest() == gj["jpeg_sha256"]
+    r = subprocess.run([CLI, "--quality", str(gj["quality"]), "--verbose", "-", "-"], stdin=open(jpg_in, "rb"),
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0 and hashlib.sha256(r.stdout).hexdigest() == gj["jpeg_sha256"]
+    assert hashlib.sha256(r.stderr).hexdigest() == gj["trace_sha256"]
+    assert subprocess.run([CLI, "--memlimit", "50", jpg_in, out], stderr=subprocess.PIPE).returncode == 1
     # failures: exit code 1
     assert subprocess.run([CLI, os.devnull, out], stderr=subprocess.PIPE).returncode == 1
     assert subprocess.run([CLI, "--memlimit", "50", small, out], stderr=subprocess.PIPE).returncode == 1
