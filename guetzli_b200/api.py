@@ -218,6 +218,23 @@ def read_jpeg(jpeg_in, lib=None):
     return bool(ok), d, out[:n].copy()
 
 
+def butteraugli_diffmap(rgb0, rgb1, device=0, lib=None):
+    """butteraugli::ButteraugliInterface: rgb0, rgb1 planar linear RGB float32 [3][h][w] (0..255).
+    -> (diffmap [h][w] float32, score)."""
+    lib = lib or load_library()
+    a = np.ascontiguousarray(rgb0, dtype=np.float32)
+    b = np.ascontiguousarray(rgb1, dtype=np.float32)
+    assert a.shape == b.shape and a.ndim == 3 and a.shape[0] == 3
+    _, h, w = a.shape
+    dm = np.zeros((h, w), dtype=np.float32)
+    score = C.c_double()
+    lib.gb200_butteraugli_diffmap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                              C.POINTER(C.c_double)]
+    if not lib.gb200_butteraugli_diffmap(a.ctypes.data, b.ctypes.data, w, h, device, dm.ctypes.data, C.byref(score)):
+        raise RuntimeError(_err(lib))
+    return dm, score.value
+
+
 def counters(lib=None):
     """-> (kernel launches, h2d bytes, d2h bytes): process-wide running totals."""
     lib = lib or load_library()

@@ -52,7 +52,11 @@ inline bool unfilter(const uint8_t* in, size_t in_len, int h, size_t rowbytes, i
   return true;
 }
 
-inline bool ReadPNG(const std::string& data, int* xsize, int* ysize, std::vector<uint8_t>* rgb) {
+// Decodes to 8-bit RGBA (alpha 255 where the file has none); *has_alpha tells whether the
+// file carries transparency (alpha channel or tRNS).  16-bit samples keep their high byte.
+inline bool ReadPNGRGBA(const std::string& data, int* xsize, int* ysize, std::vector<uint8_t>* rgba,
+                        bool* file_has_alpha) {
+  std::vector<uint8_t>* rgb = rgba;
   static const uint8_t kMagic[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
   if (data.size() < 8 || memcmp(data.data(), kMagic, 8) != 0) return false;
   const uint8_t* p = reinterpret_cast<const uint8_t*>(data.data());
@@ -173,7 +177,8 @@ inline bool ReadPNG(const std::string& data, int* xsize, int* ysize, std::vector
   // EXPAND / STRIP_16 semantics of libpng, then the reference's channel handling
   *xsize = static_cast<int>(w);
   *ysize = static_cast<int>(h);
-  rgb->resize(static_cast<size_t>(3) * w * h);
+  rgb->resize(static_cast<size_t>(4) * w * h);
+  *file_has_alpha = ctype == 4 || ctype == 6 || have_trns;
   const int maxv = (1 << depth) - 1;
   auto to8 = [&](uint16_t v) -> uint8_t {
     if (depth == 16) return static_cast<uint8_t>(v >> 8);
@@ -220,11 +225,24 @@ inline bool ReadPNG(const std::string& data, int* xsize, int* ysize, std::vector
         break;
       }
     }
-    const bool has_alpha = ctype == 4 || ctype == 6 || have_trns;
-    (*rgb)[3 * i + 0] = has_alpha ? BlendOnBlack(r, a) : r;
-    (*rgb)[3 * i + 1] = has_alpha ? BlendOnBlack(g, a) : g;
-    (*rgb)[3 * i + 2] = has_alpha ? BlendOnBlack(b, a) : b;
+    (*rgb)[4 * i + 0] = r;
+    (*rgb)[4 * i + 1] = g;
+    (*rgb)[4 * i + 2] = b;
+    (*rgb)[4 * i + 3] = a;
   }
+  return true;
+}
+
+// guetzli's reader (g/guetzli.cc:43-152): RGB, transparent pixels blended on black.
+inline bool ReadPNG(const std::string& data, int* xsize, int* ysize, std::vector<uint8_t>* rgb) {
+  std::vector<uint8_t> rgba;
+  bool has_alpha = false;
+  if (!ReadPNGRGBA(data, xsize, ysize, &rgba, &has_alpha)) return false;
+  const size_t n = static_cast<size_t>(*xsize) * *ysize;
+  rgb->resize(3 * n);
+  for (size_t i = 0; i < n; ++i)
+    for (int c = 0; c < 3; ++c)
+      (*rgb)[3 * i + c] = has_alpha ? BlendOnBlack(rgba[4 * i + c], rgba[4 * i + 3]) : rgba[4 * i + c];
   return true;
 }
 

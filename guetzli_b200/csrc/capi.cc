@@ -155,6 +155,55 @@ int gb200_process_jpeg(const gb200_params* params, const uint8_t* jpeg_in, size_
   return (guarded_ok && ok) ? 1 : 0;
 }
 
+// butteraugli::ButteraugliInterface (b/butteraugli.cc:1858) on the device kernels.
+int gb200_butteraugli_diffmap(const float* rgb0, const float* rgb1, int w, int h, int device, float* diffmap,
+                              double* score) {
+  if (rgb0 == nullptr || rgb1 == nullptr || w < 1 || h < 1) {
+    g_err = "butteraugli: no image";
+    return 0;
+  }
+  return guarded([&]() {
+    // images below 8 pixels in a dimension are edge-replicated to 8 (b/butteraugli.cc:1825-1853)
+    const int kMin = 8;
+    const int xb = w < kMin ? (kMin - w) / 2 : 0, yb = h < kMin ? (kMin - h) / 2 : 0;
+    const int ws = std::max(w, kMin), hs = std::max(h, kMin);
+    std::vector<float> s0, s1;
+    const float* p0 = rgb0;
+    const float* p1 = rgb1;
+    if (ws != w || hs != h) {
+      s0.resize(static_cast<size_t>(3) * ws * hs);
+      s1.resize(s0.size());
+      for (int c = 0; c < 3; ++c)
+        for (int y = 0; y < hs; ++y)
+          for (int x = 0; x < ws; ++x) {
+            const int x2 = std::min(w - 1, std::max(0, x - xb)), y2 = std::min(h - 1, std::max(0, y - yb));
+            const size_t d = (static_cast<size_t>(c) * hs + y) * ws + x, s = (static_cast<size_t>(c) * h + y2) * w + x2;
+            s0[d] = rgb0[s];
+            s1[d] = rgb1[s];
+          }
+      p0 = s0.data();
+      p1 = s1.data();
+    }
+    gb200::ImageContext ctx(p0, ws, hs, device);
+    const float dmax = ctx.compare_linear(p1);
+    std::vector<float> dm(static_cast<size_t>(ws) * hs);
+    if (diffmap != nullptr || ws != w || hs != h) ctx.download_distmap(dm.data());
+    float m = 0.0f;
+    if (ws != w || hs != h) {
+      for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+          const float v = dm[static_cast<size_t>(y + yb) * ws + x + xb];
+          if (diffmap) diffmap[static_cast<size_t>(y) * w + x] = v;
+          m = std::max(m, v);
+        }
+    } else {
+      if (diffmap) memcpy(diffmap, dm.data(), dm.size() * sizeof(float));
+      m = dmax;
+    }
+    if (score) *score = m;
+  });
+}
+
 int gb200_jpeg_dimensions(const uint8_t* jpeg_in, size_t jpeg_len, int* width, int* height) {
   return gb200::read_jpeg_dimensions(jpeg_in, jpeg_len, width, height) ? 1 : 0;
 }

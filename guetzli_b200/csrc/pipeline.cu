@@ -110,6 +110,25 @@ ImageContext::ImageContext(const int16_t* dq_coeffs, int w, int h, int device, b
   init(nullptr, dq_coeffs, w, h, prepare_now);
 }
 
+ImageContext::ImageContext(const float* linear_rgb, int w, int h, int device)
+    : g_(make_geom(w, h)), device_(device), comm_(nullptr) {
+  metric_only_ = true;
+  init(nullptr, nullptr, w, h, false);
+  metric_ = true;
+  prepared_ = true;
+  // PsychoImage of the first image (butteraugli.cc:784), resident
+  upload_planes(linear_rgb, lin_, 3);
+  opsin(lin_, xyb_);
+  separate(xyb_, ps0_);
+  stream_sync(s_);
+}
+
+float ImageContext::compare_linear(const float* linear_rgb) {
+  bind();
+  upload_planes(linear_rgb, lin_, 3);
+  return compare_tail();
+}
+
 void ImageContext::download_rgb(uint8_t* rgb) {
   bind();
   d2h(rgb, d_rgb_, static_cast<size_t>(3) * g_.w * g_.h, s_);
@@ -211,7 +230,9 @@ void ImageContext::init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int
   num_dirty_ = 0;
   d_dirty_ = static_cast<int*>(dev_alloc(sizeof(int) * g_.nblocks));
   owned_.push_back(d_dirty_);
-  if (from_coeffs_) {
+  if (metric_only_) {
+    // nothing to upload here
+  } else if (from_coeffs_) {
     h2d(d_orig_, dq_coeffs, static_cast<size_t>(3) * g_.nblocks * 64 * sizeof(int16_t), s_);
   } else {
     h2d(d_rgb_, rgb, static_cast<size_t>(3) * w * h, s_);
@@ -368,6 +389,12 @@ float ImageContext::compare() {
   render_all_ = false;
   for (size_t i = 0; i < dirty_list_.size(); ++i) dirty_flag_[dirty_list_[i]] = 0;
   dirty_list_.clear();
+  return compare_tail();
+}
+
+// S1..S13 on the linear RGB planes in lin_ (butteraugli::ButteraugliComparator::Diffmap).
+float ImageContext::compare_tail() {
+  const size_t P = g_.plane;
   opsin(lin_, xyb_);
   separate(xyb_, ps1_);
   // S7 Malta: uhf[Y], uhf[X] with 9-tap lines; hf[Y], hf[X], mf[Y], mf[X] with 5-tap lines

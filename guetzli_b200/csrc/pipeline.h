@@ -30,6 +30,10 @@ class ImageContext {
   // JPEG input (4:4:4): the original is given as dequantised DCT coefficients
   // [3][nblocks][64]; its pixels (DecodeJpegToRGB) are rendered on the device.
   ImageContext(const int16_t* dq_coeffs, int w, int h, int device, bool prepare_now, Comm* comm);
+  // Metric only (stand-alone butteraugli, scope row f4): the first image as linear RGB
+  // float planes [3][h][w]; compare_linear() scores a second one against it.
+  ImageContext(const float* linear_rgb, int w, int h, int device);
+  float compare_linear(const float* linear_rgb);
   // the one-time kernels (idempotent); split from the upload so that a caller can
   // time the job with the image already resident in HBM
   void prepare();
@@ -144,6 +148,8 @@ class ImageContext {
   float* hf_blr_;  // [2]
   float* ps1_;     // [10]
   float* diffs_;   // [1]
+  bool metric_only_ = false;  // no coefficients at all: butteraugli of two linear images
+  float compare_tail();
   bool from_coeffs_ = false;  // original given as coefficients (JPEG input)
   void init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int h, bool prepare_now);
   float* ac_;      // [2]

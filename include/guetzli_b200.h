@@ -78,6 +78,13 @@ int gb200_process_jpeg(const gb200_params* params, const uint8_t* jpeg_in, size_
                        gb200_log_fn log, void* log_user, uint8_t** out, size_t* out_len,
                        gb200_stats* stats);
 
+/* butteraugli::ButteraugliInterface(rgb0, rgb1, diffmap, diffvalue)
+ * (third_party/butteraugli/butteraugli/butteraugli.cc:1858; the stand-alone `butteraugli`
+ * tool, butteraugli_main.cc:362): both images as planar linear RGB floats [3][h][w] in
+ * 0..255; diffmap (may be NULL) receives w*h floats, *score their maximum. */
+int gb200_butteraugli_diffmap(const float* rgb0, const float* rgb1, int w, int h, int device, float* diffmap,
+                              double* score);
+
 /* ReadJpeg(JPEG_READ_HEADER) as the CLI uses it (guetzli/guetzli.cc:306): frame size only. */
 int gb200_jpeg_dimensions(const uint8_t* jpeg_in, size_t jpeg_len, int* width, int* height);
 

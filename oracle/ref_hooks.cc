@@ -121,6 +121,35 @@ int gref_process_rgb_ex(const uint8_t* rgb, int w, int h, float butteraugli_targ
   return ok ? 1 : 0;
 }
 
+// butteraugli::ButteraugliInterface (butteraugli.cc:1858): planar linear RGB [3][h][w].
+int gref_butteraugli_interface(const float* rgb0, const float* rgb1, int w, int h, float* diffmap, double* score) {
+  std::vector<butteraugli::ImageF> a, b;
+  for (int c = 0; c < 3; ++c) {
+    a.emplace_back(w, h);
+    b.emplace_back(w, h);
+    for (int y = 0; y < h; ++y) {
+      memcpy(a[c].Row(y), rgb0 + ((size_t)c * h + y) * w, sizeof(float) * w);
+      memcpy(b[c].Row(y), rgb1 + ((size_t)c * h + y) * w, sizeof(float) * w);
+    }
+  }
+  butteraugli::ImageF dm;
+  double v = 0;
+  if (!butteraugli::ButteraugliInterface(a, b, dm, v)) return 0;
+  for (int y = 0; y < h; ++y) memcpy(diffmap + (size_t)y * w, dm.Row(y), sizeof(float) * w);
+  *score = v;
+  return 1;
+}
+
+// The tool's heat map (butteraugli.cc:1979 CreateHeatMapImage with the thresholds of
+// butteraugli_main.cc:423-424).
+void gref_heatmap(const float* distmap, int w, int h, uint8_t* rgb) {
+  std::vector<float> dm(distmap, distmap + (size_t)w * h);
+  std::vector<uint8_t> out;
+  butteraugli::CreateHeatMapImage(dm, butteraugli::ButteraugliFuzzyInverse(1.5), butteraugli::ButteraugliFuzzyInverse(0.5),
+                                  w, h, &out);
+  memcpy(rgb, out.data(), out.size());
+}
+
 // guetzli::Process(jpeg bytes) (processor.cc:890).  clear_metadata: Params::clear_metadata.
 int gref_process_jpeg(const uint8_t* jpeg, size_t len, float butteraugli_target, int clear_metadata,
                       uint8_t** out, size_t* out_len, char** trace, size_t* trace_len, int* counters) {

@@ -87,6 +87,17 @@ def read_jpeg(jpeg_in):
     return bool(ok), d, out[:n].copy()
 
 
+def butteraugli_interface(rgb0, rgb1):
+    """butteraugli::ButteraugliInterface on planar linear float32 [3][h][w] -> (diffmap, score)"""
+    a = np.ascontiguousarray(rgb0, dtype=np.float32)
+    b = np.ascontiguousarray(rgb1, dtype=np.float32)
+    _, h, w = a.shape
+    dm = np.zeros((h, w), dtype=np.float32)
+    score = C.c_double()
+    assert lib().gref_butteraugli_interface(_p(a, C.c_float), _p(b, C.c_float), w, h, _p(dm, C.c_float), C.byref(score))
+    return dm, score.value
+
+
 def nblocks(w, h):
     return ((w + 7) // 8) * ((h + 7) // 8)
 
