@@ -222,24 +222,57 @@ class Search {
 
   // a11 on the device: exact size of the candidate's JPEG; the bytes are fetched
   // only when the candidate becomes the best output.
-  size_t encoded_size() {
+  // host_ac != nullptr: the AC histograms the selection walk keeps up to date on the
+  // host (exactly the candidate's, like the reference's own incremental bookkeeping,
+  // g/processor.cc:471-495) replace the device histogram pass and its round trip; DC
+  // symbols do not change during frequency masking (sfm_dc_hist_, captured at its start).
+  size_t encoded_size(const SymbolHistogram* host_ac = nullptr) {
     Clock::time_point t0 = Clock::now();
     unsigned int hist[6][257];
     bool chroma = false;
-    ctx_->jpeg_histograms(&hist[0][0], &chroma);
-    const int ncomp = (img_.as_encoded || img_.as_read) ? 3 : (chroma ? 3 : 1);
     SymbolHistogram dc_h[3], ac_h[3];
-    for (int c = 0; c < ncomp; ++c)
-      for (int i = 0; i < 256; ++i) {
-        dc_h[c].counts[i] = 2 * hist[c][i];
-        ac_h[c].counts[i] = 2 * hist[3 + c][i];
+    int ncomp;
+    if (host_ac != nullptr) {
+      const size_t per = static_cast<size_t>(img_.nblocks) * 64;
+      for (size_t i = per; i < 3 * per && !chroma; ++i) chroma = cand_[i] != 0;
+      ncomp = chroma ? 3 : 1;
+      for (int c = 0; c < ncomp; ++c) {
+        for (int i = 0; i < 256; ++i) dc_h[c].counts[i] = 2 * sfm_dc_hist_[c][i];
+        ac_h[c] = host_ac[c];
       }
+      static const bool kCheck = getenv("GB200_CHECK_HOST_HIST") != nullptr;
+      if (kCheck) {
+        bool dev_chroma = false;
+        ctx_->jpeg_histograms(&hist[0][0], &dev_chroma);
+        bool same = dev_chroma == chroma;
+        for (int c = 0; c < ncomp && same; ++c)
+          for (int i = 0; i < 256 && same; ++i)
+            same = 2 * hist[c][i] == dc_h[c].counts[i] && 2 * hist[3 + c][i] == ac_h[c].counts[i];
+        if (!same) throw std::runtime_error("host symbol histograms differ from the device's");
+      }
+    } else {
+      ctx_->jpeg_histograms(&hist[0][0], &chroma);
+      ncomp = (img_.as_encoded || img_.as_read) ? 3 : (chroma ? 3 : 1);
+      for (int c = 0; c < ncomp; ++c)
+        for (int i = 0; i < 256; ++i) {
+          dc_h[c].counts[i] = 2 * hist[c][i];
+          ac_h[c].counts[i] = 2 * hist[3 + c][i];
+        }
+    }
     plan_ = plan_jpeg(img_, ncomp, dc_h, ac_h);
     size_t nbytes = 0, num_ff = 0;
     ctx_->jpeg_encode_scan(ncomp, &plan_.depth[0][0], &plan_.code[0][0], &nbytes, &num_ff);
     scan_bytes_ = nbytes;
     st_->ms_jpeg += ms_since(t0);
     return plan_.prefix.size() + nbytes + num_ff + plan_.trailer.size();
+  }
+
+  // DC symbol counts of the current candidate (device pass), for encoded_size(host_ac)
+  void capture_dc_histograms() {
+    unsigned int hist[6][257];
+    bool chroma = false;
+    ctx_->jpeg_histograms(&hist[0][0], &chroma);
+    memcpy(sfm_dc_hist_, hist, sizeof(sfm_dc_hist_));
   }
 
   std::string fetch_encoded() {
@@ -568,6 +601,7 @@ class Search {
     m.header_size = static_cast<int>(jpeg_header_bytes(img_));
     m.dc_size = static_cast<int>(estimate_dc_bytes(img_));
     build_ac_histograms(img_, m.ac_h);
+    capture_dc_histograms();
     m.ac_depths.resize(3 * SymbolHistogram::kSize);
     m.ac_histogram_size = static_cast<int>(compute_entropy_codes(m.ac_h, m.ac_depths.data()));
     const int base_size = m.header_size + m.dc_size + m.ac_histogram_size +
@@ -734,7 +768,7 @@ class Search {
         ++st_->iterations;
         if (direction > 0) ++st_->iterations_up; else ++st_->iterations_down;
         ctx_->scatter_coeffs(m.edit_index, m.edit_value);
-        const size_t encoded = encoded_size();
+        const size_t encoded = encoded_size(m.ac_h);
         logf("Iter %2d: %s(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
              st_->iterations, "f111111", 7, direction > 0 ? "up" : "down", static_cast<int>(out.consumed),
              order_size, out.changed_blocks, blocks_to_change, num_blocks, out.val_threshold, encoded,
@@ -759,6 +793,7 @@ class Search {
   JpegPlan plan_;
   size_t scan_bytes_ = 0;
   int tie_fallbacks_ = 0;
+  unsigned int sfm_dc_hist_[3][257];
   bool jpeg_source_ = false;
   int q_in_[3][64];
   const JpegFileLayout* layout_ = nullptr;

@@ -6,6 +6,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+# every frequency-masking iteration also runs the device histogram pass and checks the
+# host-maintained symbol histograms against it (search.cc, encoded_size)
+os.environ.setdefault("GB200_CHECK_HOST_HIST", "1")
 
 
 def pytest_configure(config):
