@@ -12,6 +12,7 @@
 #if !defined(GB200_HOSTSIM)
 #include "tiled_kernels.cuh"
 #include "zeroing_warp.cuh"
+#include "render_warp.cuh"
 #endif
 
 namespace gb200 {
@@ -380,11 +381,19 @@ float ImageContext::compare() {
     for (size_t i = 0; i < keep; ++i) dirty_flag_[dirty_list_[i]] = 1;
   }
   if (render_all_ || dirty_list_.size() > static_cast<size_t>(rb_hi - rb_lo) * g_.bw / 2) {
+#if defined(GB200_HOSTSIM)
     block_rows(RenderBlocks{d_cand_, lin_, g_, t_}, "render_blocks", rb_lo, rb_hi);
+#else
+    launch_render_blocks_warp(s_, RenderWarpArgs{d_cand_, lin_, nullptr, rb_lo * g_.bw, (rb_hi - rb_lo) * g_.bw, g_, t_});
+#endif
   } else if (!dirty_list_.empty()) {
     const int nd = static_cast<int>(dirty_list_.size());
     h2d(d_dirty_, dirty_list_.data(), sizeof(int) * nd, s_);
+#if defined(GB200_HOSTSIM)
     launch_1d(s_, RenderBlockList{RenderBlocks{d_cand_, lin_, g_, t_}, d_dirty_}, nd, "render_blocks");
+#else
+    launch_render_blocks_warp(s_, RenderWarpArgs{d_cand_, lin_, d_dirty_, 0, nd, g_, t_});
+#endif
   }
   render_all_ = false;
   for (size_t i = 0; i < dirty_list_.size(); ++i) dirty_flag_[dirty_list_[i]] = 0;
