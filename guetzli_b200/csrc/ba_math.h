@@ -141,36 +141,38 @@ GB_HD float suppress_x_by_y(float xv, float yv) {
 // ---------------------------------------------------------------------------
 // Malta pre-pass (butteraugli.cc:1476-1529): one "diffs" sample.
 GB_HD float malta_diff(float v0, float v1, const MaltaParams& mp) {
-  const float absval =
-      static_cast<float>(0.5 * static_cast<double>(hd_fabsf(v0)) + 0.5 * static_cast<double>(hd_fabsf(v1)));
+  // one float -> double conversion per input; everything below reuses them
+  const double r0 = v0, r1 = v1;
+  const double fabs0 = ::fabs(r0), fabs1 = ::fabs(r1);
+  const float absval = static_cast<float>(0.5 * fabs0 + 0.5 * fabs1);
   const float diff = v0 - v1;
-  const float scaler = mp.norm2_0gt1 / (mp.norm1 + absval);
-  float d = scaler * diff;
-  const float scaler2 = mp.norm2_0lt1 / (mp.norm1 + absval);
-  const double fabs0 = hd_fabsf(v0);
+  const float den = mp.norm1 + absval;
+  float d = (mp.norm2_0gt1 / den) * diff;
   const double too_small = 0.55 * fabs0;
   const double too_big = 1.05 * fabs0;
-  const double r1 = v1;
-  double impact;
+  // which half-open objective applies, if any (the second division only happens then)
+  double excess;
   bool has = false;
   if (v0 < 0) {
     if (r1 > -too_small) {
-      impact = scaler2 * (r1 + too_small);
+      excess = r1 + too_small;
       has = true;
     } else if (r1 < -too_big) {
-      impact = scaler2 * (-r1 - too_big);
+      excess = -r1 - too_big;
       has = true;
     }
   } else {
     if (r1 < too_small) {
-      impact = scaler2 * (too_small - r1);
+      excess = too_small - r1;
       has = true;
     } else if (r1 > too_big) {
-      impact = scaler2 * (r1 - too_big);
+      excess = r1 - too_big;
       has = true;
     }
   }
   if (has) {
+    const float scaler2 = mp.norm2_0lt1 / den;
+    const double impact = scaler2 * excess;
     if (diff < 0) {
       d = static_cast<float>(static_cast<double>(d) - impact);
     } else {

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--w", type=int, default=1920)
     ap.add_argument("--n", type=int, default=20)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--zeroing", action="store_true", help="also run the zeroing-order kernel (a14) once")
     args = ap.parse_args()
     lib = gb.load_library()
     rgb = synth.noise(args.h, args.w, 1234)
@@ -29,6 +30,8 @@ def main():
     q = np.full(192, 3, dtype=np.int32)
     img.apply_global_quant(q)
     d = img.compare()  # warm-up
+    if args.zeroing:
+        img.zeroing_orders(1.0)
     lib.gb200_profile_reset()
     lib.gb200_profile_enable(1)
     t0 = time.perf_counter()
