@@ -52,8 +52,9 @@ ALG_BYTES = {
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu
 # --set full captures (profiles/), bytes; None until captured.
 NCU_TRAFFIC = {
-    # profiles/r01_ncu_full_malta_blur.csv (noise1080p, per launch: read + write)
-    "malta_channel": 49.8e6 + 8.6e6,
+    # profiles/r01_final2_ncu_full.csv (k_malta_pre3 + k_malta_sums) and r01_ncu_full_malta_blur.csv
+    # (noise1080p, per launch: read + write)
+    "malta_channel": 49.8e6 + 1.7e6 + 24.9e6,
     "blur_x": 8.33e6, "blur_y": 8.32e6,
 }
 
