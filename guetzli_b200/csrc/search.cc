@@ -386,6 +386,7 @@ class Search {
     float val_threshold = 0.0f;
     int est_jpg_size = 0;
     bool ambiguous = false;    // check_ties only: result depends on the order of equal keys
+    int why = 0;               // diagnostic: which rule flagged the ambiguity
   };
 
   // The sequential selection walk (g/processor.cc:700-750) over `order`.
@@ -508,6 +509,7 @@ class Search {
         // tractable case: a run of exactly two entries at a plain stop test
         if (!pair_only || refresh_here || !can_test) {
           out.ambiguous = true;
+          out.why = !pair_only ? (refresh_here ? 1 : 2) : (refresh_here ? 3 : 4);
           return out;
         }
         const int other = order[i + 1].first;
@@ -550,6 +552,7 @@ class Search {
           const bool alt_stop = std::abs(alt_est - prev_size) > min_size_delta;
           if (stop || alt_stop) {
             out.ambiguous = true;
+            out.why = 5;
             return out;
           }
         }
@@ -664,6 +667,7 @@ class Search {
             std::vector<float> val;
             std::vector<int> blk;
             const size_t total = ctx_->order_smallest(direction, m.last_indexes, m.max_block_error, want, &val, &blk);
+            dbg_ms_[0] += ms_since(t0);
             if (total != order_size) throw std::runtime_error("order_smallest: entry count mismatch");
             if (val.size() >= order_size) break;
             order.resize(val.size());
@@ -691,6 +695,7 @@ class Search {
             st_->ms_walk += ms_since(tw);
             if (out.ambiguous) {
               ++tie_fallbacks_;
+              ++tie_why_[out.why];
               unwalk(m, order, out, direction, saved_h, saved_hist_size, saved_depths);
               break;  // take the exact path
             }
@@ -744,6 +749,8 @@ class Search {
               min_coeffs = std::max<int>(min_coeffs, static_cast<int>(below));
             }
             if (want > order.size()) want = order.size();
+            dbg_ms_[1] += ms_since(t0);
+            dbg_n_[0] += order.size();
             const size_t k_end = exact_sort::partial_std_sort(order.data(), order.size(), want);
             order.resize(k_end);
             st_->ms_sort += ms_since(t0);
@@ -778,6 +785,13 @@ class Search {
         prev_size = out.est_jpg_size;
       }
     }
+    if (getenv("GB200_TIE_DEBUG"))
+      fprintf(stderr, "tie fallbacks %d: run-at-refresh %d, run-at-test %d, pair-at-refresh %d, pair-untestable %d, pair-decides %d; exact %d partial %d\n",
+              tie_fallbacks_, tie_why_[1], tie_why_[2], tie_why_[3], tie_why_[4], tie_why_[5], st_->order_exact,
+              st_->order_partial);
+    if (getenv("GB200_TIE_DEBUG"))
+      fprintf(stderr, "order timing: device top-K fetch %.1f ms, exact-order build %.1f ms over %zu entries, sort total %.1f ms, walk %.1f ms\n",
+              dbg_ms_[0], dbg_ms_[1], dbg_n_[0], st_->ms_sort, st_->ms_walk);
   }
 
   SearchParams params_;
@@ -793,6 +807,9 @@ class Search {
   JpegPlan plan_;
   size_t scan_bytes_ = 0;
   int tie_fallbacks_ = 0;
+  int tie_why_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double dbg_ms_[4] = {0, 0, 0, 0};   // GB200_TIE_DEBUG: device top-K fetch, exact-order build
+  size_t dbg_n_[2] = {0, 0};
   unsigned int sfm_dc_hist_[3][257];
   bool jpeg_source_ = false;
   int q_in_[3][64];
