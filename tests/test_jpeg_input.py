@@ -51,6 +51,33 @@ def test_reader_matches_reference(port_lib, name):
         assert hashlib.sha256(coeffs.tobytes()).hexdigest() == g["coeffs_sha256"]
 
 
+@pytest.mark.parametrize("name", ["base444_q90", "prog444_q85", "restart444_prog", "sub420", "gray", "odd444_prog",
+                                  "meta_kept"])
+def test_reader_differential_on_damaged_files(port_lib, ref, name):
+    """Byte edits, bit flips and truncations of the fixtures: the parser must accept / reject and
+    decode exactly like ReadJpeg (run live against oracle/_ref)."""
+    import numpy as np
+    rng = np.random.default_rng(sum(name.encode()))
+    data = fixture(name)
+    accepted = 0
+    for t in range(60):
+        b = bytearray(data)
+        if t % 3 == 0:
+            for _ in range(rng.integers(1, 4)):
+                b[rng.integers(2, len(b))] = rng.integers(0, 256)
+        elif t % 3 == 1:
+            b[rng.integers(2, len(b))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            b = b[:rng.integers(10, len(b))] + bytearray([0xff, 0xd9])
+        rok, rdims, rcoeffs = ref.read_jpeg(bytes(b))
+        ok, dims, coeffs = gb.api.read_jpeg(bytes(b), lib=port_lib)
+        assert ok == rok, (name, t)
+        if ok:
+            accepted += 1
+            assert dims == rdims and np.array_equal(coeffs, rcoeffs), (name, t)
+    assert accepted > 0
+
+
 @pytest.mark.parametrize("name", sorted(GOLDEN))
 def test_port_process_jpeg_matches_golden(port_lib, name):
     check_case(port_lib, name)

@@ -92,3 +92,15 @@ def test_partial_order_is_arrangement_independent(port_lib, ref, monkeypatch):
         ok, jpeg, trace, st = parity.run_process(port_lib, rgb, 95)
         assert st.device["order_partial"] > 50
         assert trace == rtrace and jpeg == rjpeg
+
+
+def test_process_is_reentrant(port_lib):
+    """Process() from several host threads at once (one context + stream per call, the
+    batch mode of bench.py): every result equals the sequential one."""
+    from concurrent.futures import ThreadPoolExecutor
+    jobs = [(synth.gradnoise(40 + 8 * i, 48, 20 + i), 88 + i) for i in range(6)]
+    jobs.append((synth.noise(24, 40, 3), 95))   # below 32 px: no search
+    seq = [parity.run_process(port_lib, rgb, q)[:3] for rgb, q in jobs]
+    with ThreadPoolExecutor(4) as pool:
+        par = list(pool.map(lambda j: parity.run_process(port_lib, j[0], j[1])[:3], jobs * 2))
+    assert par == seq + seq
