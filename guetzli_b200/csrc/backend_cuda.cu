@@ -108,16 +108,41 @@ void h2d(void* dst, const void* src, size_t n, Stream s) {
   g_h2d_bytes += static_cast<long long>(n);
   GB_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s));
 }
+// Waiting for a stream.  cudaStreamSynchronize spins on the host; that is the lowest latency
+// for one image, but with many image contexts in flight (batch mode: one host thread per
+// image, times one process per GPU) the spinning threads take the cores that the other
+// threads' selection walks need.  With more than two live streams in the process the wait
+// therefore sleeps on a blocking event instead.  GB200_SYNC=spin|block forces either.
+static std::atomic<int> g_live_streams(0);
+static void wait_stream(Stream s) {
+  static const int forced = [] {
+    const char* e = getenv("GB200_SYNC");
+    return e == nullptr ? 0 : (e[0] == 'b' ? 2 : 1);
+  }();
+  const bool block = forced ? forced == 2 : g_live_streams.load(std::memory_order_relaxed) > 2;
+  if (!block) {
+    GB_CUDA(cudaStreamSynchronize(s));
+    return;
+  }
+  thread_local std::map<int, cudaEvent_t> events;  // one per device this thread has used
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  cudaEvent_t& ev = events[dev];
+  if (ev == nullptr) GB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming));
+  GB_CUDA(cudaEventRecord(ev, s));
+  GB_CUDA(cudaEventSynchronize(ev));
+}
+
 void d2h(void* dst, const void* src, size_t n, Stream s) {
   g_d2h_bytes += static_cast<long long>(n);
   GB_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, s));
-  GB_CUDA(cudaStreamSynchronize(s));
+  wait_stream(s);
 }
 void d2d(void* dst, const void* src, size_t n, Stream s) {
   GB_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s));
 }
 void dev_zero(void* dst, size_t n, Stream s) { GB_CUDA(cudaMemsetAsync(dst, 0, n, s)); }
-void stream_sync(Stream s) { GB_CUDA(cudaStreamSynchronize(s)); }
+void stream_sync(Stream s) { wait_stream(s); }
 
 int cuda_device_count() {
   int n = 0;
@@ -138,10 +163,14 @@ void select_device(int device) {
 Stream make_stream() {
   cudaStream_t s;
   GB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  ++g_live_streams;
   return s;
 }
 
-void destroy_stream(Stream s) { cudaStreamDestroy(s); }
+void destroy_stream(Stream s) {
+  --g_live_streams;
+  cudaStreamDestroy(s);
+}
 
 namespace {
 struct Prof {
