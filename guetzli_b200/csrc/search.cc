@@ -652,7 +652,8 @@ class Search {
         const float coeffs_to_change_per_block = direction > 0 ? 2.0f : 1 * 1 * 0.2f;
         int min_coeffs_to_change = coeffs_to_change_per_block * blocks_to_change;
 
-        std::vector<std::pair<int, float> > order;
+        std::vector<std::pair<int, float> >& order = order_buf_;  // capacity kept across iterations: no page faults
+        order.clear();
         WalkOutcome out;
         bool done = false;
         // Fast path ("down" iterations consume a tiny prefix of the order): fetch only
@@ -767,7 +768,7 @@ class Search {
         }
         first_up_iter = false;
         last_consumed = out.consumed;
-        std::vector<std::pair<int, float> >().swap(order);
+        order.clear();
 
         for (int i = 0; i < num_blocks; ++i)
           m.max_block_error[i] += block_weight[i] * out.val_threshold * direction;
@@ -806,6 +807,7 @@ class Search {
   std::vector<int16_t> cand_;
   JpegPlan plan_;
   size_t scan_bytes_ = 0;
+  std::vector<std::pair<int, float> > order_buf_;
   int tie_fallbacks_ = 0;
   int tie_why_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double dbg_ms_[4] = {0, 0, 0, 0};   // GB200_TIE_DEBUG: device top-K fetch, exact-order build
