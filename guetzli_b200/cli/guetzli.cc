@@ -1,14 +1,16 @@
-// Drop-in `guetzli` command line (guetzli/guetzli.cc:232-326): same flags, same
-// exit codes, same messages; the work goes through guetzli::Process(RGB) of
-// include/guetzli_b200_compat.h (C ABI of libguetzli_b200.so).  JPEG input (4:4:4)
-// goes through guetzli::Process(jpeg bytes) of the same header.
+// `guetzli` command line on top of libguetzli_b200.so.
+//
+// Behavioural contract = the reference tool (guetzli/guetzli.cc:155-326, exercised by
+// tests/smoke_test.sh): `guetzli [--verbose] [--quality Q] [--memlimit M] [--nomemlimit]
+// [--] in out`, "-" for stdin / stdout, PNG or JPEG input told apart by the PNG signature,
+// every failure (usage included) exits with 1 after the reference's message on stderr.
+// The encoding itself is guetzli::Process of include/guetzli_b200_compat.h.
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
-#include <algorithm>
 #include <exception>
-#include <memory>
 #include <string>
 #include <vector>
 
@@ -17,147 +19,144 @@
 
 namespace {
 
-constexpr int kDefaultJPEGQuality = 95;
-constexpr int kBytesPerPixel = 350;
-constexpr int kLowestMemusageMB = 100;
-constexpr int kDefaultMemlimitMB = 6000;
+struct Options {
+  bool verbose = false;
+  int quality = 95;        // --quality
+  int memlimit_mb = 6000;  // --memlimit; -1 = --nomemlimit
+  const char* input = nullptr;
+  const char* output = nullptr;
+};
 
-std::string ReadFileOrDie(const char* filename) {
-  const bool read_from_stdin = strncmp(filename, "-", 2) == 0;
-  FILE* f = read_from_stdin ? stdin : fopen(filename, "rb");
-  if (!f) {
-    perror("Can't open input file");
-    exit(1);
-  }
-  std::string result;
-  char buf[1 << 16];
-  for (;;) {
-    const size_t n = fread(buf, 1, sizeof(buf), f);
-    if (ferror(f)) {
-      perror("fread");
-      exit(1);
+[[noreturn]] void UsageAndExit() {
+  static const char kText[] =
+      "Guetzli JPEG compressor. Usage: \n"
+      "guetzli [flags] input_filename output_filename\n"
+      "\n"
+      "Flags:\n"
+      "  --verbose    - Print a verbose trace of all attempts to standard output.\n"
+      "  --quality Q  - Visual quality to aim for, expressed as a JPEG quality value.\n"
+      "                 Default value is %d.\n"
+      "  --memlimit M - Memory limit in MB. Guetzli will fail if unable to stay under\n"
+      "                 the limit. Default limit is %d MB.\n"
+      "  --nomemlimit - Do not limit memory usage.\n";
+  const Options defaults;
+  fprintf(stderr, kText, defaults.quality, defaults.memlimit_mb);
+  exit(1);
+}
+
+[[noreturn]] void DieWithErrno(const char* what) {
+  perror(what);
+  exit(1);
+}
+
+// Flags are the leading arguments that start with "--"; a bare "--" ends them.  Exactly two
+// positional arguments must remain.
+Options ParseCommandLine(int argc, char** argv) {
+  Options o;
+  int i = 1;
+  auto value_of = [&](int* into) {
+    if (++i >= argc) UsageAndExit();
+    *into = atoi(argv[i]);
+  };
+  while (i < argc && strncmp(argv[i], "--", 2) == 0) {
+    const std::string flag = argv[i];
+    if (flag == "--") {
+      ++i;
+      break;
     }
-    result.append(buf, n);
-    if (n == 0 || feof(f)) break;
+    if (flag == "--verbose") {
+      o.verbose = true;
+    } else if (flag == "--quality") {
+      value_of(&o.quality);
+    } else if (flag == "--memlimit") {
+      value_of(&o.memlimit_mb);
+    } else if (flag == "--nomemlimit") {
+      o.memlimit_mb = -1;
+    } else {
+      fprintf(stderr, "Unknown commandline flag: %s\n", argv[i]);
+      UsageAndExit();
+    }
+    ++i;
   }
-  if (!read_from_stdin) fclose(f);
-  return result;
+  if (argc - i != 2) UsageAndExit();
+  o.input = argv[i];
+  o.output = argv[i + 1];
+  return o;
 }
 
-void WriteFileOrDie(const char* filename, const std::string& contents) {
-  const bool write_to_stdout = strncmp(filename, "-", 2) == 0;
-  FILE* f = write_to_stdout ? stdout : fopen(filename, "wb");
-  if (!f) {
-    perror("Can't open output file for writing");
-    exit(1);
-  }
-  if (fwrite(contents.data(), 1, contents.size(), f) != contents.size()) {
-    perror("fwrite");
-    exit(1);
-  }
-  if (fclose(f) < 0) {
-    perror("fclose");
-    exit(1);
-  }
+bool IsDash(const char* name) { return name[0] == '-' && name[1] == '\0'; }
+
+std::string Slurp(const char* name) {
+  FILE* f = IsDash(name) ? stdin : fopen(name, "rb");
+  if (f == nullptr) DieWithErrno("Can't open input file");
+  std::string bytes;
+  std::vector<char> chunk(1 << 16);
+  size_t got;
+  while ((got = fread(chunk.data(), 1, chunk.size(), f)) > 0) bytes.append(chunk.data(), got);
+  if (ferror(f)) DieWithErrno("fread");
+  if (f != stdin) fclose(f);
+  return bytes;
 }
 
-void TerminateHandler() {
+void Spill(const char* name, const std::string& bytes) {
+  FILE* f = IsDash(name) ? stdout : fopen(name, "wb");
+  if (f == nullptr) DieWithErrno("Can't open output file for writing");
+  if (fwrite(bytes.data(), 1, bytes.size(), f) != bytes.size()) DieWithErrno("fwrite");
+  if (fclose(f) < 0) DieWithErrno("fclose");
+}
+
+// The reference budgets 350 bytes per pixel and refuses limits under 100 MB.
+bool WithinMemoryLimit(const Options& o, int width, int height) {
+  if (o.memlimit_mb == -1) return true;
+  const double need_mb = static_cast<double>(width) * height * 350 / (1 << 20);
+  return need_mb <= o.memlimit_mb && o.memlimit_mb >= 100;
+}
+
+bool LooksLikePng(const std::string& bytes) {
+  static const unsigned char kSignature[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+  return bytes.size() >= sizeof(kSignature) && memcmp(bytes.data(), kSignature, sizeof(kSignature)) == 0;
+}
+
+int Fail(const char* message) {
+  fprintf(stderr, "%s\n", message);
+  return 1;
+}
+
+void OnUnhandledException() {
   fprintf(stderr,
           "Unhandled exception. Most likely insufficient memory available.\n"
           "Make sure that there is 300MB/MPix of memory available.\n");
   exit(1);
 }
 
-void Usage() {
-  fprintf(stderr,
-          "Guetzli JPEG compressor. Usage: \n"
-          "guetzli [flags] input_filename output_filename\n"
-          "\n"
-          "Flags:\n"
-          "  --verbose    - Print a verbose trace of all attempts to standard output.\n"
-          "  --quality Q  - Visual quality to aim for, expressed as a JPEG quality value.\n"
-          "                 Default value is %d.\n"
-          "  --memlimit M - Memory limit in MB. Guetzli will fail if unable to stay under\n"
-          "                 the limit. Default limit is %d MB.\n"
-          "  --nomemlimit - Do not limit memory usage.\n",
-          kDefaultJPEGQuality, kDefaultMemlimitMB);
-  exit(1);
-}
-
 }  // namespace
 
 int main(int argc, char** argv) {
-  std::set_terminate(TerminateHandler);
-  int verbose = 0;
-  int quality = kDefaultJPEGQuality;
-  int memlimit_mb = kDefaultMemlimitMB;
-  int opt_idx = 1;
-  for (; opt_idx < argc; opt_idx++) {
-    if (strnlen(argv[opt_idx], 2) < 2 || argv[opt_idx][0] != '-' || argv[opt_idx][1] != '-') break;
-    if (!strcmp(argv[opt_idx], "--verbose")) {
-      verbose = 1;
-    } else if (!strcmp(argv[opt_idx], "--quality")) {
-      opt_idx++;
-      if (opt_idx >= argc) Usage();
-      quality = atoi(argv[opt_idx]);
-    } else if (!strcmp(argv[opt_idx], "--memlimit")) {
-      opt_idx++;
-      if (opt_idx >= argc) Usage();
-      memlimit_mb = atoi(argv[opt_idx]);
-    } else if (!strcmp(argv[opt_idx], "--nomemlimit")) {
-      memlimit_mb = -1;
-    } else if (!strcmp(argv[opt_idx], "--")) {
-      opt_idx++;
-      break;
-    } else {
-      fprintf(stderr, "Unknown commandline flag: %s\n", argv[opt_idx]);
-      Usage();
-    }
-  }
-  if (argc - opt_idx != 2) Usage();
+  std::set_terminate(OnUnhandledException);
+  const Options opt = ParseCommandLine(argc, argv);
+  const std::string input = Slurp(opt.input);
 
-  std::string in_data = ReadFileOrDie(argv[opt_idx]);
-  std::string out_data;
   guetzli::Params params;
-  params.butteraugli_target = static_cast<float>(guetzli::ButteraugliScoreForQuality(quality));
+  params.butteraugli_target = static_cast<float>(guetzli::ButteraugliScoreForQuality(opt.quality));
   guetzli::ProcessStats stats;
-  if (verbose) stats.debug_output_file = stderr;
+  if (opt.verbose) stats.debug_output_file = stderr;
 
-  static const unsigned char kPNGMagicBytes[] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
-  if (in_data.size() >= 8 && memcmp(in_data.data(), kPNGMagicBytes, sizeof(kPNGMagicBytes)) == 0) {
-    int xsize, ysize;
+  std::string jpeg;
+  int width = 0, height = 0;
+  bool ok;
+  if (LooksLikePng(input)) {
     std::vector<uint8_t> rgb;
-    if (!gb200_cli::ReadPNG(in_data, &xsize, &ysize, &rgb)) {
-      fprintf(stderr, "Error reading PNG data from input file\n");
-      return 1;
-    }
-    const double pixels = static_cast<double>(xsize) * ysize;
-    if (memlimit_mb != -1 &&
-        (pixels * kBytesPerPixel / (1 << 20) > memlimit_mb || memlimit_mb < kLowestMemusageMB)) {
-      fprintf(stderr, "Memory limit would be exceeded. Failing.\n");
-      return 1;
-    }
-    if (!guetzli::Process(params, &stats, rgb, xsize, ysize, &out_data)) {
-      fprintf(stderr, "Guetzli processing failed\n");
-      return 1;
-    }
+    if (!gb200_cli::ReadPNG(input, &width, &height, &rgb)) return Fail("Error reading PNG data from input file");
+    if (!WithinMemoryLimit(opt, width, height)) return Fail("Memory limit would be exceeded. Failing.");
+    ok = guetzli::Process(params, &stats, rgb, width, height, &jpeg);
   } else {
-    int xsize = 0, ysize = 0;
-    if (!gb200_jpeg_dimensions(reinterpret_cast<const uint8_t*>(in_data.data()), in_data.size(), &xsize, &ysize)) {
-      fprintf(stderr, "Error reading JPG data from input file\n");
-      return 1;
-    }
-    const double pixels = static_cast<double>(xsize) * ysize;
-    if (memlimit_mb != -1 &&
-        (pixels * kBytesPerPixel / (1 << 20) > memlimit_mb || memlimit_mb < kLowestMemusageMB)) {
-      fprintf(stderr, "Memory limit would be exceeded. Failing.\n");
-      return 1;
-    }
-    if (!guetzli::Process(params, &stats, in_data, &out_data)) {
-      fprintf(stderr, "Guetzli processing failed\n");
-      return 1;
-    }
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(input.data());
+    if (!gb200_jpeg_dimensions(bytes, input.size(), &width, &height))
+      return Fail("Error reading JPG data from input file");
+    if (!WithinMemoryLimit(opt, width, height)) return Fail("Memory limit would be exceeded. Failing.");
+    ok = guetzli::Process(params, &stats, input, &jpeg);
   }
-  WriteFileOrDie(argv[opt_idx + 1], out_data);
+  if (!ok) return Fail("Guetzli processing failed");
+  Spill(opt.output, jpeg);
   return 0;
 }
