@@ -104,3 +104,15 @@ def test_process_is_reentrant(port_lib):
     with ThreadPoolExecutor(4) as pool:
         par = list(pool.map(lambda j: parity.run_process(port_lib, j[0], j[1])[:3], jobs * 2))
     assert par == seq + seq
+
+
+def test_repeated_blocks_tie_everywhere(port_lib, ref):
+    """An image made of two copies of the same noise tile: every block has a twin with
+    bit-identical candidate errors, so the global order is full of equal keys of
+    different blocks.  The device top-K path must notice where the arrangement of such
+    runs matters (and then take the reference-ordered sort) and still end up with the
+    reference's bytes and trace."""
+    import numpy as np
+    rgb = np.ascontiguousarray(np.tile(synth.noise(112, 112, 11), (1, 2, 1)))
+    st = parity.check_process_vs_ref(port_lib, ref, rgb, 94)
+    assert st.device["order_exact"] > 100 and st.device["order_partial"] > 50
