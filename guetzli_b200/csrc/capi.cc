@@ -485,6 +485,21 @@ size_t gb200_debug_partial_sort(int* block, float* key, size_t n, size_t want) {
   }
   return k;
 }
+// the same replay with the large partition passes on the device (order_exact.h); needs an image
+// context only for its stream and scratch
+size_t gb200_debug_device_partial_sort(gb200_image* img, int* block, float* key, size_t n, size_t want) {
+  size_t k = 0;
+  guarded([&]() {
+    std::vector<gb200::exact_sort::Item> v(n);
+    for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(block[i], key[i]);
+    k = img->ctx->debug_device_partial_sort(v.data(), n, want);
+    for (size_t i = 0; i < k; ++i) {
+      block[i] = v[i].first;
+      key[i] = v[i].second;
+    }
+  });
+  return k;
+}
 void gb200_debug_std_sort(int* block, float* key, size_t n) {
   std::vector<std::pair<int, float> > v(n);
   for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(block[i], key[i]);

@@ -86,22 +86,18 @@ inline void insertion_sort(Item* a, ptrdiff_t first, ptrdiff_t last) {
   }
 }
 
-inline size_t partial_std_sort(Item* a, size_t n_, size_t want_) {
-  const ptrdiff_t n = static_cast<ptrdiff_t>(n_);
-  const ptrdiff_t want = static_cast<ptrdiff_t>(want_ < n_ ? want_ : n_);
-  if (n < 2) return n_;
-  // std::__introsort_loop(first, last, 2 * floor(log2(n))) with an explicit stack of the
-  // right-hand sub-ranges; sub-ranges starting at or beyond `want` are never needed.
-  ptrdiff_t depth_limit = 0;
-  for (ptrdiff_t m = n; m > 1; m >>= 1) ++depth_limit;
-  depth_limit *= 2;
+// std::__introsort_loop on a[first, last) with `depth` levels left, restricted to the
+// sub-ranges that start before `want`; *k_end grows to the end of the last leaf range
+// (<= 16 elements, not yet insertion-sorted) visited.  partition(first, last) may be
+// replaced by an equivalent implementation (order_exact.h runs large ranges on the device).
+inline void introsort_prefix(Item* a, ptrdiff_t first0, ptrdiff_t last0, ptrdiff_t depth0, ptrdiff_t want,
+                             ptrdiff_t* k_end) {
   ptrdiff_t st_first[160], st_last[160], st_depth[160];
   int sp = 0;
-  st_first[sp] = 0;
-  st_last[sp] = n;
-  st_depth[sp] = depth_limit;
+  st_first[sp] = first0;
+  st_last[sp] = last0;
+  st_depth[sp] = depth0;
   ++sp;
-  ptrdiff_t k_end = 0;  // end of the last leaf range that starts before `want`
   while (sp > 0) {
     --sp;
     ptrdiff_t first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
@@ -145,19 +141,37 @@ inline size_t partial_std_sort(Item* a, size_t n_, size_t want_) {
       }
       last = cut;
     }
-    if (last > k_end) k_end = last;  // leaf range [first, last), first < want
+    if (last > *k_end) *k_end = last;  // leaf range [first, last), first < want
   }
-  // ranges are visited right-to-left within a parent, so k_end is the maximum end
-  // over all leaf ranges that start before `want`; they tile [0, k_end).
-  // std::__final_insertion_sort restricted to that prefix.
+}
+
+inline ptrdiff_t introsort_depth_limit(ptrdiff_t n) {
+  ptrdiff_t depth_limit = 0;
+  for (ptrdiff_t m = n; m > 1; m >>= 1) ++depth_limit;
+  return 2 * depth_limit;
+}
+
+// std::__final_insertion_sort of an n-element array restricted to the prefix [0, k_end).
+inline void final_insertion_prefix(Item* a, ptrdiff_t n, ptrdiff_t* k_end) {
   if (n > 16) {
-    const ptrdiff_t head = k_end < 16 ? k_end : 16;
+    const ptrdiff_t head = *k_end < 16 ? *k_end : 16;
     insertion_sort(a, 0, head);
-    for (ptrdiff_t i = 16; i < k_end; ++i) unguarded_linear_insert(a, i);
+    for (ptrdiff_t i = 16; i < *k_end; ++i) unguarded_linear_insert(a, i);
   } else {
     insertion_sort(a, 0, n);
-    k_end = n;
+    *k_end = n;
   }
+}
+
+inline size_t partial_std_sort(Item* a, size_t n_, size_t want_) {
+  const ptrdiff_t n = static_cast<ptrdiff_t>(n_);
+  const ptrdiff_t want = static_cast<ptrdiff_t>(want_ < n_ ? want_ : n_);
+  if (n < 2) return n_;
+  // ranges are visited right-to-left within a parent, so k_end is the maximum end over all
+  // leaf ranges that start before `want`; they tile [0, k_end).
+  ptrdiff_t k_end = 0;
+  introsort_prefix(a, 0, n, introsort_depth_limit(n), want, &k_end);
+  final_insertion_prefix(a, n, &k_end);
   return static_cast<size_t>(k_end);
 }
 

@@ -1,6 +1,8 @@
 // Kernel sequences of the hot path (see pipeline.h).  Compiled by nvcc for
 // sm_100a in the product, and by g++ -DGB200_HOSTSIM for the CPU port.
 #include "pipeline.h"
+#include "exact_sort.h"
+#include "order_exact.h"
 
 #include <string.h>
 
@@ -288,6 +290,10 @@ ImageContext::~ImageContext() {
   stream_sync(s_);
   if (d_sel_val_) dev_free(d_sel_val_);
   if (d_sel_block_) dev_free(d_sel_block_);
+  if (x_items_) dev_free(x_items_);
+  if (x_u32_) dev_free(x_u32_);
+  if (x_i32_) dev_free(x_i32_);
+  if (x_small_) dev_free(x_small_);
   if (j_words_) dev_free(j_words_);
   if (d_edit_i_) dev_free(d_edit_i_);
   if (d_edit_v_) dev_free(d_edit_v_);
@@ -366,7 +372,6 @@ void ImageContext::download_candidate(int16_t* coeffs) {
 }
 
 float ImageContext::compare() {
-  const size_t P = g_.plane;
   // S0 render (only blocks edited since the last render), S1 opsin, S2-S6 frequency split
   const int rb_lo = cr_lo_ / 8, rb_hi = (cr_hi_ + 7) / 8;  // block rows that intersect the computed rows
   if (comm_ && comm_->world() > 1 && !render_all_) {
@@ -625,9 +630,156 @@ size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_
 }
 
 // ---------------------------------------------------------------------------
+// EXPERIMENTAL: reference-ordered selection order with the large partition passes on the
+// device (order_exact.h).  Ranges of at most kOrderHostRange items go back to the host replay.
+static const ptrdiff_t kOrderHostRange = [] {
+  const char* e = getenv("GB200_ORDER_HOST_RANGE");  // tests lower it to reach the device passes on small images
+  const long v = e ? atol(e) : 0;
+  return static_cast<ptrdiff_t>(v >= 16 ? v : (1 << 15));
+}();
+
+void ImageContext::order_scratch(size_t n) {
+  if (n <= x_cap_) return;
+  stream_sync(s_);
+  if (x_items_) dev_free(x_items_);
+  if (x_u32_) dev_free(x_u32_);
+  if (x_i32_) dev_free(x_i32_);
+  if (x_small_) dev_free(x_small_);
+  x_cap_ = n + n / 4 + 1024;
+  x_items_ = static_cast<OrderItem*>(dev_alloc(x_cap_ * sizeof(OrderItem)));
+  x_u32_ = static_cast<unsigned int*>(dev_alloc(4 * x_cap_ * sizeof(unsigned int)));
+  x_i32_ = static_cast<int*>(dev_alloc(2 * x_cap_ * sizeof(int)));
+  x_small_ = static_cast<unsigned int*>(dev_alloc((x_cap_ / 1024 + 64) * sizeof(unsigned int) + 64));
+}
+
+size_t ImageContext::device_partial_sort_resident(size_t n_, size_t want_, std::vector<std::pair<int, float> >* out) {
+  typedef exact_sort::Item Item;
+  static_assert(sizeof(Item) == sizeof(OrderItem), "pair<int,float> layout");
+  const ptrdiff_t n = static_cast<ptrdiff_t>(n_);
+  const ptrdiff_t want = static_cast<ptrdiff_t>(want_ < n_ ? want_ : n_);
+  if (n < 2 || n <= kOrderHostRange) {
+    out->resize(n_);
+    if (n_) d2h(out->data(), x_items_, n_ * sizeof(Item), s_);
+    const size_t k = exact_sort::partial_std_sort(out->data(), n_, want_);
+    out->resize(k);
+    return k;
+  }
+  // host mirror of the prefix, filled range by range as the replay hands ranges back
+  Item* host = static_cast<Item*>(malloc(n_ * sizeof(Item)));
+  if (host == nullptr) throw std::bad_alloc();
+  unsigned int* fl = x_u32_;
+  unsigned int* sl = x_u32_ + x_cap_;
+  unsigned int* fr = x_u32_ + 2 * x_cap_;
+  unsigned int* sr = x_u32_ + 3 * x_cap_;
+  int* llist = x_i32_;
+  int* rlist = x_i32_ + x_cap_;
+  unsigned int* num_swaps = x_small_;
+  long long* d_cut = reinterpret_cast<long long*>(x_small_ + 2);
+  unsigned int* scan_scratch = x_small_ + 8;
+  ptrdiff_t k_end = 0;
+  ptrdiff_t st_first[160], st_last[160], st_depth[160];
+  int sp = 0;
+  st_first[sp] = 0;
+  st_last[sp] = n;
+  st_depth[sp] = exact_sort::introsort_depth_limit(n);
+  ++sp;
+  try {
+    while (sp > 0) {
+      --sp;
+      ptrdiff_t first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
+      if (first >= want) continue;
+      bool handed_back = false;
+      while (last - first > 16) {
+        if (depth == 0 || last - first <= kOrderHostRange) {
+          // small (or depth-exhausted) range: the host replay finishes it
+          d2h(host + first, x_items_ + first, static_cast<size_t>(last - first) * sizeof(Item), s_);
+          exact_sort::introsort_prefix(host, first, last, depth, want, &k_end);
+          handed_back = true;
+          break;
+        }
+        --depth;
+        launch_1d(s_, OrderPivot{x_items_, first, last}, 1, "order_pivot");
+        const int m = static_cast<int>(last - first - 1);
+        launch_1d(s_, OrderPartFlags{x_items_, first, m, fl, fr}, m, "order_part_flags");
+        unsigned long long total_l = 0, total_r = 0;
+        exclusive_scan_with(fl, sl, m, &total_l, scan_scratch);
+        exclusive_scan_with(fr, sr, m, &total_r, scan_scratch);
+        dev_zero(num_swaps, sizeof(unsigned int), s_);
+        launch_1d(s_, OrderPartLists{fl, sl, fr, sr, m, llist, rlist, num_swaps}, m, "order_part_lists");
+        launch_1d(s_, OrderPartCut{first, llist, rlist, num_swaps, static_cast<unsigned int>(total_l), d_cut}, 1,
+                  "order_part_cut");
+        unsigned int k = 0;
+        d2h(&k, num_swaps, sizeof(k), s_);
+        if (k) launch_1d(s_, OrderPartSwap{x_items_, first, llist, rlist}, static_cast<int>(k), "order_part_swap");
+        long long cut_ll = 0;
+        d2h(&cut_ll, d_cut, sizeof(cut_ll), s_);
+        const ptrdiff_t cut = static_cast<ptrdiff_t>(cut_ll);
+        if (cut <= first || cut > last) throw std::runtime_error("device order replay: partition out of range");
+        if (cut < want) {
+          st_first[sp] = cut;
+          st_last[sp] = last;
+          st_depth[sp] = depth;
+          ++sp;
+        }
+        last = cut;
+      }
+      if (!handed_back) {
+        if (last > first) d2h(host + first, x_items_ + first, static_cast<size_t>(last - first) * sizeof(Item), s_);
+        if (last > k_end) k_end = last;
+      }
+    }
+    exact_sort::final_insertion_prefix(host, n, &k_end);
+    out->assign(host, host + k_end);
+  } catch (...) {
+    free(host);
+    throw;
+  }
+  free(host);
+  return static_cast<size_t>(k_end);
+}
+
+size_t ImageContext::debug_device_partial_sort(std::pair<int, float>* items, size_t n, size_t want) {
+  bind();
+  order_scratch(n);
+  if (n) h2d(x_items_, items, n * sizeof(OrderItem), s_);
+  std::vector<std::pair<int, float> > out;
+  const size_t k = device_partial_sort_resident(n, want, &out);
+  std::copy(out.begin(), out.begin() + k, items);
+  return k;
+}
+
+size_t ImageContext::exact_order_prefix(int direction, const std::vector<int>& last_index,
+                                        const std::vector<float>& max_err, size_t want,
+                                        std::vector<std::pair<int, float> >* out, size_t* order_size) {
+  h2d(d_last_index_, last_index.data(), sizeof(int) * g_.nblocks, s_);
+  h2d(d_max_err_, max_err.data(), sizeof(float) * g_.nblocks, s_);
+  order_scratch(num_entries_ + 16);
+  unsigned int* count = x_u32_;
+  unsigned int* offset = x_u32_ + x_cap_;
+  launch_1d(s_, OrderRefCount{d_last_index_, z_cnt_, weights_, direction, count}, g_.nblocks, "order_ref_count");
+  unsigned long long total = 0;
+  exclusive_scan_with(count, offset, g_.nblocks, &total, x_small_ + 8);
+  *order_size = static_cast<size_t>(total);
+  OrderKeyCommon c;
+  c.err = z_err_;
+  c.entry_block = e_block_;
+  c.entry_slot = e_slot_;
+  c.last_index = d_last_index_;
+  c.max_err = d_max_err_;
+  c.weight = weights_;
+  c.direction = direction;
+  launch_1d(s_, OrderRefBuild{c, offset, x_items_}, static_cast<int>(num_entries_), "order_ref_build");
+  return device_partial_sort_resident(static_cast<size_t>(total), want, out);
+}
+
+// ---------------------------------------------------------------------------
 // a11 on the device
 #if defined(GB200_HOSTSIM)
 void ImageContext::exclusive_scan(const unsigned int* in, unsigned int* out, int n, unsigned long long* total) {
+  exclusive_scan_with(in, out, n, total, nullptr);
+}
+void ImageContext::exclusive_scan_with(const unsigned int* in, unsigned int* out, int n, unsigned long long* total,
+                                       unsigned int*) {
   unsigned long long acc = 0;
   for (int i = 0; i < n; ++i) {
     out[i] = static_cast<unsigned int>(acc);
@@ -702,6 +854,10 @@ __global__ void __launch_bounds__(256) k_scan_add(unsigned int* out, const unsig
 }  // namespace
 
 void ImageContext::exclusive_scan(const unsigned int* in, unsigned int* out, int n, unsigned long long* total) {
+  exclusive_scan_with(in, out, n, total, j_sums_);
+}
+void ImageContext::exclusive_scan_with(const unsigned int* in, unsigned int* out, int n, unsigned long long* total,
+                                       unsigned int* j_sums_) {
   const int ctas = (n + 1023) / 1024;
   unsigned long long* d_total = reinterpret_cast<unsigned long long*>(j_sums_ + ((ctas + 3) & ~1) + 2);
   // keep the 64-bit total 8-byte aligned inside the scratch buffer

@@ -20,6 +20,8 @@ struct KernelStat {
   double elements;  // pixels / blocks launched (for algorithmic-bytes rooflines)
 };
 
+struct OrderItem;
+
 class ImageContext {
  public:
   // Uploads the image, runs the one-time kernels (a2 FDCT, a3 PsychoImage of the
@@ -30,6 +32,13 @@ class ImageContext {
   // JPEG input (4:4:4): the original is given as dequantised DCT coefficients
   // [3][nblocks][64]; its pixels (DecodeJpegToRGB) are rendered on the device.
   ImageContext(const int16_t* dq_coeffs, int w, int h, int device, bool prepare_now, Comm* comm);
+  // EXPERIMENTAL (order_exact.h, GB200_DEVICE_ORDER=1): the reference-ordered candidate list
+  // and the introsort partition passes over large ranges on the device.  Returns k_end and the
+  // first k_end entries exactly as std::sort would leave them (exact_sort.h semantics).
+  size_t exact_order_prefix(int direction, const std::vector<int>& last_index, const std::vector<float>& max_err,
+                            size_t want, std::vector<std::pair<int, float> >* out, size_t* order_size);
+  // test hook: the same replay on caller-provided items
+  size_t debug_device_partial_sort(std::pair<int, float>* items, size_t n, size_t want);
   // Metric only (stand-alone butteraugli, scope row f4): the first image as linear RGB
   // float planes [3][h][w]; compare_linear() scores a second one against it.
   ImageContext(const float* linear_rgb, int w, int h, int device);
@@ -148,6 +157,14 @@ class ImageContext {
   float* hf_blr_;  // [2]
   float* ps1_;     // [10]
   float* diffs_;   // [1]
+  // scratch of the device order replay (allocated on first use)
+  OrderItem* x_items_ = nullptr;
+  unsigned int* x_u32_ = nullptr;  // fl, sl, fr, sr
+  int* x_i32_ = nullptr;           // llist, rlist
+  unsigned int* x_small_ = nullptr;
+  size_t x_cap_ = 0;
+  void order_scratch(size_t n);
+  size_t device_partial_sort_resident(size_t n, size_t want, std::vector<std::pair<int, float> >* out);
   bool metric_only_ = false;  // no coefficients at all: butteraugli of two linear images
   float compare_tail();
   bool from_coeffs_ = false;  // original given as coefficients (JPEG input)
@@ -191,6 +208,9 @@ class ImageContext {
   size_t j_words_cap_;
   size_t j_nbytes_;
   void exclusive_scan(const unsigned int* in, unsigned int* out, int n, unsigned long long* total);
+  // same with caller-provided scratch for the per-CTA sums (n / 1024 + 8 words)
+  void exclusive_scan_with(const unsigned int* in, unsigned int* out, int n, unsigned long long* total,
+                           unsigned int* scratch);
   MaltaParams malta_[6];
   double asym_w0_, asym_w1_;
 };

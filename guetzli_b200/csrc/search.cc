@@ -718,8 +718,33 @@ class Search {
           // sorts just that prefix (element for element what std::sort would leave there).
           size_t want = direction > 0 ? order_size
                                       : std::max<size_t>(4 * static_cast<size_t>(min_coeffs_to_change) + 1024, 4096);
+          // EXPERIMENTAL (GB200_DEVICE_ORDER=1|check): list and large partition passes on the
+          // device (order_exact.h); "check" also runs the host replay and compares.
+          static const int kDeviceOrder = [] {
+            const char* e = getenv("GB200_DEVICE_ORDER");
+            return e == nullptr ? 0 : (e[0] == 'c' ? 2 : (e[0] == '1' ? 1 : 0));
+          }();
+          const bool device_order = kDeviceOrder != 0 && direction < 0;
           for (;;) {
             Clock::time_point t0 = Clock::now();
+            if (device_order && kDeviceOrder == 1) {
+              size_t dev_total = 0;
+              if (want > order_size) want = order_size;
+              const size_t k_end = ctx_->exact_order_prefix(direction, m.last_indexes, m.max_block_error, want, &order,
+                                                            &dev_total);
+              if (dev_total != order_size) throw std::runtime_error("exact_order_prefix: entry count mismatch");
+              st_->ms_sort += ms_since(t0);
+              Clock::time_point tw = Clock::now();
+              SymbolHistogram saved_h[3] = {m.ac_h[0], m.ac_h[1], m.ac_h[2]};
+              const int saved_hist_size = m.ac_histogram_size;
+              const std::vector<uint8_t> saved_depths = m.ac_depths;
+              out = walk(m, order, order_size, direction, min_coeffs_to_change, min_size_delta, prev_size, false);
+              st_->ms_walk += ms_since(tw);
+              if (k_end == order_size || (out.stopped && out.consumed < k_end)) break;
+              unwalk(m, order, out, direction, saved_h, saved_hist_size, saved_depths);
+              want = std::min(order_size, want * 4);
+              continue;
+            }
             order.clear();
             order.reserve(order_size);
             for (int block_ix = 0; block_ix < num_blocks; ++block_ix) {
@@ -754,6 +779,14 @@ class Search {
             dbg_n_[0] += order.size();
             const size_t k_end = exact_sort::partial_std_sort(order.data(), order.size(), want);
             order.resize(k_end);
+            if (device_order && kDeviceOrder == 2) {
+              std::vector<std::pair<int, float> > dev;
+              size_t dev_total = 0;
+              const size_t dk = ctx_->exact_order_prefix(direction, m.last_indexes, m.max_block_error, want, &dev, &dev_total);
+              if (dev_total != order_size || dk != k_end || dev != order)
+                throw std::runtime_error("device order replay differs from the host replay");
+              ++device_order_checked_;
+            }
             st_->ms_sort += ms_since(t0);
             Clock::time_point tw = Clock::now();
             SymbolHistogram saved_h[3] = {m.ac_h[0], m.ac_h[1], m.ac_h[2]};
@@ -790,6 +823,8 @@ class Search {
       fprintf(stderr, "tie fallbacks %d: run-at-refresh %d, run-at-test %d, pair-at-refresh %d, pair-untestable %d, pair-decides %d; exact %d partial %d\n",
               tie_fallbacks_, tie_why_[1], tie_why_[2], tie_why_[3], tie_why_[4], tie_why_[5], st_->order_exact,
               st_->order_partial);
+    if (getenv("GB200_TIE_DEBUG") && device_order_checked_)
+      fprintf(stderr, "device order replay checked against the host replay %d times\n", device_order_checked_);
     if (getenv("GB200_TIE_DEBUG"))
       fprintf(stderr, "order timing: device top-K fetch %.1f ms, exact-order build %.1f ms over %zu entries, sort total %.1f ms, walk %.1f ms\n",
               dbg_ms_[0], dbg_ms_[1], dbg_n_[0], st_->ms_sort, st_->ms_walk);
@@ -808,6 +843,7 @@ class Search {
   JpegPlan plan_;
   size_t scan_bytes_ = 0;
   std::vector<std::pair<int, float> > order_buf_;
+  int device_order_checked_ = 0;
   int tie_fallbacks_ = 0;
   int tie_why_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double dbg_ms_[4] = {0, 0, 0, 0};   // GB200_TIE_DEBUG: device top-K fetch, exact-order build

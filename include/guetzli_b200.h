@@ -161,6 +161,8 @@ int gb200_write_jpeg(const int16_t* coeffs, int w, int h, const int* q, uint8_t*
 /* test hooks: prefix-exact replay of std::sort on (block, key) pairs vs std::sort itself */
 size_t gb200_debug_partial_sort(int* block, float* key, size_t n, size_t want);
 void gb200_debug_std_sort(int* block, float* key, size_t n);
+/* experimental: the replay with the large partition passes on the device */
+size_t gb200_debug_device_partial_sort(gb200_image* img, int* block, float* key, size_t n, size_t want);
 
 /* The library keeps freed device blocks in a size-bucketed cache (cudaMalloc/cudaFree
  * would serialise concurrent image contexts); this returns the cache to the driver. */
