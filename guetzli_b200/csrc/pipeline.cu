@@ -753,7 +753,7 @@ size_t ImageContext::exact_order_prefix(int direction, const std::vector<int>& l
                                         std::vector<std::pair<int, float> >* out, size_t* order_size) {
   h2d(d_last_index_, last_index.data(), sizeof(int) * g_.nblocks, s_);
   h2d(d_max_err_, max_err.data(), sizeof(float) * g_.nblocks, s_);
-  order_scratch(num_entries_ + 16);
+  order_scratch(std::max<size_t>(num_entries_, static_cast<size_t>(g_.nblocks)) + 16);
   unsigned int* count = x_u32_;
   unsigned int* offset = x_u32_ + x_cap_;
   launch_1d(s_, OrderRefCount{d_last_index_, z_cnt_, weights_, direction, count}, g_.nblocks, "order_ref_count");
