@@ -456,6 +456,7 @@ class Search {
   WalkOutcome walk(Sfm& m, const std::vector<std::pair<int, float> >& order, size_t n_total, int direction,
                    int min_coeffs_to_change, double min_size_delta, int prev_size, bool check_ties) {
     const size_t per = static_cast<size_t>(img_.nblocks) * 64;
+    const int16_t* orig_ = ctx_->orig_coeffs().data();
     WalkOutcome out;
     out.est_jpg_size = prev_size;
     std::fill(m.block_changed.begin(), m.block_changed.end(), 0);
@@ -482,6 +483,13 @@ class Search {
           __builtin_prefetch(&cand_[c * per + static_cast<size_t>(pb) * 64]);
           __builtin_prefetch(&cand_[c * per + static_cast<size_t>(pb) * 64 + 32]);
         }
+      }
+      if (i + 3 < n_avail) {
+        // the candidate index is in cache by now: fetch the original coefficient it refers to
+        const int pb = order[i + 3].first;
+        const int pli = m.last_indexes[pb] + std::min(direction, 0);
+        const int idx = m.cand_idx[m.offsets[pb] + (pli < 0 ? 0 : pli)];
+        __builtin_prefetch(&orig_[(idx >> 6) * per + static_cast<size_t>(pb) * 64 + (idx & 63)]);
       }
       const int block_ix = order[i].first;
       const bool refresh_here =
