@@ -726,16 +726,20 @@ class Search {
           // sorts just that prefix (element for element what std::sort would leave there).
           size_t want = direction > 0 ? order_size
                                       : std::max<size_t>(4 * static_cast<size_t>(min_coeffs_to_change) + 1024, 4096);
-          // EXPERIMENTAL (GB200_DEVICE_ORDER=1|check): list and large partition passes on the
-          // device (order_exact.h); "check" also runs the host replay and compares.
+          // List and large partition passes on the device (order_exact.h); GB200_DEVICE_ORDER=check
+          // runs the host replay as well and compares.
+          // Default: on for lists of at least a million entries (1080p and larger), where the host
+          // replay costs tens of milliseconds; GB200_DEVICE_ORDER=0 turns it off, =1 forces it for
+          // every size.
           static const int kDeviceOrder = [] {
             const char* e = getenv("GB200_DEVICE_ORDER");
-            return e == nullptr ? 0 : (e[0] == 'c' ? 2 : (e[0] == '1' ? 1 : 0));
+            return e == nullptr ? 3 : (e[0] == 'c' ? 2 : (e[0] == '1' ? 1 : 0));
           }();
-          const bool device_order = kDeviceOrder != 0 && direction < 0;
+          const bool device_order =
+              direction < 0 && (kDeviceOrder == 1 || kDeviceOrder == 2 || (kDeviceOrder == 3 && order_size >= 1000000));
           for (;;) {
             Clock::time_point t0 = Clock::now();
-            if (device_order && kDeviceOrder == 1) {
+            if (device_order && kDeviceOrder != 2) {
               size_t dev_total = 0;
               if (want > order_size) want = order_size;
               const size_t k_end = ctx_->exact_order_prefix(direction, m.last_indexes, m.max_block_error, want, &order,
