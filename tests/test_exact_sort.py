@@ -80,3 +80,27 @@ def test_device_order_end_to_end_in_check_mode(port_lib):
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     assert b"OK" in r.stdout and b"checked against the host replay" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,levels,seed", [(300000, 10 ** 6, 3), (200000, 7, 2), (150000, 1, 4), (2000000, 10 ** 7, 9)])
+def test_device_partition_replay_matches_host_cuda(cuda_lib, n, levels, seed):
+    """The same comparison with the partition passes as CUDA kernels (tools/check_device_order.py)."""
+    import guetzli_b200 as gb
+    from guetzli_b200 import synth
+    rng = np.random.default_rng(seed)
+    keys = (rng.integers(0, levels, n) / 7.0).astype(np.float32)
+    blocks = np.arange(n, dtype=np.int32)
+    img = gb.DeviceImage(synth.gradnoise(16, 16, 1), lib=cuda_lib)
+    cuda_lib.gb200_debug_partial_sort.restype = C.c_size_t
+    cuda_lib.gb200_debug_partial_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    cuda_lib.gb200_debug_device_partial_sort.restype = C.c_size_t
+    cuda_lib.gb200_debug_device_partial_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    for want in (100, n // 50, n // 3):
+        b0, k0 = blocks.copy(), keys.copy()
+        ke0 = cuda_lib.gb200_debug_partial_sort(b0.ctypes.data, k0.ctypes.data, n, want)
+        b1, k1 = blocks.copy(), keys.copy()
+        ke1 = cuda_lib.gb200_debug_device_partial_sort(img._h, b1.ctypes.data, k1.ctypes.data, n, want)
+        assert ke1 == ke0, (n, want)
+        assert np.array_equal(b1[:ke1], b0[:ke0]) and np.array_equal(k1[:ke1], k0[:ke0]), (n, want)
+    img.close()
