@@ -73,6 +73,7 @@ def load_library(path=None):
     lib.gb200_image_process.argtypes = [C.c_void_p, P(_CParams), _LOG_FN, C.c_void_p,
                                         P(P(C.c_uint8)), P(C.c_size_t), P(_CStats)]
     lib.gb200_image_destroy.argtypes = [C.c_void_p]
+    lib.gb200_image_reset.argtypes = [C.c_void_p]
     for name in ("num_blocks", "orig_coeffs", "apply_global_quant", "upload_candidate",
                  "download_candidate", "compare", "distmap", "debug_render", "debug_psycho0",
                  "debug_corner_mask"):
@@ -165,7 +166,7 @@ def process(params, stats, rgb, w, h, device=0, lib=None):
         stats.device = {k: getattr(cs, k) for k, _ in _CStats._fields_}
     if not ok and not data:
         msg = _err(lib)
-        if "CUDA" in msg or "no CUDA device" in msg:
+        if "CUDA" in msg or "no CUDA device" in msg or "out of memory" in msg:
             raise RuntimeError(msg)
     return bool(ok), data
 
@@ -199,7 +200,7 @@ def process_jpeg(params, stats, jpeg_in, device=0, lib=None):
         stats.device = {k: getattr(cs, k) for k, _ in _CStats._fields_}
     if not ok and not data:
         msg = _err(lib)
-        if "CUDA" in msg or "no CUDA device" in msg:
+        if "CUDA" in msg or "no CUDA device" in msg or "out of memory" in msg:
             raise RuntimeError(msg)
     return bool(ok), data
 
@@ -279,6 +280,15 @@ def dist_unique_id(lib=None):
     return bytes(buf)
 
 
+def last_error(lib=None):
+    """gb200_last_error() of the calling thread."""
+    return _err(lib or load_library())
+
+
+def dist_shutdown(lib=None):
+    (lib or load_library()).gb200_dist_shutdown()
+
+
 def dist_init(uid, rank, world, device, lib=None):
     lib = lib or load_library()
     buf = (C.c_uint8 * 128).from_buffer_copy(uid)
@@ -341,6 +351,10 @@ class DeviceImage:
         if not ok:
             raise RuntimeError(_err(self.lib))
 
+    def reset(self):
+        """Forget the one-time results: the next process() repeats the whole job."""
+        self._ck(self.lib.gb200_image_reset(self._h))
+
     def process(self, params, stats=None):
         """guetzli::Process on the resident image -> (ok, jpeg bytes)."""
         cp = _CParams(params.butteraugli_target, int(params.clear_metadata), int(params.try_420),
@@ -359,6 +373,8 @@ class DeviceImage:
             stats.counters["number of iterations up"] = cs.iterations_up
             stats.counters["number of iterations down"] = cs.iterations_down
             stats.device = {k: getattr(cs, k) for k, _ in _CStats._fields_}
+        if not ok and not data:
+            raise RuntimeError("gb200_image_process failed: " + _err(self.lib))
         return bool(ok), data
 
     def orig_coeffs(self):

@@ -390,6 +390,10 @@ void gb200_image_destroy(gb200_image* img) {
   delete img;
 }
 
+int gb200_image_reset(gb200_image* img) {
+  return guarded([&]() { img->ctx->reset_prepared(); });
+}
+
 int gb200_image_num_blocks(const gb200_image* img) { return img->ctx->geom().nblocks; }
 
 int gb200_image_orig_coeffs(gb200_image* img, int16_t* out) {

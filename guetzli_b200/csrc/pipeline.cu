@@ -104,26 +104,43 @@ float* ImageContext::planes(int n) {
 
 ImageContext::ImageContext(const uint8_t* rgb, int w, int h, int device, bool prepare_now, Comm* comm)
     : g_(make_geom(w, h)), device_(device), comm_(comm) {
-  init(rgb, nullptr, w, h, prepare_now);
+  guarded_init(rgb, nullptr, w, h, prepare_now);
 }
 
 ImageContext::ImageContext(const int16_t* dq_coeffs, int w, int h, int device, bool prepare_now, Comm* comm)
     : g_(make_geom(w, h)), device_(device), comm_(comm) {
   from_coeffs_ = true;
-  init(nullptr, dq_coeffs, w, h, prepare_now);
+  guarded_init(nullptr, dq_coeffs, w, h, prepare_now);
 }
 
 ImageContext::ImageContext(const float* linear_rgb, int w, int h, int device)
     : g_(make_geom(w, h)), device_(device), comm_(nullptr) {
   metric_only_ = true;
-  init(nullptr, nullptr, w, h, false);
+  guarded_init(nullptr, nullptr, w, h, false);
   metric_ = true;
   prepared_ = true;
-  // PsychoImage of the first image (butteraugli.cc:784), resident
-  upload_planes(linear_rgb, lin_, 3);
-  opsin(lin_, xyb_);
-  separate(xyb_, ps0_);
-  stream_sync(s_);
+  try {
+    // PsychoImage of the first image (butteraugli.cc:784), resident
+    upload_planes(linear_rgb, lin_, 3);
+    opsin(lin_, xyb_);
+    separate(xyb_, ps0_);
+    stream_sync(s_);
+  } catch (...) {
+    release();
+    throw;
+  }
+}
+
+// A constructor that throws never reaches the destructor: everything acquired so far
+// (device buffers of owned_, the stream) is handed back here, so that an out-of-memory
+// condition does not become permanent for the process.
+void ImageContext::guarded_init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int h, bool prepare_now) {
+  try {
+    init(rgb, dq_coeffs, w, h, prepare_now);
+  } catch (...) {
+    release();
+    throw;
+  }
 }
 
 float ImageContext::compare_linear(const float* linear_rgb) {
@@ -147,6 +164,7 @@ void ImageContext::init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int
   cr_hi_ = std::min(g_.h, 8 * by_hi_ + 56);
   select_device(device);
   s_ = make_stream();
+  have_stream_ = true;
   t_ = build_tables(w, h, s_, &owned_, &ht_);
   malta_call_params(malta_);
   l2_asym_weights(&asym_w0_, &asym_w1_);
@@ -286,21 +304,32 @@ void ImageContext::prepare() {
   stream_sync(s_);
 }
 
-ImageContext::~ImageContext() {
-  stream_sync(s_);
-  if (d_sel_val_) dev_free(d_sel_val_);
-  if (d_sel_block_) dev_free(d_sel_block_);
-  if (x_items_) dev_free(x_items_);
-  if (x_u32_) dev_free(x_u32_);
-  if (x_i32_) dev_free(x_i32_);
-  if (x_small_) dev_free(x_small_);
-  if (j_words_) dev_free(j_words_);
-  if (d_edit_i_) dev_free(d_edit_i_);
-  if (d_edit_v_) dev_free(d_edit_v_);
-  if (e_block_) dev_free(e_block_);
-  if (e_slot_) dev_free(e_slot_);
+ImageContext::~ImageContext() { release(); }
+
+void ImageContext::release() {
+  if (released_) return;
+  released_ = true;
+  try {
+    select_device(device_);
+    if (have_stream_) stream_sync(s_);
+  } catch (...) {
+    // a failed device cannot be waited for; the blocks still go back to the cache
+  }
+  if (d_sel_val_) { dev_free(d_sel_val_); d_sel_val_ = nullptr; }
+  if (d_sel_block_) { dev_free(d_sel_block_); d_sel_block_ = nullptr; }
+  if (x_items_) { dev_free(x_items_); x_items_ = nullptr; }
+  if (x_u32_) { dev_free(x_u32_); x_u32_ = nullptr; }
+  if (x_i32_) { dev_free(x_i32_); x_i32_ = nullptr; }
+  if (x_small_) { dev_free(x_small_); x_small_ = nullptr; }
+  if (j_words_) { dev_free(j_words_); j_words_ = nullptr; }
+  if (d_edit_i_) { dev_free(d_edit_i_); d_edit_i_ = nullptr; }
+  if (d_edit_v_) { dev_free(d_edit_v_); d_edit_v_ = nullptr; }
+  if (e_block_) { dev_free(e_block_); e_block_ = nullptr; }
+  if (e_slot_) { dev_free(e_slot_); e_slot_ = nullptr; }
   for (size_t i = 0; i < owned_.size(); ++i) dev_free(owned_[i]);
-  destroy_stream(s_);
+  owned_.clear();
+  if (have_stream_) destroy_stream(s_);
+  have_stream_ = false;
 }
 
 void ImageContext::blur(const float* in, float* out, int nplanes, int id) {
@@ -338,8 +367,8 @@ void ImageContext::scatter_coeffs(const std::vector<int>& index, const std::vect
   if (n == 0) return;
   if (static_cast<size_t>(n) > edit_cap_) {
     stream_sync(s_);
-    if (d_edit_i_) dev_free(d_edit_i_);
-    if (d_edit_v_) dev_free(d_edit_v_);
+    if (d_edit_i_) { dev_free(d_edit_i_); d_edit_i_ = nullptr; }
+    if (d_edit_v_) { dev_free(d_edit_v_); d_edit_v_ = nullptr; }
     edit_cap_ = static_cast<size_t>(n) * 2 + 4096;
     d_edit_i_ = static_cast<int*>(dev_alloc(edit_cap_ * sizeof(int)));
     d_edit_v_ = static_cast<int16_t*>(dev_alloc(edit_cap_ * sizeof(int16_t)));
@@ -372,6 +401,7 @@ void ImageContext::download_candidate(int16_t* coeffs) {
 }
 
 float ImageContext::compare() {
+  bind();
   // S0 render (only blocks edited since the last render), S1 opsin, S2-S6 frequency split
   const int rb_lo = cr_lo_ / 8, rb_hi = (cr_hi_ + 7) / 8;  // block rows that intersect the computed rows
   if (comm_ && comm_->world() > 1 && !render_all_) {
@@ -408,6 +438,7 @@ float ImageContext::compare() {
 
 // S1..S13 on the linear RGB planes in lin_ (butteraugli::ButteraugliComparator::Diffmap).
 float ImageContext::compare_tail() {
+  bind();
   const size_t P = g_.plane;
   opsin(lin_, xyb_);
   separate(xyb_, ps1_);
@@ -568,8 +599,8 @@ void ImageContext::zeroing_orders(float block_error_limit, int lookahead, bool n
       es.push_back(static_cast<uint8_t>(i));
     }
   num_entries_ = eb.size();
-  if (e_block_) dev_free(e_block_);
-  if (e_slot_) dev_free(e_slot_);
+  if (e_block_) { dev_free(e_block_); e_block_ = nullptr; }
+  if (e_slot_) { dev_free(e_slot_); e_slot_ = nullptr; }
   e_block_ = static_cast<int*>(dev_alloc(sizeof(int) * (num_entries_ + 1)));
   e_slot_ = static_cast<uint8_t*>(dev_alloc(num_entries_ + 1));
   if (num_entries_) {
@@ -612,8 +643,8 @@ size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_
   d2h(&got, st, sizeof(got), s_);
   const size_t kept = got.kept;
   if (kept > sel_cap_) {
-    if (d_sel_val_) dev_free(d_sel_val_);
-    if (d_sel_block_) dev_free(d_sel_block_);
+    if (d_sel_val_) { dev_free(d_sel_val_); d_sel_val_ = nullptr; }
+    if (d_sel_block_) { dev_free(d_sel_block_); d_sel_block_ = nullptr; }
     sel_cap_ = kept + kept / 2 + 1024;
     d_sel_val_ = static_cast<float*>(dev_alloc(sel_cap_ * sizeof(float)));
     d_sel_block_ = static_cast<int*>(dev_alloc(sel_cap_ * sizeof(int)));
@@ -641,10 +672,10 @@ static const ptrdiff_t kOrderHostRange = [] {
 void ImageContext::order_scratch(size_t n) {
   if (n <= x_cap_) return;
   stream_sync(s_);
-  if (x_items_) dev_free(x_items_);
-  if (x_u32_) dev_free(x_u32_);
-  if (x_i32_) dev_free(x_i32_);
-  if (x_small_) dev_free(x_small_);
+  if (x_items_) { dev_free(x_items_); x_items_ = nullptr; }
+  if (x_u32_) { dev_free(x_u32_); x_u32_ = nullptr; }
+  if (x_i32_) { dev_free(x_i32_); x_i32_ = nullptr; }
+  if (x_small_) { dev_free(x_small_); x_small_ = nullptr; }
   x_cap_ = n + n / 4 + 1024;
   x_items_ = static_cast<OrderItem*>(dev_alloc(x_cap_ * sizeof(OrderItem)));
   x_u32_ = static_cast<unsigned int*>(dev_alloc(4 * x_cap_ * sizeof(unsigned int)));
@@ -907,7 +938,7 @@ void ImageContext::jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint1
   if (total_bits >= (1ull << 32)) throw std::runtime_error("jpeg scan exceeds 2^32 bits");
   const size_t nwords = static_cast<size_t>((total_bits + 31) >> 5);
   if (nwords + 1 > j_words_cap_) {
-    if (j_words_) dev_free(j_words_);
+    if (j_words_) { dev_free(j_words_); j_words_ = nullptr; }
     j_words_cap_ = nwords + nwords / 4 + 1024;
     j_words_ = static_cast<unsigned int*>(dev_alloc(j_words_cap_ * sizeof(unsigned int)));
   }

@@ -46,6 +46,9 @@ class ImageContext {
   // the one-time kernels (idempotent); split from the upload so that a caller can
   // time the job with the image already resident in HBM
   void prepare();
+  // forgets the one-time results so that the next prepare() recomputes them (a resident
+  // image encoded again must redo all of its work, bench.py)
+  void reset_prepared() { prepared_ = false; }
   // sRGB bytes of the original as the metric sees it (tests)
   void download_rgb(uint8_t* rgb);
   // makes this context's device current for the calling host thread
@@ -126,6 +129,10 @@ class ImageContext {
   void download_planes(const float* src, float* packed, int n);
   float* planes(int n);
 
+  void guarded_init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int h, bool prepare_now);
+  void release();
+  bool released_ = false;
+  bool have_stream_ = false;
   Geom g_;
   int device_;
   bool metric_;
@@ -139,24 +146,24 @@ class ImageContext {
   std::vector<void*> owned_;
   std::vector<int16_t> orig_host_;
 
-  uint8_t* d_rgb_;
-  int16_t* d_orig_;
-  int16_t* d_cand_;
-  int* d_q_;
-  float* ps0_;        // [10]
-  float* corner_mask_;  // [nblocks][3]
+  uint8_t* d_rgb_ = nullptr;
+  int16_t* d_orig_ = nullptr;
+  int16_t* d_cand_ = nullptr;
+  int* d_q_ = nullptr;
+  float* ps0_ = nullptr;        // [10]
+  float* corner_mask_ = nullptr;  // [nblocks][3]
   // work planes
-  float* lin_;     // [3]
-  float* tmp_;     // [3] blur x-pass output
-  float* blr_;     // [3]
-  float* xyb_;     // [3]
-  float* lf_;      // [3]
-  float* mf_in_;   // [3]
-  float* mf_blr_;  // [3]
-  float* hf_raw_;  // [2]
-  float* hf_blr_;  // [2]
-  float* ps1_;     // [10]
-  float* diffs_;   // [1]
+  float* lin_ = nullptr;     // [3]
+  float* tmp_ = nullptr;     // [3] blur x-pass output
+  float* blr_ = nullptr;     // [3]
+  float* xyb_ = nullptr;     // [3]
+  float* lf_ = nullptr;      // [3]
+  float* mf_in_ = nullptr;   // [3]
+  float* mf_blr_ = nullptr;  // [3]
+  float* hf_raw_ = nullptr;  // [2]
+  float* hf_blr_ = nullptr;  // [2]
+  float* ps1_ = nullptr;     // [10]
+  float* diffs_ = nullptr;   // [1]
   // scratch of the device order replay (allocated on first use)
   OrderItem* x_items_ = nullptr;
   unsigned int* x_u32_ = nullptr;  // fl, sl, fr, sr
@@ -169,44 +176,44 @@ class ImageContext {
   float compare_tail();
   bool from_coeffs_ = false;  // original given as coefficients (JPEG input)
   void init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int h, bool prepare_now);
-  float* ac_;      // [2]
-  float* noise_;   // [2] pre, blurred
-  float* mpre_;    // [2]
-  float* sact_;    // [3] sx, sy1, sy2
-  float* dm_;      // [2] diffmap, blurred
-  float* block_max_;  // [nblocks]
-  float* weights_;    // [nblocks]
-  float* partial_;    // [1024]
-  float* zero_block_max_;
-  uint8_t* z_idx_;   // [nblocks][192] candidate coefficient index
-  float* z_err_;     // [nblocks][192] candidate block error
-  int* z_cnt_;       // [nblocks]
-  int* d_last_index_;
-  float* d_max_err_;
-  unsigned int* d_hist_;  // [65536] + 1 counter
-  float* d_sel_val_;
-  int* d_sel_block_;
-  size_t sel_cap_;
-  int* e_block_;      // [entries] block of every candidate (compact list)
-  uint8_t* e_slot_;   // [entries] its slot
-  size_t num_entries_;
-  int* d_edit_i_;
-  int16_t* d_edit_v_;
-  size_t edit_cap_;
+  float* ac_ = nullptr;      // [2]
+  float* noise_ = nullptr;   // [2] pre, blurred
+  float* mpre_ = nullptr;    // [2]
+  float* sact_ = nullptr;    // [3] sx, sy1, sy2
+  float* dm_ = nullptr;      // [2] diffmap, blurred
+  float* block_max_ = nullptr;  // [nblocks]
+  float* weights_ = nullptr;    // [nblocks]
+  float* partial_ = nullptr;    // [1024]
+  float* zero_block_max_ = nullptr;
+  uint8_t* z_idx_ = nullptr;   // [nblocks][192] candidate coefficient index
+  float* z_err_ = nullptr;     // [nblocks][192] candidate block error
+  int* z_cnt_ = nullptr;       // [nblocks]
+  int* d_last_index_ = nullptr;
+  float* d_max_err_ = nullptr;
+  unsigned int* d_hist_ = nullptr;  // [65536] + 1 counter
+  float* d_sel_val_ = nullptr;
+  int* d_sel_block_ = nullptr;
+  size_t sel_cap_ = 0;
+  int* e_block_ = nullptr;      // [entries] block of every candidate (compact list)
+  uint8_t* e_slot_ = nullptr;   // [entries] its slot
+  size_t num_entries_ = 0;
+  int* d_edit_i_ = nullptr;
+  int16_t* d_edit_v_ = nullptr;
+  size_t edit_cap_ = 0;
   bool render_all_;
   int num_dirty_;
-  int* d_dirty_;
+  int* d_dirty_ = nullptr;
   std::vector<char> dirty_flag_;
   std::vector<int> dirty_list_;
-  unsigned int* j_hist_;      // [kHistCopies][6][257] + [6][257] + flag + ff counter
-  unsigned int* j_bits_;      // [3*nblocks] unit bit lengths (scan order)
-  unsigned int* j_offset_;    // [3*nblocks] exclusive scan
-  unsigned int* j_sums_;      // scan scratch
-  uint8_t* j_depth_;          // [6][256]
-  uint16_t* j_code_;          // [6][256]
-  unsigned int* j_words_;     // scan bits, big-endian 32-bit words
-  size_t j_words_cap_;
-  size_t j_nbytes_;
+  unsigned int* j_hist_ = nullptr;      // [kHistCopies][6][257] + [6][257] + flag + ff counter
+  unsigned int* j_bits_ = nullptr;      // [3*nblocks] unit bit lengths (scan order)
+  unsigned int* j_offset_ = nullptr;    // [3*nblocks] exclusive scan
+  unsigned int* j_sums_ = nullptr;      // scan scratch
+  uint8_t* j_depth_ = nullptr;          // [6][256]
+  uint16_t* j_code_ = nullptr;          // [6][256]
+  unsigned int* j_words_ = nullptr;     // scan bits, big-endian 32-bit words
+  size_t j_words_cap_ = 0;
+  size_t j_nbytes_ = 0;
   void exclusive_scan(const unsigned int* in, unsigned int* out, int n, unsigned long long* total);
   // same with caller-provided scratch for the per-CTA sums (n / 1024 + 8 words)
   void exclusive_scan_with(const unsigned int* in, unsigned int* out, int n, unsigned long long* total,

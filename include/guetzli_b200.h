@@ -127,6 +127,9 @@ void gb200_image_destroy(gb200_image* img);
  * gb200_process_rgb; used to time the job without the host->device upload) */
 int gb200_image_process(gb200_image* img, const gb200_params* params, gb200_log_fn log, void* log_user,
                         uint8_t** out, size_t* out_len, gb200_stats* stats);
+/* forgets the one-time results (FDCT, PsychoImage, masks) of a resident image: the next
+ * gb200_image_process recomputes them from the resident pixels, i.e. repeats the whole job */
+int gb200_image_reset(gb200_image* img);
 int gb200_image_num_blocks(const gb200_image* img);
 /* coefficients: int16 [3][num_blocks][64], block-major (JPEGComponent::coeffs) */
 int gb200_image_orig_coeffs(gb200_image* img, int16_t* out);

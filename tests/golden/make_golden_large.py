@@ -18,7 +18,11 @@ CASES = {
     "noise1080p_s1234_q95": (lambda: synth.noise(1080, 1920, 1234), 95),       # BASELINE configs[1]
     "gradnoise4k_s4321_q90": (lambda: synth.gradnoise(2160, 3840, 4321), 90),  # BASELINE configs[2]
     "gradnoise1024_s1000_q84": (lambda: synth.gradnoise(1024, 1024, 1000), 84),  # configs[4], image 0
+    "gradnoise8k_s8192_q95": (lambda: synth.gradnoise(4320, 7680, 8192), 95),   # BASELINE configs[3] (tiled)
 }
+# BASELINE configs[4]: the other 63 images of the batch (seed 1000+i)
+for _i in range(1, 64):
+    CASES["gradnoise1024_s%d_q84" % (1000 + _i)] = ((lambda s: (lambda: synth.gradnoise(1024, 1024, s)))(1000 + _i), 84)
 
 name = sys.argv[1]
 gen, q = CASES[name]
