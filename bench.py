@@ -53,6 +53,10 @@ WORKLOADS = {
 # Algorithmic bytes per launched element (pixel of one plane, or 8x8 block) of each kernel:
 # compulsory reads + writes of that stage.
 ALG_BYTES = {
+    # TMA-staged fused chain (fused_kernels.cuh); elements as counted by the launchers in pipeline.cu
+    "tma_blur_x": 8, "tma_blur_y": 8, "opsin_fused": 24, "lf_fused_y": 16, "mf_fused_y": 56.0 / 3, "hf_fused": 84,
+    "malta_sums": 16, "noise_fused_y": 20, "mask_pre": 28, "mask_y_combine": 40, "final_fused": 8,
+    # staged chain (GB200_COMPARE=staged) and the other per-iteration kernels
     "malta_channel": 28, "blur_x": 8, "blur_y": 8, "sub_planes": 12, "opsin_px": 36, "split_mf_hf": 44, "split_hf_uhf": 68,
     "malta_pre": 12, "malta_acc_hf": 8, "malta_acc_lf": 12, "noise_pre": 12, "noise_asym_acc": 20,
     "mask_diff_pre": 40, "combine_sqrt": 44, "diffmap_mix": 12, "render_blocks": 1152,
@@ -61,6 +65,8 @@ ALG_BYTES = {
 # Kernels that make up one ButteraugliComparator::Compare (a7+a9+a10); their summed time
 # is compared with the compulsory 50 B/px of SURVEY.md §8(d).
 COMPARE_KERNELS = {
+    "tma_blur_x", "tma_blur_y", "opsin_fused", "lf_fused_y", "mf_fused_y", "hf_fused", "malta_sums", "noise_fused_y",
+    "mask_pre", "mask_y_combine", "final_fused",
     "render_blocks", "blur_x", "blur_y", "opsin_px", "sub_planes", "split_mf_hf", "split_hf_uhf", "malta_channel",
     "noise_pre", "noise_asym_acc", "mask_diff_pre", "combine_sqrt", "diffmap_mix", "block_max", "partial_max",
 }

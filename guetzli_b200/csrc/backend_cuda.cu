@@ -11,6 +11,7 @@
 
 #include "backend.h"
 #include "pipeline.h"
+#include "tma.cuh"
 
 namespace gb200 {
 
@@ -98,6 +99,40 @@ void dev_free(void* p) {
   if (it == c.live.end()) return;
   c.free_list[it->second].push_back(p);
   c.live.erase(it);
+}
+
+// Tensor map of a float plane group (tma.cuh).  cuTensorMapEncodeTiled is a driver-API
+// entry point; it is fetched through the runtime so that the library does not link libcuda.
+CUtensorMap make_plane_map(const float* base, int w, int h, int pitch, size_t plane_floats, int nplanes, int box_w,
+                           int box_h) {
+  typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiled encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    GB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || fn == nullptr)
+      throw std::runtime_error("guetzli_b200: the CUDA driver does not provide cuTensorMapEncodeTiled");
+    return reinterpret_cast<EncodeTiled>(fn);
+  }();
+  if (box_w % 4 != 0 || box_w > 256 || box_h > 256 || box_w < 1 || box_h < 1)
+    throw std::runtime_error("make_plane_map: illegal box");
+  CUtensorMap m;
+  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(nplanes)};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(pitch) * 4, static_cast<cuuint64_t>(plane_floats) * 4};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+  const cuuint32_t elem[3] = {1, 1, 1};
+  const CUresult rc = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, elem,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (%d) for %dx%dx%d pitch %d box %dx%d", static_cast<int>(rc),
+             w, h, nplanes, pitch, box_w, box_h);
+    throw std::runtime_error(buf);
+  }
+  return m;
 }
 
 static std::atomic<long long> g_h2d_bytes(0), g_d2h_bytes(0);

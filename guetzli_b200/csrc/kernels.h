@@ -516,8 +516,14 @@ struct CombineAndSqrt {
   const double* luts;
   GB_HD void operator()(int x, int y) const {
     const size_t o = static_cast<size_t>(y) * g.pitch + x;
+    pixel(x, y, sx[o], sy1[o], sy2[o]);
+  }
+  // the same with the three blurred activities of the pixel given by value (the fused
+  // y pass of the mask blurs hands them over in registers)
+  GB_HD void pixel(int x, int y, float s_x, float s_y1, float s_y2) const {
+    const size_t o = static_cast<size_t>(y) * g.pitch + x;
     float mask[3], dc_mask[3];
-    mask_from_activity(luts, sx[o], mask_y_activity(sy1[o], sy2[o]), mask, dc_mask);
+    mask_from_activity(luts, s_x, mask_y_activity(s_y1, s_y2), mask, dc_mask);
     float diff_dc[3], diff_ac[3];
     {
       const double d = ps0[kLfX * g.plane + o] - ps1[kLfX * g.plane + o];

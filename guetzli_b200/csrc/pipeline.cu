@@ -12,14 +12,19 @@
 #include "block_math.h"
 #include "jpeg_dev.h"
 #if !defined(GB200_HOSTSIM)
+#include <map>
+#include <tuple>
+
 #include "tiled_kernels.cuh"
 #include "zeroing_warp.cuh"
 #include "render_warp.cuh"
+#include "fused_kernels.cuh"
 #endif
 
 namespace gb200 {
 
 #if defined(GB200_HOSTSIM)
+void ImageContext::fused_sup0() {}
 static void select_device(int) {}
 static Stream make_stream() { return 0; }
 static void destroy_stream(Stream) {}
@@ -95,6 +100,259 @@ void ImageContext::gather_blocks(void* dev_buf, size_t elem_bytes_per_block) {
   comm_->allgather_inplace(dev_buf, elem_bytes_per_block, off, cnt, s_);
 }
 
+#if !defined(GB200_HOSTSIM)
+// ---------------------------------------------------------------------------
+// TMA-staged fused Compare chain (fused_kernels.cuh).
+struct ImageContext::Fused {
+  typedef std::tuple<const float*, int, int, int> Key;  // base, planes, box w, box h
+  std::map<Key, CUtensorMap> maps;
+  const CUtensorMap& map(const float* base, int nplanes, int box_w, int box_h, const Geom& g) {
+    const Key key(base, nplanes, box_w, box_h);
+    std::map<Key, CUtensorMap>::iterator it = maps.find(key);
+    if (it == maps.end())
+      it = maps.insert(std::make_pair(key, make_plane_map(base, g.w, g.h, g.pitch, g.plane, nplanes, box_w, box_h))).first;
+    return it->second;
+  }
+};
+
+namespace {
+// GB200_COMPARE=staged keeps the round-1 kernel sequence (one kernel per stage) for A/B
+// measurements and for the cross-check in tests; default is the fused chain.
+bool fused_enabled() {
+  const char* e = getenv("GB200_COMPARE");  // read per context: tests switch it between images
+  return !(e != nullptr && e[0] == 's');
+}
+
+template <int R>
+BlurK<R> make_blurk(const HostTables& ht, int id) {
+  if (static_cast<int>(ht.blur_taps[id].size()) != 2 * R + 1) throw std::runtime_error("blur radius / kernel mismatch");
+  BlurK<R> k;
+  for (int j = 0; j < 2 * R + 1; ++j) {
+    k.n[j] = ht.blur_taps_n[id][j];
+    k.raw[j] = ht.blur_taps[id][j];
+  }
+  return k;
+}
+
+template <class K>
+void allow_smem(K kernel, size_t bytes) {
+  GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// x pass of `nplanes` planes: in -> out
+template <int R>
+void launch_tma_x(Stream s, const CUtensorMap& in_map, float* out, int nplanes, const BlurTab& tab, const PlaneGeom& pg,
+                  const HostTables& ht, int id) {
+  const int rows = pg.y_end - pg.y0;
+  if (rows <= 0) return;
+  dim3 grid(cdiv(pg.w, GBX_TW), cdiv(rows, GBX_TH), nplanes);
+  note_launch("tma_blur_x", s, static_cast<double>(pg.w) * rows * nplanes);
+  k_tma_blur_x<R><<<grid, 128, 0, s>>>(in_map, out, tab.scale_x, pg, make_blurk<R>(ht, id));
+  note_launch_end("tma_blur_x", s);
+}
+
+template <int R, int NP, class Epi>
+void launch_tma_y(Stream s, const CUtensorMap& in_map, int planes_z, const BlurTab& tab, const PlaneGeom& pg,
+                  const HostTables& ht, int id, const Epi& epi, const char* name) {
+  const int rows = pg.y_end - pg.y0;
+  if (rows <= 0) return;
+  const size_t smem = static_cast<size_t>(NP) * (GBY_TH + 2 * R) * GBY_TW * sizeof(float) + 16;
+  allow_smem(k_tma_blur_y<R, NP, Epi>, smem);
+  dim3 grid(cdiv(pg.w, GBY_TW), cdiv(rows, GBY_TH), planes_z);
+  note_launch(name, s, static_cast<double>(pg.w) * rows * (NP == 1 ? planes_z : NP));
+  k_tma_blur_y<R, NP, Epi><<<grid, 256, smem, s>>>(in_map, tab.scale_y, pg, make_blurk<R>(ht, id), epi);
+  note_launch_end(name, s);
+}
+
+template <int R, int NP, class Epi>
+void launch_tma_2d(Stream s, const CUtensorMap& in_map, const BlurTab& tab, const PlaneGeom& pg, const HostTables& ht,
+                   int id, const Epi& epi, const char* name) {
+  const int rows = pg.y_end - pg.y0;
+  if (rows <= 0) return;
+  typedef Blur2dCfg<R, NP> C;
+  allow_smem(k_tma_blur_2d<R, NP, Epi>, C::kSmemBytes);
+  dim3 grid(cdiv(pg.w, GB2_TW), cdiv(rows, GB2_TH), 1);
+  note_launch(name, s, static_cast<double>(pg.w) * rows);
+  k_tma_blur_2d<R, NP, Epi><<<grid, 256, C::kSmemBytes, s>>>(in_map, tab.scale_x, tab.scale_y, pg, make_blurk<R>(ht, id), epi);
+  note_launch_end(name, s);
+}
+}  // namespace
+
+// Radii of the nine blurs (b/butteraugli.cc:145: max(1, int(2.25 * sigma))); make_blurk checks them.
+#define GB_R_OPSIN 2
+#define GB_R_LF 16
+#define GB_R_MF 8
+#define GB_R_HF 4
+#define GB_R_NOISE 23
+#define GB_R_MASKX 20
+#define GB_R_MASKY0 5
+#define GB_R_MASKY1 20
+#define GB_R_FINAL 3
+
+void ImageContext::fused_opsin(const float* lin, float* xyb) {
+  const PlaneGeom pg{g_.w, g_.h, g_.pitch, g_.plane, cr_lo_, cr_hi_};
+  typedef Blur2dCfg<GB_R_OPSIN, 3> C;
+  const CUtensorMap& m = fused_->map(lin, 3, C::SWI, C::HI, g_);
+  launch_tma_2d<GB_R_OPSIN, 3>(s_, m, t_.blur[kBlurOpsin], pg, ht_, kBlurOpsin, EpiOpsin{xyb, g_.pitch, g_.plane},
+                               "opsin_fused");
+}
+
+// SeparateFrequencies; with_diffs: also the Malta pre-pass and the noise difference against ps0_.
+void ImageContext::fused_separate(const float* xyb, float* ps, bool with_diffs) {
+  const PlaneGeom pg{g_.w, g_.h, g_.pitch, g_.plane, cr_lo_, cr_hi_};
+  const size_t P = g_.plane;
+  // S2: lf = Blur(xyb, 7.47); mf_in = xyb - lf
+  launch_tma_x<GB_R_LF>(s_, fused_->map(xyb, 3, BlurXCfg<GB_R_LF>::SW, GBX_TH, g_), tmp_, 3, t_.blur[kBlurLf], pg, ht_, kBlurLf);
+  launch_tma_y<GB_R_LF, 1>(s_, fused_->map(tmp_, 3, GBY_TW, GBY_TH + 2 * GB_R_LF, g_), 3, t_.blur[kBlurLf], pg, ht_, kBlurLf,
+                           EpiLf{xyb, lf_, mf_in_, g_.pitch, P}, "lf_fused_y");
+  // S3 + S4: mf = Blur(mf_in, 3.73); split, range tweaks, SuppressXByY (+ Malta pre-pass of the mf bands)
+  launch_tma_x<GB_R_MF>(s_, fused_->map(mf_in_, 3, BlurXCfg<GB_R_MF>::SW, GBX_TH, g_), tmp_, 3, t_.blur[kBlurMf], pg, ht_, kBlurMf);
+  EpiMf em;
+  em.mf_in = mf_in_;
+  em.ps = ps;
+  em.hf_raw = hf_raw_;
+  em.ps0 = with_diffs ? ps0_ : nullptr;
+  em.diffs = diffs6_;
+  em.mp_x = malta_[5];
+  em.mp_y = malta_[4];
+  em.pitch = g_.pitch;
+  em.plane = P;
+  launch_tma_y<GB_R_MF, 3>(s_, fused_->map(tmp_, 3, GBY_TW, GBY_TH + 2 * GB_R_MF, g_), 1, t_.blur[kBlurMf], pg, ht_, kBlurMf, em,
+                           "mf_fused_y");
+  // S5 + S6: hf = Blur(hf_raw, 1.87) in one kernel; uhf / hf / lf "vals" (+ Malta pre-pass, noise difference)
+  EpiHf eh;
+  eh.lf_raw = lf_;
+  eh.ps = ps;
+  eh.ps0 = with_diffs ? ps0_ : nullptr;
+  eh.diffs = diffs6_;
+  eh.noise = noise_;
+  eh.mp_uhf_y = malta_[0];
+  eh.mp_uhf_x = malta_[1];
+  eh.mp_hf_y = malta_[2];
+  eh.mp_hf_x = malta_[3];
+  eh.pitch = g_.pitch;
+  eh.plane = P;
+  typedef Blur2dCfg<GB_R_HF, 2> C;
+  launch_tma_2d<GB_R_HF, 2>(s_, fused_->map(hf_raw_, 2, C::SWI, C::HI, g_), t_.blur[kBlurHf], pg, ht_, kBlurHf, eh, "hf_fused");
+}
+
+// Neighbour sums of DiffPrecompute for the original's PsychoImage (constant during the search).
+void ImageContext::fused_sup0() {
+  if (!use_fused_) return;
+  const PlaneGeom pg{g_.w, g_.h, g_.pitch, g_.plane, cr_lo_, cr_hi_};
+  const int rows = cr_hi_ - cr_lo_;
+  dim3 block(32, 8), grid(cdiv(g_.w, 32), cdiv(rows, 8));
+  note_launch("mask_sup0", s_, static_cast<double>(g_.w) * rows);
+  k_mask_sup<<<grid, block, 0, s_>>>(ps0_, sup0_, pg);
+  note_launch_end("mask_sup0", s_);
+}
+
+// One separable blur of a plane group (tests, one-time mask of the original).
+void ImageContext::fused_blur(const float* in, float* out, int nplanes, int id) {
+  const PlaneGeom pg{g_.w, g_.h, g_.pitch, g_.plane, cr_lo_, cr_hi_};
+  const EpiStore st{out, g_.pitch, g_.plane};
+#define GB_BLUR_CASE(R)                                                                                              \
+  case R:                                                                                                            \
+    launch_tma_x<R>(s_, fused_->map(in, nplanes, BlurXCfg<R>::SW, GBX_TH, g_), tmp_, nplanes, t_.blur[id], pg, ht_, id); \
+    launch_tma_y<R, 1>(s_, fused_->map(tmp_, nplanes, GBY_TW, GBY_TH + 2 * R, g_), nplanes, t_.blur[id], pg, ht_, id, st, \
+                       "tma_blur_y");                                                                              \
+    break;
+  switch (t_.blur[id].r) {
+    GB_BLUR_CASE(2)
+    GB_BLUR_CASE(3)
+    GB_BLUR_CASE(4)
+    GB_BLUR_CASE(5)
+    GB_BLUR_CASE(8)
+    GB_BLUR_CASE(16)
+    GB_BLUR_CASE(20)
+    GB_BLUR_CASE(23)
+    default: throw std::runtime_error("blur radius without a compiled kernel");
+  }
+#undef GB_BLUR_CASE
+}
+
+// S1..S13 on the linear RGB planes in lin_ (butteraugli::ButteraugliComparator::Diffmap).
+float ImageContext::fused_compare_tail() {
+  const PlaneGeom pg{g_.w, g_.h, g_.pitch, g_.plane, cr_lo_, cr_hi_};
+  const size_t P = g_.plane;
+  const int rows = cr_hi_ - cr_lo_;
+  fused_opsin(lin_, xyb_);
+  fused_separate(xyb_, ps1_, true);
+  // S7 Malta line sums of both channels: ac[ch] = ((0 + uhf) + hf) + mf
+  {
+    dim3 block(16, 16), grid(cdiv(g_.w, GB_MALTA_TILE_W), cdiv(rows, GB_MALTA_TILE_H), 2);
+    note_launch("malta_sums", s_, 2.0 * g_.w * rows);
+    k_tma_malta_sums<<<grid, block, 0, s_>>>(fused_->map(diffs6_, 6, GB_MALTA_SW, GB_MALTA_SH, g_), ac_, pg);
+    note_launch_end("malta_sums", s_);
+  }
+  // S8 + S9 on block_diff_ac[Y]: blurred noise difference, asymmetric L2 of hf[Y]
+  launch_tma_x<GB_R_NOISE>(s_, fused_->map(noise_, 1, BlurXCfg<GB_R_NOISE>::SW, GBX_TH, g_), tmp_, 1, t_.blur[kBlurNoise], pg,
+                           ht_, kBlurNoise);
+  launch_tma_y<GB_R_NOISE, 1>(s_, fused_->map(tmp_, 1, GBY_TW, GBY_TH + 2 * GB_R_NOISE, g_), 1, t_.blur[kBlurNoise], pg, ht_,
+                              kBlurNoise, EpiNoise{ps0_ + kHfY * P, ps1_ + kHfY * P, ac_ + P, asym_w0_, asym_w1_, g_.pitch},
+                              "noise_fused_y");
+  // S10 mask: DiffPrecompute against the original's resident neighbour sums, x passes
+  {
+    dim3 block(32, 8), grid(cdiv(g_.w, 32), cdiv(rows, 8));
+    note_launch("mask_pre", s_, static_cast<double>(g_.w) * rows);
+    k_mask_pre<<<grid, block, 0, s_>>>(ps1_, sup0_, mpre_, pg);
+    note_launch_end("mask_pre", s_);
+  }
+  static_assert(GB_R_MASKX == GB_R_MASKY1, "the X and the wide Y mask blur share one x-pass launch");
+  // tmp_[0] = x pass of mpre[X] (r 20), tmp_[1] = x pass of mpre[Y] (r 20), tmp_[2] = x pass of mpre[Y] (r 5)
+  if (ht_.blur_taps[kBlurMaskX] != ht_.blur_taps[kBlurMaskY1]) {
+    // different sigmas (9.24 vs 9.04): same radius, different taps -> two launches
+    launch_tma_x<GB_R_MASKX>(s_, fused_->map(mpre_, 1, BlurXCfg<GB_R_MASKX>::SW, GBX_TH, g_), tmp_, 1, t_.blur[kBlurMaskX], pg,
+                             ht_, kBlurMaskX);
+    launch_tma_x<GB_R_MASKY1>(s_, fused_->map(mpre_ + P, 1, BlurXCfg<GB_R_MASKY1>::SW, GBX_TH, g_), tmp_ + P, 1,
+                              t_.blur[kBlurMaskY1], pg, ht_, kBlurMaskY1);
+  } else {
+    launch_tma_x<GB_R_MASKX>(s_, fused_->map(mpre_, 2, BlurXCfg<GB_R_MASKX>::SW, GBX_TH, g_), tmp_, 2, t_.blur[kBlurMaskX], pg,
+                             ht_, kBlurMaskX);
+  }
+  launch_tma_x<GB_R_MASKY0>(s_, fused_->map(mpre_ + P, 1, BlurXCfg<GB_R_MASKY0>::SW, GBX_TH, g_), tmp_ + 2 * P, 1,
+                            t_.blur[kBlurMaskY0], pg, ht_, kBlurMaskY0);
+  // y passes + S11 CombineChannels + first half of S12 -> dm_[1]
+  {
+    typedef MaskYCfg<GB_R_MASKX, GB_R_MASKY0, GB_R_MASKY1> C;
+    allow_smem(k_tma_mask_y<GB_R_MASKX, GB_R_MASKY0, GB_R_MASKY1>, C::kSmemBytes);
+    CombineArgs ca{ps0_, ps1_, ac_, dm_ + P, t_.mask_lut, g_.pitch, P};
+    dim3 grid(cdiv(g_.w, GBY_TW), cdiv(rows, GBY_TH), 1);
+    note_launch("mask_y_combine", s_, static_cast<double>(g_.w) * rows);
+    k_tma_mask_y<GB_R_MASKX, GB_R_MASKY0, GB_R_MASKY1><<<grid, 256, C::kSmemBytes, s_>>>(
+        fused_->map(tmp_, 1, GBY_TW, C::HA, g_), fused_->map(tmp_ + 2 * P, 1, GBY_TW, C::HB, g_),
+        fused_->map(tmp_ + P, 1, GBY_TW, C::HC, g_), t_.blur[kBlurMaskX].scale_y, t_.blur[kBlurMaskY0].scale_y,
+        t_.blur[kBlurMaskY1].scale_y, pg, make_blurk<GB_R_MASKX>(ht_, kBlurMaskX), make_blurk<GB_R_MASKY0>(ht_, kBlurMaskY0),
+        make_blurk<GB_R_MASKY1>(ht_, kBlurMaskY1), ca);
+    note_launch_end("mask_y_combine", s_);
+  }
+  // S12 second half + S13: blur 1.73, mix, per-block maxima, global maximum
+  const bool strips = comm_ && comm_->world() > 1;
+  dev_zero(d_gmax_, sizeof(unsigned int), s_);
+  {
+    typedef Blur2dCfg<GB_R_FINAL, 1> C;
+    EpiFinal ef{dm_, block_max_, strips ? nullptr : d_gmax_, g_.pitch, g_.bw, by_lo_, by_hi_};
+    launch_tma_2d<GB_R_FINAL, 1>(s_, fused_->map(dm_ + P, 1, C::SWI, C::HI, g_), t_.blur[kBlurFinal], pg, ht_, kBlurFinal, ef,
+                                 "final_fused");
+  }
+  if (strips) {
+    gather_blocks(block_max_, sizeof(float));  // strip mode: one float per block crosses NVLink
+    const int lanes = 1024;
+    launch_1d(s_, PartialMax{block_max_, partial_, g_.nblocks, lanes}, lanes, "partial_max");
+    float part[1024];
+    d2h(part, partial_, sizeof(part), s_);
+    float m = 0.0f;
+    for (int i = 0; i < lanes; ++i) m = std::max(m, part[i]);
+    return m;
+  }
+  float m = 0.0f;
+  d2h(&m, d_gmax_, sizeof(float), s_);
+  return m;
+}
+#endif  // !GB200_HOSTSIM
+
 float* ImageContext::planes(int n) {
   void* p = dev_alloc(sizeof(float) * g_.plane * n);
   dev_zero(p, sizeof(float) * g_.plane * n, s_);
@@ -124,6 +382,7 @@ ImageContext::ImageContext(const float* linear_rgb, int w, int h, int device)
     upload_planes(linear_rgb, lin_, 3);
     opsin(lin_, xyb_);
     separate(xyb_, ps0_);
+    fused_sup0();
     stream_sync(s_);
   } catch (...) {
     release();
@@ -244,6 +503,16 @@ void ImageContext::init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int
   mpre_ = planes(2);
   sact_ = planes(3);
   dm_ = planes(2);
+#if !defined(GB200_HOSTSIM)
+  use_fused_ = fused_enabled();
+  if (use_fused_) {
+    fused_ = new Fused();
+    diffs6_ = planes(6);
+    sup0_ = planes(2);
+    d_gmax_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int)));
+    owned_.push_back(d_gmax_);
+  }
+#endif
 
   metric_ = (w >= 32 && h >= 32);  // g/processor.cc:940: no Butteraugli below 32x32
   prepared_ = false;
@@ -293,6 +562,7 @@ void ImageContext::prepare() {
   px(LinearizeRgb{d_rgb_, lin_, g_, t_.srgb_lin}, "linearize_rgb");
   opsin(lin_, xyb_);
   separate(xyb_, ps0_);
+  fused_sup0();
 
   // a13: mask_xyz_ = Mask(xyb0, xyb0), only its block-corner samples are ever read.
   px(MaskDiffPreSelf{xyb_, mpre_, g_}, "mask_diff_pre_self");
@@ -328,11 +598,21 @@ void ImageContext::release() {
   if (e_slot_) { dev_free(e_slot_); e_slot_ = nullptr; }
   for (size_t i = 0; i < owned_.size(); ++i) dev_free(owned_[i]);
   owned_.clear();
+#if !defined(GB200_HOSTSIM)
+  delete fused_;
+  fused_ = nullptr;
+#endif
   if (have_stream_) destroy_stream(s_);
   have_stream_ = false;
 }
 
 void ImageContext::blur(const float* in, float* out, int nplanes, int id) {
+#if !defined(GB200_HOSTSIM)
+  if (use_fused_) {
+    fused_blur(in, out, nplanes, id);
+    return;
+  }
+#endif
 #if defined(GB200_HOSTSIM)
   px(BlurX{in, tmp_, t_.blur[id], g_}, "blur_x", nplanes);
   px(BlurY{tmp_, out, t_.blur[id], g_}, "blur_y", nplanes);
@@ -342,11 +622,23 @@ void ImageContext::blur(const float* in, float* out, int nplanes, int id) {
 }
 
 void ImageContext::opsin(const float* lin, float* xyb) {
+#if !defined(GB200_HOSTSIM)
+  if (use_fused_) {
+    fused_opsin(lin, xyb);
+    return;
+  }
+#endif
   blur(lin, blr_, 3, kBlurOpsin);
   px(OpsinPx{lin, blr_, xyb, g_}, "opsin_px");
 }
 
 void ImageContext::separate(const float* xyb, float* ps) {
+#if !defined(GB200_HOSTSIM)
+  if (use_fused_) {
+    fused_separate(xyb, ps, false);
+    return;
+  }
+#endif
   blur(xyb, lf_, 3, kBlurLf);
   px(SubPlanes{xyb, lf_, mf_in_, g_}, "sub_planes", 3);
   blur(mf_in_, mf_blr_, 3, kBlurMf);
@@ -439,6 +731,9 @@ float ImageContext::compare() {
 // S1..S13 on the linear RGB planes in lin_ (butteraugli::ButteraugliComparator::Diffmap).
 float ImageContext::compare_tail() {
   bind();
+#if !defined(GB200_HOSTSIM)
+  if (use_fused_) return fused_compare_tail();
+#endif
   const size_t P = g_.plane;
   opsin(lin_, xyb_);
   separate(xyb_, ps1_);
@@ -501,6 +796,7 @@ float ImageContext::compare_tail() {
   for (int i = 0; i < lanes; ++i) m = std::max(m, part[i]);
   return m;
 }
+
 
 void ImageContext::download_planes(const float* src, float* packed, int n) {
   std::vector<float> buf(g_.plane * n);

@@ -129,6 +129,18 @@ class ImageContext {
   void download_planes(const float* src, float* packed, int n);
   float* planes(int n);
 
+  // TMA-staged fused Compare chain (fused_kernels.cuh; CUDA build only)
+  struct Fused;
+  Fused* fused_ = nullptr;
+  float* diffs6_ = nullptr;  // [6] Malta pre-pass planes: X uhf, hf, mf; Y uhf, hf, mf
+  float* sup0_ = nullptr;    // [2] DiffPrecompute neighbour sums of the original (X, Y)
+  unsigned int* d_gmax_ = nullptr;  // global maximum of the distmap (float bits)
+  bool use_fused_ = false;
+  void fused_opsin(const float* lin, float* xyb);
+  void fused_separate(const float* xyb, float* ps, bool with_diffs);
+  void fused_blur(const float* in, float* out, int nplanes, int id);
+  float fused_compare_tail();
+  void fused_sup0();
   void guarded_init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int h, bool prepare_now);
   void release();
   bool released_ = false;

@@ -97,18 +97,21 @@ def _large_cases():
     return json.load(open(path)) if os.path.exists(path) else {}
 
 
-@pytest.mark.parametrize("name", sorted(_large_cases()))
+FULL_SIZE = {
+    "noise1080p_s1234_q95": lambda: synth.noise(1080, 1920, 1234),          # BASELINE configs[1]
+    "gradnoise4k_s4321_q90": lambda: synth.gradnoise(2160, 3840, 4321),     # configs[2]
+    "gradnoise1024_s1000_q84": lambda: synth.gradnoise(1024, 1024, 1000),   # configs[4], image 0
+    "gradnoise8k_s8192_q95": lambda: synth.gradnoise(4320, 7680, 8192),     # configs[3] (here: untiled, one GPU)
+}
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(FULL_SIZE) if n in _large_cases()])
 def test_process_matches_golden_full_size(cuda_lib, name):
     """BASELINE.json full-size configurations against the reference's own answers
-    (tests/golden/make_golden_large.py: minutes to tens of minutes of CPU each)."""
+    (tests/golden/make_golden_large.py: minutes to hours of CPU each)."""
     import hashlib
     g = _large_cases()[name]
-    gens = {
-        "noise1080p_s1234_q95": lambda: synth.noise(1080, 1920, 1234),
-        "gradnoise4k_s4321_q90": lambda: synth.gradnoise(2160, 3840, 4321),
-        "gradnoise1024_s1000_q84": lambda: synth.gradnoise(1024, 1024, 1000),
-    }
-    rgb = gens[name]()
+    rgb = FULL_SIZE[name]()
     assert synth.sha256(rgb) == g["input_sha256"]
     ok, jpeg, trace, st = parity.run_process(cuda_lib, rgb, g["quality"])
     assert ok and len(jpeg) == g["jpeg_size"]
@@ -116,6 +119,81 @@ def test_process_matches_golden_full_size(cuda_lib, name):
     assert hashlib.sha256(trace.encode()).hexdigest() == g["trace_sha256"]
     assert [st.counters["number of iterations"], st.counters["number of iterations up"],
             st.counters["number of iterations down"]] == g["iterations"]
+
+
+def test_batch64_matches_golden(cuda_lib):
+    """BASELINE configs[4]: all 64 images gradnoise(1024, 1024, 1000 + i) at q84 against the
+    reference's hashes (tests/golden/make_golden_batch64.sh), 16 at a time on this GPU."""
+    import hashlib
+    from concurrent.futures import ThreadPoolExecutor
+    cases = _large_cases()
+    names = ["gradnoise1024_s%d_q84" % (1000 + i) for i in range(64)]
+    have = [n for n in names if n in cases]
+    if len(have) < 64:
+        pytest.skip("golden_large.json holds %d of the 64 batch answers" % len(have))
+
+    def one(i):
+        g = cases[names[i]]
+        rgb = synth.gradnoise(1024, 1024, 1000 + i)
+        assert synth.sha256(rgb) == g["input_sha256"]
+        ok, jpeg, _, st = parity.run_process(cuda_lib, rgb, 84)
+        return (ok, len(jpeg), hashlib.sha256(jpeg).hexdigest(), st.counters["number of iterations"])
+
+    with ThreadPoolExecutor(16) as pool:
+        got = list(pool.map(one, range(64)))
+    for i, (ok, size, sha, iters) in enumerate(got):
+        g = cases[names[i]]
+        assert ok and size == g["jpeg_size"] and sha == g["jpeg_sha256"] and iters == g["iterations"][0], names[i]
+
+
+AB_IMAGES = [("noise", 40, 33, 2), ("gradnoise", 70, 51, 3), ("noise", 136, 200, 4), ("gradnoise", 32, 300, 5),
+             ("noise", 300, 32, 6), ("gradnoise", 260, 410, 8)]
+
+
+@pytest.mark.parametrize("gen,h,w,seed", AB_IMAGES)
+def test_fused_matches_staged(cuda_lib, gen, h, w, seed):
+    """The TMA-staged fused Compare chain (fused_kernels.cuh, default) against the staged
+    round-1 sequence of the same library (GB200_COMPARE=staged): every intermediate that both
+    expose must have identical bits.  Localises a defect to a stage."""
+    import os
+    import guetzli_b200 as gb
+    rgb = getattr(synth, gen)(h, w, seed)
+    rng = np.random.default_rng(seed)
+    plane = (rng.random((h, w), dtype=np.float32) * 255).astype(np.float32)
+    q = parity.test_quant(seed)
+    out = {}
+    for mode in ("staged", "fused"):
+        os.environ["GB200_COMPARE"] = mode
+        try:
+            img = gb.DeviceImage(rgb, lib=cuda_lib)
+        finally:
+            del os.environ["GB200_COMPARE"]
+        r = {}
+        for i in range(len(parity.BLUR_SPECS)):
+            r["blur%d" % i] = img.debug_blur(plane, i)
+        lin = img.debug_render()
+        r["opsin"] = img.debug_opsin(lin)
+        r["separate"] = img.debug_separate(r["opsin"])
+        r["psycho0"] = img.debug_psycho0()
+        r["corner_mask"] = img.debug_corner_mask()
+        img.apply_global_quant(q)
+        r["distance"] = np.float32(img.compare())
+        r["distmap"] = img.distmap()
+        r["weights"] = img.block_weights(-1, 2, 1.0, False)
+        cand = img.download_candidate().reshape(-1)
+        nz = np.flatnonzero(cand)[::7][:50].astype(np.int32)
+        img.scatter(nz, np.zeros(len(nz), dtype=np.int16))
+        r["distance2"] = np.float32(img.compare())
+        r["distmap2"] = img.distmap()
+        img.close()
+        out[mode] = r
+    for key in out["staged"]:
+        a, b = np.asarray(out["staged"][key]), np.asarray(out["fused"][key])
+        if not parity.bits_equal(a, b):
+            bad = np.argwhere(a.view(np.uint32) != b.view(np.uint32))
+            raise AssertionError(f"{key}: {len(bad)} of {a.size} values differ, first at {bad[0].tolist()}: "
+                                 f"staged {a[tuple(bad[0])]!r} fused {b[tuple(bad[0])]!r}; "
+                                 f"last at {bad[-1].tolist()}")
 
 
 @pytest.mark.parametrize("name,world", [("bees_444x258_q95", 3), ("odd_70x51_s3_q88", 2)])
