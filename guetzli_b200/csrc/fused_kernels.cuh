@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128) k_tma_blur_x(const __grid_constant__ CUte
 #define GBY_G 16
 
 template <int R, int NP, class Epi>
-__global__ void __launch_bounds__(256) k_tma_blur_y(const __grid_constant__ CUtensorMap in_map, const float* scale_y,
+__global__ void __launch_bounds__(256, NP == 1 ? 3 : 2) k_tma_blur_y(const __grid_constant__ CUtensorMap in_map, const float* scale_y,
                                                     PlaneGeom g, BlurK<R> k, Epi epi) {
   constexpr int HI = GBY_TH + 2 * R;
   extern __shared__ __align__(128) float dyn_smem[];
@@ -195,14 +195,26 @@ __global__ void __launch_bounds__(256) k_tma_blur_y(const __grid_constant__ CUte
     }
   }
   if (x >= g.w) return;
+  // Epilogue in chunks: first every global operand of the chunk's pixels (read-only path,
+  // all loads in flight together), then the arithmetic and the stores.
+  constexpr int CH = Epi::kChunk;
 #pragma unroll
-  for (int o = 0; o < GBY_G; ++o) {
-    const int y = yg + o;
-    if (y >= g.y_end) break;
-    float v[NP];
+  for (int o0 = 0; o0 < GBY_G; o0 += CH) {
+    typename Epi::Pre pre[CH];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) v[p] = res[p][o];
-    epi(x, y, pz, v);
+    for (int i = 0; i < CH; ++i) {
+      const int y = yg + o0 + i;
+      if (y < g.y_end) epi.load(x, y, pz, pre[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int y = yg + o0 + i;
+      if (y >= g.y_end) continue;
+      float v[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) v[p] = res[p][o0 + i];
+      epi.apply(x, y, pz, v, pre[i]);
+    }
   }
 }
 
@@ -295,30 +307,49 @@ __global__ void __launch_bounds__(256) k_tma_blur_2d(const __grid_constant__ CUt
   }
   const bool live_col = x < g.w;
   float carry = 0.0f;  // per-thread state of the epilogue across its 8 rows (EpiFinal: running block maximum)
+  constexpr int CH = Epi::kChunk;
 #pragma unroll
-  for (int o = 0; o < GB2_G; ++o) {
-    const int y = yg + o;
-    float v[NP], sharp[NP];
+  for (int o0 = 0; o0 < GB2_G; o0 += CH) {
+    typename Epi::Pre pre[CH];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      v[p] = res[p][o];
-      sharp[p] = in[(p * HI + R + GB2_G * grp + o) * SWI + RP + c];
+    for (int i = 0; i < CH; ++i) {
+      const int y = yg + o0 + i;
+      if (live_col && y < g.y_end) epi.load(x, y, pre[i]);
     }
-    // every thread calls the epilogue (it may contain warp-wide reductions); `live` tells
-    // whether (x, y) is a pixel this launch must produce
-    epi(x, y, live_col && y < g.y_end, sharp, v, carry);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int o = o0 + i, y = yg + o;
+      float v[NP], sharp[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        v[p] = res[p][o];
+        sharp[p] = in[(p * HI + R + GB2_G * grp + o) * SWI + RP + c];
+      }
+      // every thread calls the epilogue (it may contain warp-wide reductions); `live` tells
+      // whether (x, y) is a pixel this launch must produce
+      epi.apply(x, y, live_col && y < g.y_end, sharp, v, pre[i], carry);
+    }
   }
 }
 
 // ---------------------------------------------------------------------------
 // Epilogues.  Plane groups are addressed as base + plane_index * g.plane + y * pitch + x.
 
+// Each epilogue has two halves: load() fetches the pixel's global operands through the
+// read-only path into a Pre, apply() does the arithmetic and the stores.  The kernels call
+// load() for a chunk of kChunk pixels before the first apply(), so that the chunk's loads are
+// in flight together instead of queueing behind one another's dependent stores.
+struct NoPre {};
+
 // plain store (stand-alone blur: tests, the one-time mask of the original)
 struct EpiStore {
   float* out;
   int pitch;
   size_t plane;
-  __device__ __forceinline__ void operator()(int x, int y, int pz, const float v[1]) const {
+  typedef NoPre Pre;
+  static constexpr int kChunk = 16;
+  __device__ __forceinline__ void load(int, int, int, Pre&) const {}
+  __device__ __forceinline__ void apply(int x, int y, int pz, const float v[1], const Pre&) const {
     out[pz * plane + static_cast<size_t>(y) * pitch + x] = v[0];
   }
 };
@@ -330,10 +361,17 @@ struct EpiLf {
   float* mf_in;
   int pitch;
   size_t plane;
-  __device__ __forceinline__ void operator()(int x, int y, int pz, const float v[1]) const {
+  struct Pre {
+    float a;
+  };
+  static constexpr int kChunk = 8;
+  __device__ __forceinline__ void load(int x, int y, int pz, Pre& p) const {
+    p.a = __ldg(xyb + pz * plane + static_cast<size_t>(y) * pitch + x);
+  }
+  __device__ __forceinline__ void apply(int x, int y, int pz, const float v[1], const Pre& p) const {
     const size_t o = pz * plane + static_cast<size_t>(y) * pitch + x;
     lf[o] = v[0];
-    mf_in[o] = xyb[o] - v[0];
+    mf_in[o] = p.a - v[0];
   }
 };
 
@@ -349,11 +387,24 @@ struct EpiMf {
   MaltaParams mp_x, mp_y;
   int pitch;
   size_t plane;
-  __device__ __forceinline__ void operator()(int x, int y, int, const float v[3]) const {
+  struct Pre {
+    float inx, iny, p0x, p0y;
+  };
+  static constexpr int kChunk = 8;
+  __device__ __forceinline__ void load(int x, int y, int, Pre& p) const {
+    const size_t o = static_cast<size_t>(y) * pitch + x;
+    p.inx = __ldg(mf_in + o);
+    p.iny = __ldg(mf_in + plane + o);
+    if (ps0 != nullptr) {
+      p.p0x = __ldg(ps0 + kMfX * plane + o);
+      p.p0y = __ldg(ps0 + kMfY * plane + o);
+    }
+  }
+  __device__ __forceinline__ void apply(int x, int y, int, const float v[3], const Pre& p) const {
     const size_t o = static_cast<size_t>(y) * pitch + x;
     const float mbx = v[0], mby = v[1];
-    const float hx = mf_in[o] - mbx;
-    const float hy = mf_in[plane + o] - mby;
+    const float hx = p.inx - mbx;
+    const float hy = p.iny - mby;
     const float mfx = remove_range_around_zero(static_cast<float>(0.120079806822), mbx);
     const float mfy = amplify_range_around_zero(static_cast<float>(0.03430529365), mby);
     ps[kMfX * plane + o] = mfx;
@@ -362,8 +413,8 @@ struct EpiMf {
     hf_raw[o] = suppress_x_by_y(hx, hy);
     hf_raw[plane + o] = hy;
     if (ps0 != nullptr) {
-      diffs[2 * plane + o] = malta_diff(ps0[kMfX * plane + o], mfx, mp_x);
-      diffs[5 * plane + o] = malta_diff(ps0[kMfY * plane + o], mfy, mp_y);
+      diffs[2 * plane + o] = malta_diff(p.p0x, mfx, mp_x);
+      diffs[5 * plane + o] = malta_diff(p.p0y, mfy, mp_y);
     }
   }
 };
@@ -373,8 +424,11 @@ struct EpiOpsin {
   float* xyb;
   int pitch;
   size_t plane;
-  __device__ __forceinline__ void operator()(int x, int y, bool live, const float sharp[3], const float v[3],
-                                             float&) const {
+  typedef NoPre Pre;
+  static constexpr int kChunk = 8;
+  __device__ __forceinline__ void load(int, int, Pre&) const {}
+  __device__ __forceinline__ void apply(int x, int y, bool live, const float sharp[3], const float v[3], const Pre&,
+                                        float&) const {
     if (!live) return;
     const size_t o = static_cast<size_t>(y) * pitch + x;
     opsin_pixel(sharp[0], sharp[1], sharp[2], v[0], v[1], v[2], &xyb[o], &xyb[plane + o], &xyb[2 * plane + o]);
@@ -393,13 +447,29 @@ struct EpiHf {
   MaltaParams mp_uhf_x, mp_uhf_y, mp_hf_x, mp_hf_y;
   int pitch;
   size_t plane;
-  __device__ __forceinline__ void operator()(int x, int y, bool live, const float sharp[2], const float v[2],
-                                             float&) const {
+  struct Pre {
+    float lfx, lfy, lfb, u0x, h0x, u0y, h0y;
+  };
+  static constexpr int kChunk = 4;
+  __device__ __forceinline__ void load(int x, int y, Pre& p) const {
+    const size_t o = static_cast<size_t>(y) * pitch + x;
+    p.lfx = __ldg(lf_raw + o);
+    p.lfy = __ldg(lf_raw + plane + o);
+    p.lfb = __ldg(lf_raw + 2 * plane + o);
+    if (ps0 != nullptr) {
+      p.u0x = __ldg(ps0 + kUhfX * plane + o);
+      p.h0x = __ldg(ps0 + kHfX * plane + o);
+      p.u0y = __ldg(ps0 + kUhfY * plane + o);
+      p.h0y = __ldg(ps0 + kHfY * plane + o);
+    }
+  }
+  __device__ __forceinline__ void apply(int x, int y, bool live, const float sharp[2], const float v[2], const Pre& p,
+                                        float&) const {
     if (!live) return;
     const size_t o = static_cast<size_t>(y) * pitch + x;
     const float uhfx = sharp[0] - v[0];
     const float hfx = remove_range_around_zero(static_cast<float>(0.0287615200377), v[0]);
-    const float lfx = lf_raw[o], lfy = lf_raw[plane + o], lfb = lf_raw[2 * plane + o];
+    const float lfx = p.lfx, lfy = p.lfy, lfb = p.lfb;
     const float kMulSuppressHf = static_cast<float>(1.10684769012);
     const float kMulRegHf = static_cast<float>(0.478741530298);
     const float kRegHf = 2000 * kMulRegHf;
@@ -424,10 +494,10 @@ struct EpiHf {
     ps[kLfX * plane + o] = lfx * xmul;
     ps[kLfY * plane + o] = lfy * ymul;
     if (ps0 != nullptr) {
-      const float h0y = ps0[kHfY * plane + o];
-      diffs[0 * plane + o] = malta_diff(ps0[kUhfX * plane + o], uhfx, mp_uhf_x);
-      diffs[1 * plane + o] = malta_diff(ps0[kHfX * plane + o], hfx, mp_hf_x);
-      diffs[3 * plane + o] = malta_diff(ps0[kUhfY * plane + o], uhfy, mp_uhf_y);
+      const float h0y = p.h0y;
+      diffs[0 * plane + o] = malta_diff(p.u0x, uhfx, mp_uhf_x);
+      diffs[1 * plane + o] = malta_diff(p.h0x, hfx, mp_hf_x);
+      diffs[3 * plane + o] = malta_diff(p.u0y, uhfy, mp_uhf_y);
       diffs[4 * plane + o] = malta_diff(h0y, hfy, mp_hf_y);
       const double maxclamp = 85.7047444518;
       double v0 = hd_fabsf(h0y);
@@ -443,18 +513,28 @@ struct EpiHf {
 struct EpiNoise {
   const float* hf0;  // pi0.hf[Y]
   const float* hf1;  // pi1.hf[Y]
-  float* acc;        // block_diff_ac[Y], read-modify-write
+  float* acc;        // block_diff_ac[Y], read-modify-write (each pixel by exactly one thread)
   double w_0gt1, w_0lt1;
   int pitch;
-  __device__ __forceinline__ void operator()(int x, int y, int, const float v[1]) const {
+  struct Pre {
+    float r0, r1, a;
+  };
+  static constexpr int kChunk = 8;
+  __device__ __forceinline__ void load(int x, int y, int, Pre& p) const {
     const size_t o = static_cast<size_t>(y) * pitch + x;
-    float a = acc[o];
+    p.r0 = __ldg(hf0 + o);
+    p.r1 = __ldg(hf1 + o);
+    p.a = acc[o];  // plain load: this launch writes the location later (same thread)
+  }
+  __device__ __forceinline__ void apply(int x, int y, int, const float v[1], const Pre& p) const {
+    const size_t o = static_cast<size_t>(y) * pitch + x;
+    float a = p.a;
     {
       const double w = 884.809801415;
       const double diff = v[0];
       a = static_cast<float>(static_cast<double>(a) + w * diff * diff);
     }
-    const float r0 = hf0[o], r1f = hf1[o];
+    const float r0 = p.r0, r1f = p.r1;
     const double diff = r0 - r1f;  // float subtraction, then widened
     a = static_cast<float>(static_cast<double>(a) + w_0gt1 * diff * diff);
     const double fabs0 = hd_fabsf(r0);
@@ -492,9 +572,12 @@ struct EpiFinal {
   float* block_max;     // [nblocks], written for block rows [by_lo, by_hi)
   unsigned int* gmax;   // global maximum (float bits), or nullptr
   int pitch, bw, by_lo, by_hi;
+  typedef NoPre Pre;
+  static constexpr int kChunk = 8;
+  __device__ __forceinline__ void load(int, int, Pre&) const {}
   // m: running maximum of the thread's pixels of the current block row (one block column)
-  __device__ __forceinline__ void operator()(int x, int y, bool live, const float sharp[1], const float v[1],
-                                             float& m) const {
+  __device__ __forceinline__ void apply(int x, int y, bool live, const float sharp[1], const float v[1], const Pre&,
+                                        float& m) const {
     if (live) {
       const double mul1 = 0.458794906198;
       const float scale = static_cast<float>(1.0f / (1.0f + mul1));
@@ -588,6 +671,17 @@ __global__ void __launch_bounds__(256) k_tma_mask_y(const __grid_constant__ CUte
   mask_y_plane<RA, false>(ta + (GBY_G * grp) * GBY_TW + c, ka, sya, yg, g.h, (yb < RA) || (yb + GBY_TH + RA > g.h), sx);
   mask_y_plane<RB, false>(tb + (GBY_G * grp) * GBY_TW + c, kb, syb, yg, g.h, (yb < RB) || (yb + GBY_TH + RB > g.h), sy1);
   mask_y_plane<RC, false>(tc + (GBY_G * grp) * GBY_TW + c, kc, syc, yg, g.h, (yb < RC) || (yb + GBY_TH + RC > g.h), sy2);
+  // The three activities go back to shared memory (over the input tiles, which are dead once
+  // every thread has finished its passes), each thread into slots only it reads again: the
+  // epilogue below can then be a rolled loop instead of 16 unrolled copies of the LUT code.
+  __syncthreads();
+  float* stash = dyn_smem + threadIdx.x;  // [3][GBY_G][256]
+#pragma unroll
+  for (int o = 0; o < GBY_G; ++o) {
+    stash[(0 * GBY_G + o) * 256] = sx[o];
+    stash[(1 * GBY_G + o) * 256] = sy1[o];
+    stash[(2 * GBY_G + o) * 256] = sy2[o];
+  }
   if (x >= g.w) return;
   CombineAndSqrt comb;
   comb.ps0 = ca.ps0;
@@ -597,10 +691,29 @@ __global__ void __launch_bounds__(256) k_tma_mask_y(const __grid_constant__ CUte
   comb.luts = ca.luts;
   comb.g.pitch = ca.pitch;
   comb.g.plane = ca.plane;
+  constexpr int CH = 4;
+#pragma unroll 1
+  for (int o0 = 0; o0 < GBY_G; o0 += CH) {
+    float l0x[CH], l0b[CH], l1x[CH], l1b[CH], acx[CH], acy[CH];
 #pragma unroll
-  for (int o = 0; o < GBY_G; ++o) {
-    const int y = yg + o;
-    if (y < g.y_end) comb.pixel(x, y, sx[o], sy1[o], sy2[o]);
+    for (int i = 0; i < CH; ++i) {
+      const int y = yg + o0 + i;
+      if (y >= g.y_end) continue;
+      const size_t o = static_cast<size_t>(y) * ca.pitch + x;
+      l0x[i] = __ldg(ca.ps0 + kLfX * ca.plane + o);
+      l0b[i] = __ldg(ca.ps0 + kLfB * ca.plane + o);
+      l1x[i] = __ldg(ca.ps1 + kLfX * ca.plane + o);
+      l1b[i] = __ldg(ca.ps1 + kLfB * ca.plane + o);
+      acx[i] = __ldg(ca.ac + o);
+      acy[i] = __ldg(ca.ac + ca.plane + o);
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int y = yg + o0 + i;
+      if (y >= g.y_end) continue;
+      comb.pixel_with(x, y, stash[(0 * GBY_G + o0 + i) * 256], stash[(1 * GBY_G + o0 + i) * 256],
+                      stash[(2 * GBY_G + o0 + i) * 256], l0x[i], l0b[i], l1x[i], l1b[i], acx[i], acy[i]);
+    }
   }
 }
 

@@ -522,18 +522,25 @@ struct CombineAndSqrt {
   // y pass of the mask blurs hands them over in registers)
   GB_HD void pixel(int x, int y, float s_x, float s_y1, float s_y2) const {
     const size_t o = static_cast<size_t>(y) * g.pitch + x;
+    pixel_with(x, y, s_x, s_y1, s_y2, ps0[kLfX * g.plane + o], ps0[kLfB * g.plane + o], ps1[kLfX * g.plane + o],
+               ps1[kLfB * g.plane + o], ac[o], ac[g.plane + o]);
+  }
+  // ... and with the six plane samples of the pixel already loaded
+  GB_HD void pixel_with(int x, int y, float s_x, float s_y1, float s_y2, float lf0x, float lf0b, float lf1x, float lf1b,
+                        float ac_x, float ac_y) const {
+    const size_t o = static_cast<size_t>(y) * g.pitch + x;
     float mask[3], dc_mask[3];
     mask_from_activity(luts, s_x, mask_y_activity(s_y1, s_y2), mask, dc_mask);
     float diff_dc[3], diff_ac[3];
     {
-      const double d = ps0[kLfX * g.plane + o] - ps1[kLfX * g.plane + o];
+      const double d = lf0x - lf1x;
       diff_dc[0] = static_cast<float>(0.0 + 1.01370836411 * d * d);
       diff_dc[1] = 0.0f;
-      const double e = ps0[kLfB * g.plane + o] - ps1[kLfB * g.plane + o];
+      const double e = lf0b - lf1b;
       diff_dc[2] = static_cast<float>(0.0 + 1.74566011615 * e * e);
     }
-    diff_ac[0] = ac[o];
-    diff_ac[1] = ac[g.plane + o];
+    diff_ac[0] = ac_x;
+    diff_ac[1] = ac_y;
     diff_ac[2] = 0.0f;
     const float dot_dc = diff_dc[0] * dc_mask[0] + diff_dc[1] * dc_mask[1] + diff_dc[2] * dc_mask[2];
     const float dot_ac = diff_ac[0] * mask[0] + diff_ac[1] * mask[1] + diff_ac[2] * mask[2];
