@@ -11,6 +11,7 @@
 
 #include "block_math.h"
 #include "jpeg_dev.h"
+#include "walk_dev.h"
 #if !defined(GB200_HOSTSIM)
 #include <map>
 #include <tuple>
@@ -585,6 +586,15 @@ void ImageContext::release() {
   } catch (...) {
     // a failed device cannot be waited for; the blocks still go back to the cache
   }
+  if (d_sel_val2_) { dev_free(d_sel_val2_); d_sel_val2_ = nullptr; }
+  if (d_sel_block2_) { dev_free(d_sel_block2_); d_sel_block2_ = nullptr; }
+  if (w_log_index_) { dev_free(w_log_index_); w_log_index_ = nullptr; }
+  if (w_log_old_) { dev_free(w_log_old_); w_log_old_ = nullptr; }
+  if (w_gblocks_) { dev_free(w_gblocks_); w_gblocks_ = nullptr; }
+  if (w_gcoeffs_) { dev_free(w_gcoeffs_); w_gcoeffs_ = nullptr; }
+  if (w_gcursor_) { dev_free(w_gcursor_); w_gcursor_ = nullptr; }
+  if (w_ginbulk_) { dev_free(w_ginbulk_); w_ginbulk_ = nullptr; }
+  if (w_ablocks_) { dev_free(w_ablocks_); w_ablocks_ = nullptr; }
   if (d_sel_val_) { dev_free(d_sel_val_); d_sel_val_ = nullptr; }
   if (d_sel_block_) { dev_free(d_sel_block_); d_sel_block_ = nullptr; }
   if (x_items_) { dev_free(x_items_); x_items_ = nullptr; }
@@ -707,21 +717,34 @@ float ImageContext::compare() {
     dirty_list_.resize(keep);
     for (size_t i = 0; i < keep; ++i) dirty_flag_[dirty_list_[i]] = 1;
   }
-  if (render_all_ || dirty_list_.size() > static_cast<size_t>(rb_hi - rb_lo) * g_.bw / 2) {
+  const bool all = render_all_ || dirty_list_.size() + static_cast<size_t>(pending_touched_) >
+                                      static_cast<size_t>(rb_hi - rb_lo) * g_.bw / 2;
+  if (all) {
 #if defined(GB200_HOSTSIM)
     block_rows(RenderBlocks{d_cand_, lin_, g_, t_}, "render_blocks", rb_lo, rb_hi);
 #else
     launch_render_blocks_warp(s_, RenderWarpArgs{d_cand_, lin_, nullptr, rb_lo * g_.bw, (rb_hi - rb_lo) * g_.bw, g_, t_});
 #endif
-  } else if (!dirty_list_.empty()) {
-    const int nd = static_cast<int>(dirty_list_.size());
-    h2d(d_dirty_, dirty_list_.data(), sizeof(int) * nd, s_);
+  } else {
+    if (!dirty_list_.empty()) {
+      const int nd = static_cast<int>(dirty_list_.size());
+      h2d(d_dirty_, dirty_list_.data(), sizeof(int) * nd, s_);
 #if defined(GB200_HOSTSIM)
-    launch_1d(s_, RenderBlockList{RenderBlocks{d_cand_, lin_, g_, t_}, d_dirty_}, nd, "render_blocks");
+      launch_1d(s_, RenderBlockList{RenderBlocks{d_cand_, lin_, g_, t_}, d_dirty_}, nd, "render_blocks");
 #else
-    launch_render_blocks_warp(s_, RenderWarpArgs{d_cand_, lin_, d_dirty_, 0, nd, g_, t_});
+      launch_render_blocks_warp(s_, RenderWarpArgs{d_cand_, lin_, d_dirty_, 0, nd, g_, t_});
 #endif
+    }
+    if (pending_touched_ > 0) {
+      // blocks changed by the device half of the selection walk: their list is already resident
+#if defined(GB200_HOSTSIM)
+      launch_1d(s_, RenderBlockList{RenderBlocks{d_cand_, lin_, g_, t_}, w_touched_}, pending_touched_, "render_blocks");
+#else
+      launch_render_blocks_warp(s_, RenderWarpArgs{d_cand_, lin_, w_touched_, 0, pending_touched_, g_, t_});
+#endif
+    }
   }
+  pending_touched_ = 0;
   render_all_ = false;
   for (size_t i = 0; i < dirty_list_.size(); ++i) dirty_flag_[dirty_list_[i]] = 0;
   dirty_list_.clear();
@@ -906,11 +929,10 @@ void ImageContext::zeroing_orders(float block_error_limit, int lookahead, bool n
   }
 }
 
-size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_index,
-                                    const std::vector<float>& max_err, size_t k, std::vector<float>* val,
-                                    std::vector<int>* block) {
-  h2d(d_last_index_, last_index.data(), sizeof(int) * g_.nblocks, s_);
-  h2d(d_max_err_, max_err.data(), sizeof(float) * g_.nblocks, s_);
+// Two-level radix select of the k-th smallest key, entirely on the device, then the
+// compaction of every entry whose key is <= the threshold bin into d_sel_val_ / d_sel_block_
+// (unsorted).  Uses the resident candidate cursors and max errors.
+void ImageContext::select_keys(int direction, size_t k, OrderSelectState* got_out) {
   OrderSelectState init;
   memset(&init, 0, sizeof(init));
   init.want = static_cast<unsigned int>(k);
@@ -924,7 +946,6 @@ size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_
   c.max_err = d_max_err_;
   c.weight = weights_;
   c.direction = direction;
-  // two-level radix select of the k-th smallest key, entirely on the device
   for (int level = 0; level < 2; ++level) {
     dev_zero(d_hist_, sizeof(unsigned int) * kOrderBins, s_);
 #if defined(GB200_HOSTSIM)
@@ -947,6 +968,17 @@ size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_
   }
   launch_1d(s_, OrderKeyCompact{c, st, d_sel_val_, d_sel_block_, static_cast<unsigned int>(sel_cap_)},
             static_cast<int>(num_entries_), "order_key_compact");
+  *got_out = got;
+}
+
+size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_index,
+                                    const std::vector<float>& max_err, size_t k, std::vector<float>* val,
+                                    std::vector<int>* block) {
+  h2d(d_last_index_, last_index.data(), sizeof(int) * g_.nblocks, s_);
+  h2d(d_max_err_, max_err.data(), sizeof(float) * g_.nblocks, s_);
+  OrderSelectState got;
+  select_keys(direction, k, &got);
+  const size_t kept = got.kept;
   val->resize(kept);
   block->resize(kept);
   if (kept) {
@@ -954,6 +986,505 @@ size_t ImageContext::order_smallest(int direction, const std::vector<int>& last_
     d2h(block->data(), d_sel_block_, kept * sizeof(int), s_);
   }
   return got.total;
+}
+
+#if !defined(GB200_HOSTSIM)
+namespace {
+// entries / blocks of the order implied by the weights: one thread per block, warp-shuffle and
+// shared-memory reduction, two 64-bit atomics per CTA (same sums as WalkStatsPartial)
+__global__ void __launch_bounds__(256) k_walk_stats(const int* last_index, const int* z_cnt, const float* weight,
+                                                    int direction, int nblocks, unsigned long long* out) {
+  __shared__ unsigned int sh[2][8];
+  const int b = blockIdx.x * 256 + threadIdx.x;
+  unsigned int m = 0u, c = 0u;
+  if (b < nblocks && weight[b] != 0) {
+    const int li = last_index[b], nc = z_cnt[b];
+    const int v = direction > 0 ? (li < nc ? nc - li : 0) : (li > 0 ? li : 0);
+    m = static_cast<unsigned int>(v);
+    c = v > 0 ? 1u : 0u;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    m += __shfl_xor_sync(0xffffffffu, m, d);
+    c += __shfl_xor_sync(0xffffffffu, c, d);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sh[0][warp] = m;
+    sh[1][warp] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tm = 0, tc = 0;
+    for (int w = 0; w < 8; ++w) {
+      tm += sh[0][w];
+      tc += sh[1][w];
+    }
+    if (tm) atomicAdd(&out[0], tm);
+    if (tc) atomicAdd(&out[1], tc);
+  }
+}
+
+// BulkApply (walk_dev.h) with the symbol-count deltas privatised per CTA: the symbols cluster
+// in a few bins, global atomics on them would serialise the whole kernel.
+__global__ void __launch_bounds__(128) k_bulk_apply(BulkApply a, int n) {
+  __shared__ unsigned int sh[3 * 256 + 1];
+  for (int i = threadIdx.x; i < 3 * 256 + 1; i += 128) sh[i] = 0u;
+  __syncthreads();
+  unsigned int* g_hist = a.delta_hist;
+  unsigned int* g_chroma = a.chroma_nz;
+  a.delta_hist = sh;
+  a.chroma_nz = sh + 768;
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j < n) a(j);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * 256; i += 128)
+    if (sh[i]) atomicAdd(&g_hist[i], sh[i]);
+  if (threadIdx.x == 0 && sh[768]) atomicAdd(g_chroma, sh[768]);
+}
+}  // namespace
+#endif
+
+// ---------------------------------------------------------------------------
+// Device-resident half of the selection walk (walk_dev.h).
+void ImageContext::walk_begin() {
+  bind();
+  const size_t B = static_cast<size_t>(g_.nblocks);
+  if (w_cnt_ == nullptr) {
+    w_cnt_ = static_cast<unsigned int*>(dev_alloc(B * sizeof(unsigned int)));
+    owned_.push_back(w_cnt_);
+    w_done_ = static_cast<int*>(dev_alloc(B * sizeof(int)));
+    owned_.push_back(w_done_);
+    w_stamp_ = static_cast<int*>(dev_alloc(B * sizeof(int)));
+    owned_.push_back(w_stamp_);
+    w_touched_ = static_cast<int*>(dev_alloc(B * sizeof(int)));
+    owned_.push_back(w_touched_);
+    w_counters_ = static_cast<unsigned int*>(dev_alloc((4 + 768) * sizeof(unsigned int)));
+    owned_.push_back(w_counters_);
+    w_stats_ = static_cast<unsigned long long*>(dev_alloc(1024 * 2 * sizeof(unsigned long long)));
+    owned_.push_back(w_stats_);
+  }
+  dev_zero(w_cnt_, B * sizeof(unsigned int), s_);
+  dev_zero(w_done_, B * sizeof(int), s_);
+  dev_zero(w_stamp_, B * sizeof(int), s_);
+  dev_zero(d_last_index_, B * sizeof(int), s_);
+  dev_zero(d_max_err_, B * sizeof(float), s_);
+  w_iter_ = 0;
+  pending_touched_ = 0;
+  sel_sorted_ = 0;
+}
+
+void ImageContext::walk_upload_state(const std::vector<int>& last_index, const std::vector<float>& max_err) {
+  h2d(d_last_index_, last_index.data(), sizeof(int) * g_.nblocks, s_);
+  h2d(d_max_err_, max_err.data(), sizeof(float) * g_.nblocks, s_);
+  stream_sync(s_);
+}
+
+void ImageContext::walk_download_state(std::vector<int>* last_index, std::vector<float>* max_err) {
+  last_index->resize(g_.nblocks);
+  max_err->resize(g_.nblocks);
+  d2h(last_index->data(), d_last_index_, sizeof(int) * g_.nblocks, s_);
+  d2h(max_err->data(), d_max_err_, sizeof(float) * g_.nblocks, s_);
+}
+
+void ImageContext::walk_weights(int direction, int radius, double target_distance, bool zero_distmap,
+                                unsigned long long* order_size, unsigned long long* blocks_to_change) {
+  BlockWeights bw;
+  bw.block_max = zero_distmap ? zero_block_max_ : block_max_;
+  bw.weight = weights_;
+  bw.g = g_;
+  bw.direction = direction;
+  bw.radius = radius;
+  bw.target_distance = target_distance;
+  launch_1d(s_, bw, g_.nblocks, "block_weights");
+#if defined(GB200_HOSTSIM)
+  const int lanes = 1024;
+  launch_1d(s_, WalkStatsPartial{d_last_index_, z_cnt_, weights_, direction, g_.nblocks, lanes, w_stats_}, lanes,
+            "walk_stats");
+  unsigned long long part[2 * 1024];
+  d2h(part, w_stats_, sizeof(part), s_);
+  unsigned long long n = 0, c = 0;
+  for (int i = 0; i < lanes; ++i) {
+    n += part[2 * i];
+    c += part[2 * i + 1];
+  }
+  *order_size = n;
+  *blocks_to_change = c;
+#else
+  dev_zero(w_stats_, 2 * sizeof(unsigned long long), s_);
+  note_launch("walk_stats", s_, g_.nblocks);
+  k_walk_stats<<<(g_.nblocks + 255) / 256, 256, 0, s_>>>(d_last_index_, z_cnt_, weights_, direction, g_.nblocks, w_stats_);
+  note_launch_end("walk_stats", s_);
+  unsigned long long tot[2];
+  d2h(tot, w_stats_, sizeof(tot), s_);
+  *order_size = tot[0];
+  *blocks_to_change = tot[1];
+#endif
+}
+
+void ImageContext::download_weights(float* out) { d2h(out, weights_, sizeof(float) * g_.nblocks, s_); }
+
+#if defined(GB200_HOSTSIM)
+void ImageContext::sort_selection(size_t n) {
+  std::vector<std::pair<float, int> > v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(d_sel_val_[i], d_sel_block_[i]);
+  std::stable_sort(v.begin(), v.end(),
+                   [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first < b.first; });
+  for (size_t i = 0; i < n; ++i) {
+    d_sel_val_[i] = v[i].first;
+    d_sel_block_[i] = v[i].second;
+  }
+}
+#else
+namespace {
+// Ascending sort of n (float key, int payload) pairs by one CTA: least-significant-digit
+// radix sort on the order-preserving integer image of the keys, 4 bits per pass, passes in
+// which all keys share the digit skipped.  A thread owns a contiguous chunk of the input, so
+// the scatter is stable.  The selections it sorts are 10^4 .. 10^5 entries.
+__global__ void __launch_bounds__(1024) k_sort_pairs(float* k0, int* v0, float* k1, int* v1, int n) {
+  extern __shared__ unsigned int cnt[];  // [16][1024]
+  __shared__ unsigned int warp_tot[32];
+  __shared__ unsigned int s_or, s_and;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int chunk = (n + 1023) / 1024;
+  const int lo = min(n, t * chunk), hi = min(n, lo + chunk);
+  if (t == 0) {
+    s_or = 0u;
+    s_and = 0xffffffffu;
+  }
+  __syncthreads();
+  {
+    unsigned int o = 0u, a = 0xffffffffu;
+    for (int i = lo; i < hi; ++i) {
+      const unsigned int u = hd_float_sortable(k0[i]);
+      o |= u;
+      a &= u;
+    }
+    atomicOr(&s_or, o);
+    atomicAnd(&s_and, a);
+  }
+  __syncthreads();
+  const unsigned int varying = s_or ^ s_and;
+  float* ka = k0;
+  int* va = v0;
+  float* kb = k1;
+  int* vb = v1;
+  for (int shift = 0; shift < 32; shift += 4) {
+    if (((varying >> shift) & 15u) == 0u) continue;  // uniform
+#pragma unroll
+    for (int d = 0; d < 16; ++d) cnt[d * 1024 + t] = 0u;
+    for (int i = lo; i < hi; ++i) ++cnt[((hd_float_sortable(ka[i]) >> shift) & 15u) * 1024 + t];
+    __syncthreads();
+    // exclusive scan of the 16384 counters in (digit, thread) order; thread t owns [16t, 16t + 16)
+    unsigned int local[16], sum = 0u;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      local[j] = cnt[16 * t + j];
+      sum += local[j];
+    }
+    unsigned int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned int x = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += x;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned int base = 0u;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    unsigned int run = base + incl - sum;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      cnt[16 * t + j] = run;
+      run += local[j];
+    }
+    __syncthreads();
+    for (int i = lo; i < hi; ++i) {
+      const float key = ka[i];
+      const unsigned int pos = cnt[((hd_float_sortable(key) >> shift) & 15u) * 1024 + t]++;
+      kb[pos] = key;
+      vb[pos] = va[i];
+    }
+    __syncthreads();
+    float* tk = ka;
+    ka = kb;
+    kb = tk;
+    int* tv = va;
+    va = vb;
+    vb = tv;
+  }
+  if (ka != k0) {  // odd number of passes: the result sits in the second buffer
+    for (int i = lo; i < hi; ++i) {
+      k0[i] = ka[i];
+      v0[i] = va[i];
+    }
+  }
+}
+// The same for selections that fit in shared memory (up to kSortSmemMax entries): the keys
+// (order-preserving integer image) and 16-bit indices ping-pong between two shared-memory
+// buffers; global memory is read once and written once.
+constexpr int kSortSmemMax = 14336;
+__global__ void __launch_bounds__(1024) k_sort_pairs_smem(float* keys, int* vals, int n) {
+  extern __shared__ unsigned int dyn_sort[];
+  unsigned int* ka = dyn_sort;                                                  // [kSortSmemMax]
+  unsigned int* kb = ka + kSortSmemMax;                                         // [kSortSmemMax]
+  unsigned short* ia = reinterpret_cast<unsigned short*>(kb + kSortSmemMax);   // [kSortSmemMax]
+  unsigned short* ib = ia + kSortSmemMax;                                       // [kSortSmemMax]
+  unsigned short* cnt = ib + kSortSmemMax;                                      // [16][1024]
+  __shared__ unsigned int warp_tot[32];
+  __shared__ unsigned int s_or, s_and;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) {
+    s_or = 0u;
+    s_and = 0xffffffffu;
+  }
+  __syncthreads();
+  {
+    unsigned int o = 0u, a = 0xffffffffu;
+    for (int i = t; i < n; i += 1024) {  // coalesced load
+      const unsigned int u = hd_float_sortable(keys[i]);
+      ka[i] = u;
+      ia[i] = static_cast<unsigned short>(i);
+      o |= u;
+      a &= u;
+    }
+    atomicOr(&s_or, o);
+    atomicAnd(&s_and, a);
+  }
+  __syncthreads();
+  const unsigned int varying = s_or ^ s_and;
+  const int chunk = (n + 1023) / 1024;
+  const int lo = min(n, t * chunk), hi = min(n, lo + chunk);
+  for (int shift = 0; shift < 32; shift += 4) {
+    if (((varying >> shift) & 15u) == 0u) continue;  // uniform
+#pragma unroll
+    for (int d = 0; d < 16; ++d) cnt[d * 1024 + t] = 0;
+    for (int i = lo; i < hi; ++i) ++cnt[((ka[i] >> shift) & 15u) * 1024 + t];
+    __syncthreads();
+    unsigned int local[16], sum = 0u;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      local[j] = cnt[16 * t + j];
+      sum += local[j];
+    }
+    unsigned int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned int x = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += x;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned int base = 0u;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    unsigned int run = base + incl - sum;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      cnt[16 * t + j] = static_cast<unsigned short>(run);
+      run += local[j];
+    }
+    __syncthreads();
+    for (int i = lo; i < hi; ++i) {
+      const unsigned int u = ka[i];
+      const unsigned int pos = cnt[((u >> shift) & 15u) * 1024 + t]++;
+      kb[pos] = u;
+      ib[pos] = ia[i];
+    }
+    __syncthreads();
+    unsigned int* tk = ka;
+    ka = kb;
+    kb = tk;
+    unsigned short* ti = ia;
+    ia = ib;
+    ib = ti;
+  }
+  // gather the payloads through the permutation (read all, then write: in place)
+  int pay[kSortSmemMax / 1024];
+  float key[kSortSmemMax / 1024];
+#pragma unroll
+  for (int r = 0; r < kSortSmemMax / 1024; ++r) {
+    const int i = t + 1024 * r;
+    if (i < n) {
+      pay[r] = vals[ia[i]];
+      key[r] = keys[ia[i]];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSortSmemMax / 1024; ++r) {
+    const int i = t + 1024 * r;
+    if (i < n) {
+      vals[i] = pay[r];
+      keys[i] = key[r];
+    }
+  }
+}
+}  // namespace
+
+void ImageContext::sort_selection(size_t n) {
+  if (n < 2) return;
+  if (n <= kSortSmemMax) {
+    const size_t smem = kSortSmemMax * 12 + 16 * 1024 * sizeof(unsigned short);
+    GB_CUDA(cudaFuncSetAttribute(k_sort_pairs_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    note_launch("sort_pairs", s_, static_cast<double>(n));
+    k_sort_pairs_smem<<<1, 1024, smem, s_>>>(d_sel_val_, d_sel_block_, static_cast<int>(n));
+    note_launch_end("sort_pairs", s_);
+    return;
+  }
+  if (n > sel2_cap_) {
+    if (d_sel_val2_) { dev_free(d_sel_val2_); d_sel_val2_ = nullptr; }
+    if (d_sel_block2_) { dev_free(d_sel_block2_); d_sel_block2_ = nullptr; }
+    sel2_cap_ = n + n / 2 + 1024;
+    d_sel_val2_ = static_cast<float*>(dev_alloc(sel2_cap_ * sizeof(float)));
+    d_sel_block2_ = static_cast<int*>(dev_alloc(sel2_cap_ * sizeof(int)));
+  }
+  const size_t smem = 16 * 1024 * sizeof(unsigned int);
+  GB_CUDA(cudaFuncSetAttribute(k_sort_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  note_launch("sort_pairs", s_, static_cast<double>(n));
+  k_sort_pairs<<<1, 1024, smem, s_>>>(d_sel_val_, d_sel_block_, d_sel_val2_, d_sel_block2_, static_cast<int>(n));
+  note_launch_end("sort_pairs", s_);
+}
+#endif
+
+size_t ImageContext::walk_select_sorted(int direction, size_t want, size_t* total) {
+  OrderSelectState got;
+  select_keys(direction, want, &got);
+  *total = got.total;
+  sel_sorted_ = got.kept;
+  sort_selection(sel_sorted_);
+  return sel_sorted_;
+}
+
+void ImageContext::walk_fetch_sorted(size_t first, size_t n, float* val, int* block) {
+  if (first + n > sel_sorted_) throw std::runtime_error("walk_fetch_sorted: range outside the selection");
+  if (n == 0) return;
+  d2h(val, d_sel_val_ + first, n * sizeof(float), s_);
+  d2h(block, d_sel_block_ + first, n * sizeof(int), s_);
+}
+
+void ImageContext::walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, const int* host_blocks) {
+  const int* entry_blocks = d_sel_block_;
+  if (host_blocks != nullptr) {
+    if (nbulk > w_acap_) {
+      stream_sync(s_);
+      if (w_ablocks_) { dev_free(w_ablocks_); w_ablocks_ = nullptr; }
+      w_acap_ = nbulk + nbulk / 2 + 4096;
+      w_ablocks_ = static_cast<int*>(dev_alloc(w_acap_ * sizeof(int)));
+    }
+    if (nbulk) h2d(w_ablocks_, host_blocks, nbulk * sizeof(int), s_);
+    entry_blocks = w_ablocks_;
+  } else if (nbulk > sel_sorted_) {
+    throw std::runtime_error("walk_bulk_apply: bulk larger than the selection");
+  }
+  if (nbulk > w_log_cap_) {
+    stream_sync(s_);
+    if (w_log_index_) { dev_free(w_log_index_); w_log_index_ = nullptr; }
+    if (w_log_old_) { dev_free(w_log_old_); w_log_old_ = nullptr; }
+    w_log_cap_ = nbulk + nbulk / 2 + 4096;
+    w_log_index_ = static_cast<int*>(dev_alloc(w_log_cap_ * sizeof(int)));
+    w_log_old_ = static_cast<int16_t*>(dev_alloc(w_log_cap_ * sizeof(int16_t)));
+  }
+  ++w_iter_;
+  dev_zero(w_counters_, (4 + 768) * sizeof(unsigned int), s_);
+  unsigned int host_counters[4 + 768];
+  memset(host_counters, 0, sizeof(host_counters));
+  if (nbulk > 0) {
+    launch_1d(s_, BulkCount{entry_blocks, w_cnt_, w_touched_, w_counters_}, static_cast<int>(nbulk), "walk_bulk_count");
+    unsigned int n_touched = 0;
+    d2h(&n_touched, w_counters_, sizeof(unsigned int), s_);
+    BulkApply a;
+    a.s.orig = d_orig_;
+    a.s.cand = d_cand_;
+    a.s.q = d_q_;
+    a.s.zz2nat = t_.zigzag;
+    a.s.nat2zz = t_.nat2zz;
+    a.s.z_idx = z_idx_;
+    a.s.last_index = d_last_index_;
+    a.s.nblocks = g_.nblocks;
+    a.touched = w_touched_;
+    a.cnt = w_cnt_;
+    a.done = w_done_;
+    a.stamp = w_stamp_;
+    a.iter = w_iter_;
+    a.direction = direction;
+    a.delta_hist = w_counters_ + 4;
+    a.chroma_nz = w_counters_ + 2;
+    a.log_index = w_log_index_;
+    a.log_old = w_log_old_;
+    a.n_log = w_counters_ + 1;
+#if defined(GB200_HOSTSIM)
+    launch_1d(s_, a, static_cast<int>(n_touched), "walk_bulk_apply");
+#else
+    note_launch("walk_bulk_apply", s_, n_touched);
+    k_bulk_apply<<<(n_touched + 127) / 128, 128, 0, s_>>>(a, static_cast<int>(n_touched));
+    note_launch_end("walk_bulk_apply", s_);
+#endif
+    d2h(host_counters, w_counters_, sizeof(host_counters), s_);
+  }
+  r->touched = static_cast<int>(host_counters[0]);
+  r->logged = static_cast<int>(host_counters[1]);
+  r->chroma_delta = static_cast<int>(host_counters[2]);
+  for (int c = 0; c < 3; ++c)
+    for (int i = 0; i < 256; ++i) r->delta_hist[c][i] = static_cast<int>(host_counters[4 + 256 * c + i]);
+  w_last_touched_ = r->touched;
+  w_last_logged_ = r->logged;
+  pending_touched_ = r->touched;
+}
+
+void ImageContext::walk_bulk_undo(int direction) {
+  if (w_last_logged_ > 0)
+    launch_1d(s_, BulkUndoCoeffs{w_log_index_, w_log_old_, d_cand_}, w_last_logged_, "walk_bulk_undo");
+  if (w_last_touched_ > 0)
+    launch_1d(s_, BulkUndoCursors{w_touched_, w_done_, d_last_index_, direction}, w_last_touched_, "walk_bulk_undo");
+  w_last_logged_ = 0;
+  w_last_touched_ = 0;
+  pending_touched_ = 0;
+}
+
+void ImageContext::walk_gather(const std::vector<int>& blocks, std::vector<int16_t>* coeffs, std::vector<int>* cursor,
+                               std::vector<int>* in_bulk) {
+  const size_t n = blocks.size();
+  coeffs->resize(n * 192);
+  cursor->resize(n);
+  in_bulk->resize(n);
+  if (n == 0) return;
+  if (n > w_gcap_) {
+    stream_sync(s_);
+    if (w_gblocks_) { dev_free(w_gblocks_); w_gblocks_ = nullptr; }
+    if (w_gcoeffs_) { dev_free(w_gcoeffs_); w_gcoeffs_ = nullptr; }
+    if (w_gcursor_) { dev_free(w_gcursor_); w_gcursor_ = nullptr; }
+    if (w_ginbulk_) { dev_free(w_ginbulk_); w_ginbulk_ = nullptr; }
+    w_gcap_ = n + n / 2 + 1024;
+    w_gblocks_ = static_cast<int*>(dev_alloc(w_gcap_ * sizeof(int)));
+    w_gcoeffs_ = static_cast<int16_t*>(dev_alloc(w_gcap_ * 192 * sizeof(int16_t)));
+    w_gcursor_ = static_cast<int*>(dev_alloc(w_gcap_ * sizeof(int)));
+    w_ginbulk_ = static_cast<int*>(dev_alloc(w_gcap_ * sizeof(int)));
+  }
+  h2d(w_gblocks_, blocks.data(), n * sizeof(int), s_);
+  launch_1d(s_, GatherBlockState{w_gblocks_, d_cand_, d_last_index_, w_stamp_, w_iter_, g_.nblocks, w_gcoeffs_, w_gcursor_,
+                                 w_ginbulk_},
+            static_cast<int>(3 * n), "walk_gather");
+  d2h(coeffs->data(), w_gcoeffs_, n * 192 * sizeof(int16_t), s_);
+  d2h(cursor->data(), w_gcursor_, n * sizeof(int), s_);
+  d2h(in_bulk->data(), w_ginbulk_, n * sizeof(int), s_);
+}
+
+void ImageContext::walk_advance(const std::vector<int>& blocks, int direction) {
+  const size_t n = blocks.size();
+  if (n == 0) return;
+  if (n > w_acap_) {
+    stream_sync(s_);
+    if (w_ablocks_) { dev_free(w_ablocks_); w_ablocks_ = nullptr; }
+    w_acap_ = n + n / 2 + 4096;
+    w_ablocks_ = static_cast<int*>(dev_alloc(w_acap_ * sizeof(int)));
+  }
+  h2d(w_ablocks_, blocks.data(), n * sizeof(int), s_);
+  launch_1d(s_, AdvanceCursors{w_ablocks_, d_last_index_, direction}, static_cast<int>(n), "walk_advance");
+  stream_sync(s_);  // the host vector may go away
+}
+
+void ImageContext::walk_add_max_err(float val_threshold, int direction) {
+  launch_1d(s_, AddMaxErr{d_max_err_, weights_, val_threshold, direction}, g_.nblocks, "walk_add_max_err");
 }
 
 // ---------------------------------------------------------------------------
@@ -1080,6 +1611,11 @@ size_t ImageContext::exact_order_prefix(int direction, const std::vector<int>& l
                                         std::vector<std::pair<int, float> >* out, size_t* order_size) {
   h2d(d_last_index_, last_index.data(), sizeof(int) * g_.nblocks, s_);
   h2d(d_max_err_, max_err.data(), sizeof(float) * g_.nblocks, s_);
+  return exact_order_prefix_resident(direction, want, out, order_size);
+}
+
+size_t ImageContext::exact_order_prefix_resident(int direction, size_t want, std::vector<std::pair<int, float> >* out,
+                                                 size_t* order_size) {
   order_scratch(std::max<size_t>(num_entries_, static_cast<size_t>(g_.nblocks)) + 16);
   unsigned int* count = x_u32_;
   unsigned int* offset = x_u32_ + x_cap_;

@@ -21,6 +21,7 @@ struct KernelStat {
 };
 
 struct OrderItem;
+struct OrderSelectState;
 
 class ImageContext {
  public:
@@ -37,6 +38,9 @@ class ImageContext {
   // first k_end entries exactly as std::sort would leave them (exact_sort.h semantics).
   size_t exact_order_prefix(int direction, const std::vector<int>& last_index, const std::vector<float>& max_err,
                             size_t want, std::vector<std::pair<int, float> >* out, size_t* order_size);
+  // the same on the resident cursors / max errors (device half of the walk, walk_dev.h)
+  size_t exact_order_prefix_resident(int direction, size_t want, std::vector<std::pair<int, float> >* out,
+                                     size_t* order_size);
   // test hook: the same replay on caller-provided items
   size_t debug_device_partial_sort(std::pair<int, float>* items, size_t n, size_t want);
   // Metric only (stand-alone butteraugli, scope row f4): the first image as linear RGB
@@ -92,6 +96,32 @@ class ImageContext {
   size_t order_smallest(int direction, const std::vector<int>& last_index, const std::vector<float>& max_err,
                         size_t k, std::vector<float>* val, std::vector<int>* block);
 
+  // ---- device-resident half of the selection walk (walk_dev.h) -----------------------
+  // Candidate cursors (last_index) and max_block_error live on the device between
+  // iterations; the host mirrors are refreshed only when an iteration takes the host path.
+  void walk_begin();
+  void walk_upload_state(const std::vector<int>& last_index, const std::vector<float>& max_err);
+  void walk_download_state(std::vector<int>* last_index, std::vector<float>* max_err);
+  // a15 without the download, plus the size of the order the weights imply
+  void walk_weights(int direction, int radius, double target_distance, bool zero_distmap,
+                    unsigned long long* order_size, unsigned long long* blocks_to_change);
+  void download_weights(float* out);
+  // at least the `want` smallest keys of the order, sorted ascending, resident; -> how many
+  size_t walk_select_sorted(int direction, size_t want, size_t* total);
+  void walk_fetch_sorted(size_t first, size_t n, float* val, int* block);
+  struct BulkResult {
+    int touched, logged, chroma_delta;
+    int delta_hist[3][256];
+  };
+  // consumes entries [0, nbulk) of the sorted selection on the device; host_blocks != nullptr:
+  // the entries' blocks come from the host instead (prefix of the reference-ordered sort)
+  void walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, const int* host_blocks = nullptr);
+  void walk_bulk_undo(int direction);
+  void walk_gather(const std::vector<int>& blocks, std::vector<int16_t>* coeffs, std::vector<int>* cursor,
+                   std::vector<int>* in_bulk);
+  void walk_advance(const std::vector<int>& blocks, int direction);
+  void walk_add_max_err(float val_threshold, int direction);
+
   // a11 on the device.  Symbol histograms of the candidate (raw counts):
   // hist[6][257] = dc0 dc1 dc2 ac0 ac1 ac2; *chroma_nonzero tells whether the
   // saved JPEG has 3 components (g/output_image.cc:357).
@@ -129,6 +159,32 @@ class ImageContext {
   void download_planes(const float* src, float* packed, int n);
   float* planes(int n);
 
+  // device-resident walk state (walk_dev.h)
+  unsigned int* w_cnt_ = nullptr;       // [nblocks]
+  int* w_done_ = nullptr;               // [nblocks]
+  int* w_stamp_ = nullptr;              // [nblocks]
+  int* w_touched_ = nullptr;            // [nblocks]
+  unsigned int* w_counters_ = nullptr;  // n_touched, n_log, chroma delta, pad, delta_hist[768]
+  unsigned long long* w_stats_ = nullptr;  // [1024][2]
+  int* w_log_index_ = nullptr;
+  int16_t* w_log_old_ = nullptr;
+  size_t w_log_cap_ = 0;
+  int* w_gblocks_ = nullptr;
+  int16_t* w_gcoeffs_ = nullptr;
+  int* w_gcursor_ = nullptr;
+  int* w_ginbulk_ = nullptr;
+  size_t w_gcap_ = 0;
+  int* w_ablocks_ = nullptr;
+  size_t w_acap_ = 0;
+  float* d_sel_val2_ = nullptr;
+  int* d_sel_block2_ = nullptr;
+  size_t sel2_cap_ = 0;
+  size_t sel_sorted_ = 0;    // entries of the sorted resident selection
+  int w_iter_ = 0;
+  int w_last_touched_ = 0, w_last_logged_ = 0;
+  int pending_touched_ = 0;  // blocks the last bulk changed and compare() has not rendered yet
+  void select_keys(int direction, size_t k, OrderSelectState* got);
+  void sort_selection(size_t n);
   // TMA-staged fused Compare chain (fused_kernels.cuh; CUDA build only)
   struct Fused;
   Fused* fused_ = nullptr;

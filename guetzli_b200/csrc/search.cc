@@ -233,8 +233,7 @@ class Search {
     SymbolHistogram dc_h[3], ac_h[3];
     int ncomp;
     if (host_ac != nullptr) {
-      const size_t per = static_cast<size_t>(img_.nblocks) * 64;
-      for (size_t i = per; i < 3 * per && !chroma; ++i) chroma = cand_[i] != 0;
+      chroma = chroma_nz_ > 0;  // kept incrementally: the host mirror of the candidate may be stale
       ncomp = chroma ? 3 : 1;
       for (int c = 0; c < ncomp; ++c) {
         for (int i = 0; i < 256; ++i) dc_h[c].counts[i] = 2 * sfm_dc_hist_[c][i];
@@ -453,20 +452,30 @@ class Search {
   // complete reference-ordered sort.
   // `order` may be only a prefix of the complete sorted order of n_total entries; the
   // caller must then discard the outcome unless the walk stopped inside the prefix.
+  // `order` may also be a slice of the sorted order that starts at global position `base`
+  // (device half of the walk, walk_dev.h): entries [start, end) of the slice are consumed,
+  // the others only serve the tie analysis; fresh = false continues an iteration (edit lists
+  // and changed-block flags are kept, changed0 blocks were already counted).
   WalkOutcome walk(Sfm& m, const std::vector<std::pair<int, float> >& order, size_t n_total, int direction,
-                   int min_coeffs_to_change, double min_size_delta, int prev_size, bool check_ties) {
+                   int min_coeffs_to_change, double min_size_delta, int prev_size, bool check_ties, size_t base = 0,
+                   size_t start = 0, size_t end = static_cast<size_t>(-1), bool fresh = true, size_t changed0 = 0) {
     const size_t per = static_cast<size_t>(img_.nblocks) * 64;
     const int16_t* orig_ = ctx_->orig_coeffs().data();
     WalkOutcome out;
     out.est_jpg_size = prev_size;
-    std::fill(m.block_changed.begin(), m.block_changed.end(), 0);
-    m.edit_index.clear();
-    m.edit_value.clear();
-    m.edit_old.clear();
-    int changed_coeffs = 0;
+    out.changed_blocks = changed0;
+    out.consumed = base + start;
+    if (fresh) {
+      std::fill(m.block_changed.begin(), m.block_changed.end(), 0);
+      m.edit_index.clear();
+      m.edit_value.clear();
+      m.edit_old.clear();
+    }
     const size_t n_avail = order.size();
     const size_t n_order = n_total;
-    for (size_t i = 0; i < n_avail; ++i) {
+    const size_t i_end = std::min(end, n_avail);
+    for (size_t i = start; i < i_end; ++i) {
+      const size_t gi = base + i;  // position in the complete order
       // every entry touches a different block: hide the cache misses
       if (i + 12 < n_avail) {
         const int pb = order[i + 12].first;
@@ -493,9 +502,9 @@ class Search {
       }
       const int block_ix = order[i].first;
       const bool refresh_here =
-          (i % 10 == 0) && (static_cast<long long>(i) + 9 >= min_coeffs_to_change || n_order - 1 <= i + 9);
-      const bool can_test = changed_coeffs + 1 > min_coeffs_to_change;
-      const bool eval_here = can_test || i + 1 == n_order;
+          (gi % 10 == 0) && (static_cast<long long>(gi) + 9 >= min_coeffs_to_change || n_order - 1 <= gi + 9);
+      const bool can_test = static_cast<long long>(gi) + 1 > min_coeffs_to_change;  // changed_coeffs == gi
+      const bool eval_here = can_test || gi + 1 == n_order;
       // does a run of equal keys that contains two different blocks cross the boundary
       // i | i+1 ?  (then the set of entries applied so far depends on the arrangement)
       bool straddle = false, pair_only = false;
@@ -507,8 +516,9 @@ class Search {
         while (hi + 1 < n_avail && !(key < order[hi + 1].second)) ++hi;
         for (size_t j = lo + 1; j <= hi; ++j)
           if (order[j].first != order[lo].first) straddle = true;
-        // the run may continue beyond the fetched prefix
-        if (hi + 1 == n_avail && n_avail < n_order) straddle = true;
+        // the run may continue beyond the fetched prefix, or begin before the fetched slice
+        if (hi + 1 == n_avail && base + n_avail < n_order) straddle = true;
+        if (lo == 0 && base > 0) straddle = true;
         pair_only = straddle && lo == i && hi == i + 1;
       }
       int alt_est = 0;
@@ -549,8 +559,7 @@ class Search {
         ++out.changed_blocks;
       }
       out.val_threshold = order[i].second;
-      ++changed_coeffs;
-      out.consumed = i + 1;
+      out.consumed = gi + 1;
       if (refresh_here) m.ac_histogram_size = static_cast<int>(compute_entropy_codes(m.ac_h, m.ac_depths.data()));
       if (eval_here) {
         out.est_jpg_size = m.header_size + m.dc_size + m.ac_histogram_size +
@@ -582,6 +591,137 @@ class Search {
     for (int c = 0; c < 3; ++c) m.ac_h[c] = saved_h[c];
     m.ac_histogram_size = saved_hist_size;
     m.ac_depths = saved_depths;
+  }
+
+  // One "down" iteration with the device half of the walk (walk_dev.h).  exact: the order is
+  // the prefix of the reference-ordered std::sort (device replay, order_exact.h), else the
+  // radix-selected smallest keys sorted on the device (tie analysis on).
+  // -> 1 done (edits of the host window in m.edit_*), 0 ambiguous, -1 not applicable / ran
+  // out of entries; in the last two cases everything is as before the call.
+  int device_walk(Sfm& m, bool exact, size_t order_size, int direction, int min_coeffs_to_change, double min_size_delta,
+                  int prev_size, size_t last_consumed, WalkOutcome* result) {
+    const size_t i0 = static_cast<size_t>(10 * (min_coeffs_to_change / 10));
+    if (i0 < 256 || order_size < 2 * i0 + 4096) return -1;
+    Clock::time_point t0 = Clock::now();
+    std::vector<std::pair<int, float> >& order = order_buf_;
+    size_t base = 0, n_slice = 0, usable_end = 0;
+    std::vector<int> bulk_blocks;
+    if (exact) {
+      size_t want = std::max(last_consumed, i0) + std::max<size_t>(i0 / 8, 1024), dev_total = 0;
+      if (want > order_size) want = order_size;
+      const size_t k_end = ctx_->exact_order_prefix_resident(direction, want, &order, &dev_total);
+      if (dev_total != order_size) throw std::runtime_error("exact_order_prefix: entry count mismatch");
+      if (k_end < i0 + 16) return -1;
+      n_slice = k_end;
+      usable_end = k_end;
+      bulk_blocks.resize(i0);
+      for (size_t i = 0; i < i0; ++i) bulk_blocks[i] = order[i].first;
+    } else {
+      const size_t want = std::min(order_size, std::max(last_consumed, i0) + std::max<size_t>(i0 / 8, 1024));
+      size_t total = 0;
+      const size_t kept = ctx_->walk_select_sorted(direction, want, &total);
+      if (total != order_size) throw std::runtime_error("walk_select_sorted: entry count mismatch");
+      if (kept < i0 + 64 || kept >= order_size) {
+        st_->ms_sort += ms_since(t0);
+        return -1;
+      }
+      const size_t pre = std::min<size_t>(i0, 64);
+      base = i0 - pre;
+      n_slice = kept - base;
+      usable_end = n_slice;
+      std::vector<float> val(n_slice);
+      std::vector<int> blk(n_slice);
+      ctx_->walk_fetch_sorted(base, n_slice, val.data(), blk.data());
+      order.resize(n_slice);
+      for (size_t i = 0; i < n_slice; ++i) order[i] = std::make_pair(blk[i], val[i]);
+    }
+    ImageContext::BulkResult bulk;
+    ctx_->walk_bulk_apply(direction, i0, &bulk, exact ? bulk_blocks.data() : nullptr);
+    st_->ms_sort += ms_since(t0);
+    Clock::time_point tw = Clock::now();
+    SymbolHistogram saved_h[3] = {m.ac_h[0], m.ac_h[1], m.ac_h[2]};
+    const int saved_hist_size = m.ac_histogram_size;
+    const std::vector<uint8_t> saved_depths = m.ac_depths;
+    for (int c = 0; c < 3; ++c)
+      for (int i = 0; i < 256; ++i) m.ac_h[c].counts[i] += static_cast<uint32_t>(2 * bulk.delta_hist[c][i]);
+    mirror_valid_ = false;
+    std::fill(m.block_changed.begin(), m.block_changed.end(), 0);
+    m.edit_index.clear();
+    m.edit_value.clear();
+    m.edit_old.clear();
+    for (size_t i = 0; i < fetched_list_.size(); ++i) fetched_[fetched_list_[i]] = 0;
+    fetched_list_.clear();
+    if (fetched_.size() != static_cast<size_t>(img_.nblocks)) fetched_.assign(img_.nblocks, 0);
+    size_t pos = i0 - base, chunk = 512;
+    size_t changed = static_cast<size_t>(bulk.touched);
+    WalkOutcome out;
+    bool ok = true;
+    const size_t per = static_cast<size_t>(img_.nblocks) * 64;
+    while (true) {
+      const size_t end = std::min(usable_end, pos + chunk);
+      // state of the blocks of this chunk that the host does not hold yet
+      std::vector<int> need;
+      for (size_t i = pos; i < end; ++i) {
+        const int b = order[i].first;
+        if (!fetched_[b]) {
+          fetched_[b] = 1;
+          fetched_list_.push_back(b);
+          need.push_back(b);
+        }
+      }
+      std::vector<int16_t> gc;
+      std::vector<int> gcur, gin;
+      ctx_->walk_gather(need, &gc, &gcur, &gin);
+      for (size_t e = 0; e < need.size(); ++e) {
+        const int b = need[e];
+        for (int c = 0; c < 3; ++c)
+          memcpy(&cand_[c * per + static_cast<size_t>(b) * 64], &gc[(e * 3 + c) * 64], 64 * sizeof(int16_t));
+        m.last_indexes[b] = gcur[e];
+        if (gin[e]) m.block_changed[b] = 1;  // already counted among the bulk's blocks
+      }
+      out = walk(m, order, order_size, direction, min_coeffs_to_change, min_size_delta, prev_size, !exact, base, pos, end,
+                 false, changed);
+      if (out.ambiguous) {
+        ok = false;
+        break;
+      }
+      changed = out.changed_blocks;
+      if (out.stopped) break;
+      pos = end;
+      if (pos >= usable_end) {  // the entries ran out before the walk stopped
+        ok = base + usable_end == order_size;
+        break;
+      }
+      chunk *= 4;
+    }
+    // a stop on the very last fetched entry cannot be told from running out of them
+    if (ok && out.stopped && base + usable_end < order_size && out.consumed >= base + usable_end) ok = false;
+    st_->ms_walk += ms_since(tw);
+    if (ok) {
+      ++device_walks_;
+      // device: cursors of the window's entries, the new max errors (the window's coefficient
+      // edits follow with the common scatter)
+      std::vector<int> consumed_blocks;
+      for (size_t gi = i0; gi < out.consumed; ++gi) consumed_blocks.push_back(order[gi - base].first);
+      ctx_->walk_advance(consumed_blocks, direction);
+      ctx_->walk_add_max_err(out.val_threshold, direction);
+      chroma_nz_ += bulk.chroma_delta;
+      device_done_ = true;
+      *result = out;
+      return 1;
+    }
+    if (out.ambiguous) {
+      ++tie_fallbacks_;
+      ++tie_why_[out.why];
+    }
+    ctx_->walk_bulk_undo(direction);
+    for (int c = 0; c < 3; ++c) m.ac_h[c] = saved_h[c];
+    m.ac_histogram_size = saved_hist_size;
+    m.ac_depths = saved_depths;
+    m.edit_index.clear();
+    m.edit_value.clear();
+    m.edit_old.clear();
+    return out.ambiguous ? 0 : -1;
   }
 
   void select_frequency_masking(const double target_mul) {
@@ -624,6 +764,21 @@ class Search {
     m.block_changed.assign(num_blocks, 0);
     std::vector<float> block_weight(num_blocks);
     size_t last_consumed = 0;
+    // The candidate cursors and max errors also live on the device (walk_dev.h); the host
+    // copies above (and cand_) are a mirror that iterations on the device path leave stale.
+    ctx_->walk_begin();
+    mirror_valid_ = true;
+    {
+      const size_t per = static_cast<size_t>(img_.nblocks) * 64;
+      chroma_nz_ = 0;
+      for (size_t i = per; i < 3 * per; ++i) chroma_nz_ += cand_[i] != 0 ? 1 : 0;
+    }
+    fetched_.assign(num_blocks, 0);
+    fetched_list_.clear();
+    static const bool kDeviceWalk = [] {
+      const char* e = getenv("GB200_WALK");  // GB200_WALK=host keeps every iteration on the host path
+      return !(e != nullptr && e[0] == 'h');
+    }();
 
     bool first_up_iter = true;
     const int directions[2] = {1, -1};
@@ -634,25 +789,15 @@ class Search {
         size_t order_size = 0;
         int blocks_to_change = 0;
         for (int rblock = 1; rblock <= 4; ++rblock) {
-          ctx_->block_weights(direction, rblock, params_.butteraugli_target * target_mul, first_up_iter,
-                              block_weight.data());
-          order_size = 0;
-          blocks_to_change = 0;
-          for (int b = 0; b < num_blocks; ++b) {
-            if (block_weight[b] == 0) continue;
-            const int li = m.last_indexes[b];
-            const int nc = m.offsets[b + 1] - m.offsets[b];
-            if (direction > 0) {
-              order_size += li < nc ? nc - li : 0;
-              blocks_to_change += (li < nc ? 1 : 0);
-            } else {
-              order_size += li > 0 ? li : 0;
-              blocks_to_change += (li > 0 ? 1 : 0);
-            }
-          }
+          unsigned long long n_entries = 0, n_blocks = 0;
+          ctx_->walk_weights(direction, rblock, params_.butteraugli_target * target_mul, first_up_iter, &n_entries,
+                             &n_blocks);
+          order_size = static_cast<size_t>(n_entries);
+          blocks_to_change = static_cast<int>(n_blocks);
           if (order_size != 0) break;
         }
         if (order_size == 0) break;
+        bool have_weights = false;  // block_weight[] is downloaded only by the host paths
 
         double rel_size_delta = direction > 0 ? 0.01 : 0.0005;
         if (direction > 0 && distance_ok(1.0)) rel_size_delta = 0.05;
@@ -664,11 +809,45 @@ class Search {
         order.clear();
         WalkOutcome out;
         bool done = false;
+        device_done_ = false;
+        // Device path (walk_dev.h): the entries before the first point at which the walk looks
+        // at its state are applied on the device as a set; the host runs the sequential loop
+        // only from there on, with the state of just the blocks involved.  First on the
+        // radix-selected order (equal keys in arbitrary arrangement, tie analysis on); if that
+        // is ambiguous, on the prefix of the reference-ordered sort (device replay of std::sort).
+        bool skip_partial = false;
+        if (kDeviceWalk && direction < 0 && order_size > 16384) {
+          const int r = device_walk(m, false, order_size, direction, min_coeffs_to_change, min_size_delta, prev_size,
+                                    last_consumed, &out);
+          if (r == 1) {
+            done = true;
+            ++st_->order_partial;
+          } else if (r == 0) {
+            skip_partial = true;  // the host's partial order would stumble over the same equal keys
+            const int r2 = device_walk(m, true, order_size, direction, min_coeffs_to_change, min_size_delta, prev_size,
+                                       last_consumed, &out);
+            if (r2 == 1) {
+              done = true;
+              ++st_->order_exact;
+            }
+          }
+        }
+        if (!done) {
+          // host paths: they work on the host mirror of the candidate and of the cursors
+          if (!mirror_valid_) {
+            ctx_->download_candidate(cand_.data());
+            ctx_->walk_download_state(&m.last_indexes, &m.max_block_error);
+            mirror_valid_ = true;
+          }
+          ctx_->download_weights(block_weight.data());
+          have_weights = true;
+        }
+        const bool device_done = device_done_;
         // Fast path ("down" iterations consume a tiny prefix of the order): fetch only
         // the smallest keys from the device, sort those, and fall back to the complete
         // reference-ordered sort whenever the result could depend on how std::sort
         // places equal keys of different blocks, or the prefix runs out.
-        if (direction < 0 && order_size > 16384) {
+        if (!done && !skip_partial && direction < 0 && order_size > 16384) {
           // the walk usually stops right after min_coeffs_to_change entries
           size_t want = std::max<size_t>(last_consumed, static_cast<size_t>(min_coeffs_to_change)) * 5 / 4 + 512;
           while (!done && want < order_size / 2) {
@@ -815,8 +994,19 @@ class Search {
         last_consumed = out.consumed;
         order.clear();
 
-        for (int i = 0; i < num_blocks; ++i)
-          m.max_block_error[i] += block_weight[i] * out.val_threshold * direction;
+        if (!device_done) {
+          if (!have_weights) throw std::runtime_error("host path without block weights");
+          for (int i = 0; i < num_blocks; ++i)
+            m.max_block_error[i] += block_weight[i] * out.val_threshold * direction;
+          // the device copies of the cursors and max errors follow the host's
+          ctx_->walk_upload_state(m.last_indexes, m.max_block_error);
+        }
+        {
+          const size_t per = static_cast<size_t>(img_.nblocks) * 64;
+          for (size_t i = 0; i < m.edit_index.size(); ++i)
+            if (static_cast<size_t>(m.edit_index[i]) >= per)
+              chroma_nz_ += (m.edit_value[i] != 0 ? 1 : 0) - (m.edit_old[i] != 0 ? 1 : 0);
+        }
 
         ++st_->iterations;
         if (direction > 0) ++st_->iterations_up; else ++st_->iterations_down;
@@ -831,6 +1021,8 @@ class Search {
         prev_size = out.est_jpg_size;
       }
     }
+    if (getenv("GB200_TIE_DEBUG"))
+      fprintf(stderr, "device walks %d; ", device_walks_);
     if (getenv("GB200_TIE_DEBUG"))
       fprintf(stderr, "tie fallbacks %d: run-at-refresh %d, run-at-test %d, pair-at-refresh %d, pair-untestable %d, pair-decides %d; exact %d partial %d\n",
               tie_fallbacks_, tie_why_[1], tie_why_[2], tie_why_[3], tie_why_[4], tie_why_[5], st_->order_exact,
@@ -856,6 +1048,12 @@ class Search {
   size_t scan_bytes_ = 0;
   std::vector<std::pair<int, float> > order_buf_;
   int device_order_checked_ = 0;
+  int device_walks_ = 0;
+  bool device_done_ = false;   // the current iteration took the device path
+  std::vector<char> fetched_;  // blocks whose state the host holds for the current iteration
+  std::vector<int> fetched_list_;
+  bool mirror_valid_ = true;   // cand_ / last_indexes / max_block_error equal the device's
+  long long chroma_nz_ = 0;    // nonzero chroma coefficients of the candidate
   int tie_fallbacks_ = 0;
   int tie_why_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double dbg_ms_[4] = {0, 0, 0, 0};   // GB200_TIE_DEBUG: device top-K fetch, exact-order build

@@ -1,0 +1,221 @@
+// Device-resident half of the selection walk (a16, g/processor.cc:611-779).
+//
+// An iteration of SelectFrequencyMasking consumes the first N entries of a global
+// order of (block, key) pairs; consuming an entry of block b flips that block's next
+// candidate coefficient.  The walk only LOOKS at its state (entropy-code refresh,
+// stop test) from entry i0 = the first multiple of 10 with i0 + 9 >= min_coeffs_to_change
+// on; before that it is a pure fold over a SET of entries, and the result of a fold
+// over a set does not depend on the order inside the set.  So:
+//
+//   bulk    entries [0, i0) of the sorted order are applied here, on the device, one
+//           thread per touched block (a block's own entries are consumed in its
+//           candidate order, exactly like the sequential walk would), producing the
+//           AC symbol histogram delta, the chroma-nonzero delta and an undo log;
+//   window  the entries from i0 on go to the host, which runs the reference's sequential
+//           loop (Search::walk) on them with the state of just the blocks involved.
+//
+// All integer work; every function mirrors its host counterpart in search.cc / jpeg_out.cc
+// (plan_edit, ac_symbols_of_range) and is run by the CPU port through the same functors.
+#pragma once
+#include "hd.h"
+#include "jpeg_dev.h"
+#include "jpeg_math.h"
+
+namespace gb200 {
+
+// entries / blocks of the order of one direction, summed by `lanes` lanes
+struct WalkStatsPartial {
+  const int* last_index;
+  const int* z_cnt;
+  const float* weight;
+  int direction, nblocks, lanes;
+  unsigned long long* out;  // [lanes][2]: entries, blocks with entries
+  GB_HD void operator()(int i) const {
+    unsigned long long n = 0, c = 0;
+    for (int b = i; b < nblocks; b += lanes) {
+      if (weight[b] == 0) continue;
+      const int li = last_index[b], nc = z_cnt[b];
+      const int m = direction > 0 ? (li < nc ? nc - li : 0) : (li > 0 ? li : 0);
+      n += static_cast<unsigned long long>(m);
+      c += m > 0 ? 1u : 0u;
+    }
+    out[2 * i] = n;
+    out[2 * i + 1] = c;
+  }
+};
+
+// how many of the first `n` sorted entries belong to each block; first toucher lists the block
+struct BulkCount {
+  const int* sel_block;
+  unsigned int* cnt;       // [nblocks], zero on entry
+  int* touched;            // [nblocks]
+  unsigned int* n_touched;
+  GB_HD void operator()(int i) const {
+    const int b = sel_block[i];
+    if (hd_atomic_add(&cnt[b], 1u) == 0u) touched[hd_atomic_add(n_touched, 1u)] = b;
+  }
+};
+
+struct WalkState {
+  const int16_t* orig;     // [3][nblocks][64]
+  int16_t* cand;
+  const int* q;            // [192]
+  const int* zz2nat;       // [64]
+  const int* nat2zz;       // [64]
+  const uint8_t* z_idx;    // [nblocks][192]
+  int* last_index;         // [nblocks]
+  int nblocks;
+};
+
+// AC symbols of zig-zag positions (a, b] of a block, weight +-1 into hist[256] (ac_symbols_of_range)
+GB_HD void dev_ac_symbols_of_range(const int16_t* dq, const int* q, const int* zz, int a, int b, unsigned int weight,
+                                   unsigned int* hist) {
+  int run = 0;
+  const int last = b < 64 ? b : 63;
+  for (int k = a + 1; k <= last; ++k) {
+    const int nat = zz[k];
+    const int coeff = dq[nat];
+    if (coeff == 0) {
+      ++run;
+      continue;
+    }
+    while (run > 15) {
+      hd_atomic_add(&hist[0xf0], weight);
+      run -= 16;
+    }
+    const int v = coeff / q[nat];
+    const int nbits = hd_floor_log2_nz(static_cast<unsigned int>(v < 0 ? -v : v)) + 1;
+    hd_atomic_add(&hist[(run << 4) + nbits], weight);
+    run = 0;
+  }
+  if (b >= 64 && run > 0) hd_atomic_add(&hist[0], weight);
+}
+
+// One thread per touched block: consumes cnt[b] candidates of the block (plan_edit + the
+// body of Search::walk), logs what it overwrote.
+struct BulkApply {
+  WalkState s;
+  const int* touched;
+  unsigned int* cnt;        // reset to 0 here
+  int* done;                // [nblocks] entries consumed from the block by this bulk (undo, host bookkeeping)
+  int* stamp;               // [nblocks] = iter for touched blocks
+  int iter;
+  int direction;
+  unsigned int* delta_hist; // [3][256] symbol count deltas (two's complement)
+  unsigned int* chroma_nz;  // [1] delta of the number of nonzero chroma coefficients (two's complement)
+  int* log_index;           // undo log: flat coefficient index
+  int16_t* log_old;         //           value before
+  unsigned int* n_log;
+  GB_HD void operator()(int j) const {
+    const int b = touched[j];
+    const int n = static_cast<int>(cnt[b]);
+    cnt[b] = 0u;
+    done[b] = n;
+    stamp[b] = iter;
+    const size_t per = static_cast<size_t>(s.nblocks) * 64;
+    for (int t = 0; t < n; ++t) {
+      const int li = s.last_index[b];
+      const int idx = s.z_idx[static_cast<size_t>(b) * 192 + li + (direction < 0 ? -1 : 0)];
+      const int c = idx >> 6, k = idx & 63;
+      const int* qc = s.q + 64 * c;
+      const int16_t* ob = s.orig + c * per + static_cast<size_t>(b) * 64;
+      int16_t* blk = s.cand + c * per + static_cast<size_t>(b) * 64;
+      const int newval = direction > 0 ? 0 : quantize_coeff(ob[k], qc[k]);
+      const int zp = s.nat2zz[k];
+      int za = zp - 1, zb = zp + 1;
+      while (za > 0 && blk[s.zz2nat[za]] == 0) --za;
+      while (zb < 64 && blk[s.zz2nat[zb]] == 0) ++zb;
+      bool precious = false;
+      if (k == 1 || k == 8) {
+        int sum_of_hf = 0;
+        for (int ii = 3; ii < 64; ++ii) {
+          if ((ii & 7) < 3 && ii < 3 * 8) continue;
+          const int v = ob[ii];
+          sum_of_hf += v < 0 ? -v : v;
+        }
+        const int limit = sum_of_hf < 60 ? 4 : 8;
+        const int a = ob[k] < 0 ? -ob[k] : ob[k];
+        precious = a >= limit;
+      }
+      const bool store = !precious || newval != 0;
+      unsigned int* h = delta_hist + 256 * c;
+      dev_ac_symbols_of_range(blk, qc, s.zz2nat, za, zb, 0xffffffffu, h);
+      if (store) {
+        const int16_t old = blk[k];
+        const unsigned int at = hd_atomic_add(n_log, 1u);
+        log_index[at] = static_cast<int>(c * per + static_cast<size_t>(b) * 64 + k);
+        log_old[at] = old;
+        blk[k] = static_cast<int16_t>(newval);
+        if (c > 0) {
+          const int d = (newval != 0 ? 1 : 0) - (old != 0 ? 1 : 0);
+          if (d != 0) hd_atomic_add(chroma_nz, static_cast<unsigned int>(d));
+        }
+      }
+      dev_ac_symbols_of_range(blk, qc, s.zz2nat, za, zb, 1u, h);
+      s.last_index[b] = li + direction;
+    }
+  }
+};
+
+// Rolls a bulk back: coefficient values from the log, candidate cursors from `done`.
+struct BulkUndoCoeffs {
+  const int* log_index;
+  const int16_t* log_old;
+  int16_t* cand;
+  GB_HD void operator()(int i) const { cand[log_index[i]] = log_old[i]; }
+};
+struct BulkUndoCursors {
+  const int* touched;
+  const int* done;
+  int* last_index;
+  int direction;
+  GB_HD void operator()(int j) const {
+    const int b = touched[j];
+    last_index[b] -= direction * done[b];
+  }
+};
+
+// State of the blocks the host window walk will touch: coefficients [n][3][64], candidate
+// cursor, and whether the bulk of iteration `iter` touched the block.
+struct GatherBlockState {
+  const int* blocks;
+  const int16_t* cand;
+  const int* last_index;
+  const int* stamp;
+  int iter, nblocks;
+  int16_t* out_coeffs;  // [n][3][64]
+  int* out_cursor;      // [n]
+  int* out_in_bulk;     // [n]
+  GB_HD void operator()(int i) const {  // i over n * 3
+    const int e = i / 3, c = i - 3 * e;
+    const int b = blocks[e];
+    const int16_t* src = cand + (static_cast<size_t>(c) * nblocks + b) * 64;
+    int16_t* dst = out_coeffs + static_cast<size_t>(i) * 64;
+    for (int k = 0; k < 64; ++k) dst[k] = src[k];
+    if (c == 0) {
+      out_cursor[e] = last_index[b];
+      out_in_bulk[e] = stamp[b] == iter ? 1 : 0;
+    }
+  }
+};
+
+// the host window consumed one more candidate of each listed block (a block may repeat)
+struct AdvanceCursors {
+  const int* blocks;
+  int* last_index;
+  int direction;
+  GB_HD void operator()(int i) const {
+    hd_atomic_add(reinterpret_cast<unsigned int*>(&last_index[blocks[i]]), static_cast<unsigned int>(direction));
+  }
+};
+
+// max_block_error[b] += block_weight[b] * val_threshold * direction (g/processor.cc:752-755)
+struct AddMaxErr {
+  float* max_err;
+  const float* weight;
+  float val_threshold;
+  int direction;
+  GB_HD void operator()(int b) const { max_err[b] += weight[b] * val_threshold * direction; }
+};
+
+}  // namespace gb200
