@@ -1025,6 +1025,102 @@ __global__ void __launch_bounds__(256) k_walk_stats(const int* last_index, const
   }
 }
 
+// Select2Hist1 with a per-CTA shared-memory histogram pair.
+__global__ void __launch_bounds__(256) k_select2_hist1(OrderKeyCommon c, unsigned int* hist, const Select2State* st,
+                                                       int entries) {
+  __shared__ unsigned int sh[2 * kOrderBins];
+  for (int i = threadIdx.x; i < 2 * kOrderBins; i += 256) sh[i] = 0;
+  __syncthreads();
+  const unsigned int b_lo = st->bin0_lo, b_hi = st->bin0_hi;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < entries; e += gridDim.x * 256) {
+    float v;
+    int b;
+    if (!c.key(e, &b, &v)) continue;
+    const unsigned int u = hd_float_sortable(v);
+    const unsigned int top = u >> 21, mid = (u >> 10) & 0x7ffu;
+    if (top == b_lo) atomicAdd(&sh[mid], 1u);
+    if (top == b_hi) atomicAdd(&sh[kOrderBins + mid], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * kOrderBins; i += 256) {
+    const unsigned int n = sh[i];
+    if (n) atomicAdd(&hist[i], n);
+  }
+}
+
+// rank_bin_serial by one CTA of 1024 threads (two bins per thread): the bin whose inclusive
+// prefix first reaches `want`.
+__device__ void rank_bin_block(const unsigned int* hist, unsigned int want, unsigned int* bin, unsigned int* before,
+                               unsigned int* total) {
+  __shared__ unsigned int warp_tot[32];
+  __shared__ unsigned int res[3];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const unsigned int h0 = hist[2 * t], h1 = hist[2 * t + 1];
+  const unsigned int local = h0 + h1;
+  unsigned int incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  __syncthreads();  // protects warp_tot / res of a previous call
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  unsigned int base = 0, tot = 0;
+  for (int k = 0; k < 32; ++k) {
+    if (k < warp) base += warp_tot[k];
+    tot += warp_tot[k];
+  }
+  const unsigned int excl = base + incl - local;
+  if (t == 0) {
+    res[0] = kOrderBins - 1;
+    res[1] = tot - hist[kOrderBins - 1];
+    res[2] = tot;
+  }
+  __syncthreads();
+  if (excl < want && want <= excl + h0) {
+    res[0] = 2 * t;
+    res[1] = excl;
+  } else if (excl + h0 < want && want <= excl + local) {
+    res[0] = 2 * t + 1;
+    res[1] = excl + h0;
+  }
+  __syncthreads();
+  *bin = res[0];
+  *before = res[1];
+  *total = res[2];
+}
+
+__global__ void __launch_bounds__(1024) k_select2_level0(const unsigned int* hist, Select2State* st) {
+  unsigned int bin, before, total;
+  rank_bin_block(hist, st->want_lo, &bin, &before, &total);
+  unsigned int bin2, before2, total2;
+  rank_bin_block(hist, st->want_hi, &bin2, &before2, &total2);
+  if (threadIdx.x == 0) {
+    st->bin0_lo = bin;
+    st->below0_lo = before;
+    st->bin0_hi = bin2;
+    st->below0_hi = before2;
+    st->total = total;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_select2_level1(const unsigned int* hist, Select2State* st) {
+  const unsigned int w_lo = st->want_lo > st->below0_lo ? st->want_lo - st->below0_lo : 1u;
+  const unsigned int w_hi = st->want_hi > st->below0_hi ? st->want_hi - st->below0_hi : 1u;
+  unsigned int bin, before, total;
+  rank_bin_block(hist, w_lo, &bin, &before, &total);
+  unsigned int bin2, before2, total2;
+  rank_bin_block(hist + kOrderBins, w_hi, &bin2, &before2, &total2);
+  if (threadIdx.x == 0) {
+    st->lo22 = (st->bin0_lo << 11) | bin;
+    st->before_lo = st->below0_lo + before;
+    st->hi22 = (st->bin0_hi << 11) | bin2;
+    st->kept_hi = st->below0_hi + before2 + hist[kOrderBins + bin2];
+    st->mid_count = 0;
+  }
+}
+
 // BulkApply (walk_dev.h) with the symbol-count deltas privatised per CTA: the symbols cluster
 // in a few bins, global atomics on them would serialise the whole kernel.
 __global__ void __launch_bounds__(128) k_bulk_apply(BulkApply a, int n) {
@@ -1220,17 +1316,19 @@ __global__ void __launch_bounds__(1024) k_sort_pairs(float* k0, int* v0, float* 
     }
   }
 }
-// The same for selections that fit in shared memory (up to kSortSmemMax entries): the keys
+// The same for selections that fit in shared memory (CAP entries, NT threads): the keys
 // (order-preserving integer image) and 16-bit indices ping-pong between two shared-memory
 // buffers; global memory is read once and written once.
 constexpr int kSortSmemMax = 14336;
-__global__ void __launch_bounds__(1024) k_sort_pairs_smem(float* keys, int* vals, int n) {
+constexpr int kSortSmemSmall = 3072;
+template <int CAP, int NT>
+__global__ void __launch_bounds__(NT) k_sort_pairs_smem(float* keys, int* vals, int n) {
   extern __shared__ unsigned int dyn_sort[];
-  unsigned int* ka = dyn_sort;                                                  // [kSortSmemMax]
-  unsigned int* kb = ka + kSortSmemMax;                                         // [kSortSmemMax]
-  unsigned short* ia = reinterpret_cast<unsigned short*>(kb + kSortSmemMax);   // [kSortSmemMax]
-  unsigned short* ib = ia + kSortSmemMax;                                       // [kSortSmemMax]
-  unsigned short* cnt = ib + kSortSmemMax;                                      // [16][1024]
+  unsigned int* ka = dyn_sort;                                       // [CAP]
+  unsigned int* kb = ka + CAP;                                       // [CAP]
+  unsigned short* ia = reinterpret_cast<unsigned short*>(kb + CAP);  // [CAP]
+  unsigned short* ib = ia + CAP;                                     // [CAP]
+  unsigned short* cnt = ib + CAP;                                    // [16][NT]
   __shared__ unsigned int warp_tot[32];
   __shared__ unsigned int s_or, s_and;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -1241,7 +1339,7 @@ __global__ void __launch_bounds__(1024) k_sort_pairs_smem(float* keys, int* vals
   __syncthreads();
   {
     unsigned int o = 0u, a = 0xffffffffu;
-    for (int i = t; i < n; i += 1024) {  // coalesced load
+    for (int i = t; i < n; i += NT) {  // coalesced load
       const unsigned int u = hd_float_sortable(keys[i]);
       ka[i] = u;
       ia[i] = static_cast<unsigned short>(i);
@@ -1253,13 +1351,13 @@ __global__ void __launch_bounds__(1024) k_sort_pairs_smem(float* keys, int* vals
   }
   __syncthreads();
   const unsigned int varying = s_or ^ s_and;
-  const int chunk = (n + 1023) / 1024;
+  const int chunk = (n + NT - 1) / NT;
   const int lo = min(n, t * chunk), hi = min(n, lo + chunk);
   for (int shift = 0; shift < 32; shift += 4) {
     if (((varying >> shift) & 15u) == 0u) continue;  // uniform
 #pragma unroll
-    for (int d = 0; d < 16; ++d) cnt[d * 1024 + t] = 0;
-    for (int i = lo; i < hi; ++i) ++cnt[((ka[i] >> shift) & 15u) * 1024 + t];
+    for (int d = 0; d < 16; ++d) cnt[d * NT + t] = 0;
+    for (int i = lo; i < hi; ++i) ++cnt[((ka[i] >> shift) & 15u) * NT + t];
     __syncthreads();
     unsigned int local[16], sum = 0u;
 #pragma unroll
@@ -1286,7 +1384,7 @@ __global__ void __launch_bounds__(1024) k_sort_pairs_smem(float* keys, int* vals
     __syncthreads();
     for (int i = lo; i < hi; ++i) {
       const unsigned int u = ka[i];
-      const unsigned int pos = cnt[((u >> shift) & 15u) * 1024 + t]++;
+      const unsigned int pos = cnt[((u >> shift) & 15u) * NT + t]++;
       kb[pos] = u;
       ib[pos] = ia[i];
     }
@@ -1299,11 +1397,12 @@ __global__ void __launch_bounds__(1024) k_sort_pairs_smem(float* keys, int* vals
     ib = ti;
   }
   // gather the payloads through the permutation (read all, then write: in place)
-  int pay[kSortSmemMax / 1024];
-  float key[kSortSmemMax / 1024];
+  constexpr int PER = (CAP + NT - 1) / NT;
+  int pay[PER];
+  float key[PER];
 #pragma unroll
-  for (int r = 0; r < kSortSmemMax / 1024; ++r) {
-    const int i = t + 1024 * r;
+  for (int r = 0; r < PER; ++r) {
+    const int i = t + NT * r;
     if (i < n) {
       pay[r] = vals[ia[i]];
       key[r] = keys[ia[i]];
@@ -1311,8 +1410,8 @@ __global__ void __launch_bounds__(1024) k_sort_pairs_smem(float* keys, int* vals
   }
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < kSortSmemMax / 1024; ++r) {
-    const int i = t + 1024 * r;
+  for (int r = 0; r < PER; ++r) {
+    const int i = t + NT * r;
     if (i < n) {
       vals[i] = pay[r];
       keys[i] = key[r];
@@ -1323,11 +1422,19 @@ __global__ void __launch_bounds__(1024) k_sort_pairs_smem(float* keys, int* vals
 
 void ImageContext::sort_selection(size_t n) {
   if (n < 2) return;
+  if (n <= kSortSmemSmall) {
+    const size_t smem = kSortSmemSmall * 12 + 16 * 256 * sizeof(unsigned short);  // 44 KB
+    note_launch("sort_pairs", s_, static_cast<double>(n));
+    k_sort_pairs_smem<kSortSmemSmall, 256><<<1, 256, smem, s_>>>(d_sel_val_, d_sel_block_, static_cast<int>(n));
+    note_launch_end("sort_pairs", s_);
+    return;
+  }
   if (n <= kSortSmemMax) {
     const size_t smem = kSortSmemMax * 12 + 16 * 1024 * sizeof(unsigned short);
-    GB_CUDA(cudaFuncSetAttribute(k_sort_pairs_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    GB_CUDA(cudaFuncSetAttribute(k_sort_pairs_smem<kSortSmemMax, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
     note_launch("sort_pairs", s_, static_cast<double>(n));
-    k_sort_pairs_smem<<<1, 1024, smem, s_>>>(d_sel_val_, d_sel_block_, static_cast<int>(n));
+    k_sort_pairs_smem<kSortSmemMax, 1024><<<1, 1024, smem, s_>>>(d_sel_val_, d_sel_block_, static_cast<int>(n));
     note_launch_end("sort_pairs", s_);
     return;
   }
@@ -1346,6 +1453,81 @@ void ImageContext::sort_selection(size_t n) {
 }
 #endif
 
+size_t ImageContext::walk_select_split(int direction, size_t rank_lo, size_t rank_hi, size_t* before, size_t* total) {
+  // d_hist_ holds 2048 bins + the old select state; the pair of level-1 histograms and the
+  // two-rank state live in w_sel2_
+  if (w_sel2_ == nullptr) {
+    w_sel2_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * (2 * kOrderBins + 64)));
+    owned_.push_back(w_sel2_);
+  }
+  Select2State* st = reinterpret_cast<Select2State*>(w_sel2_ + 2 * kOrderBins);
+  Select2State init;
+  memset(&init, 0, sizeof(init));
+  init.want_lo = static_cast<unsigned int>(rank_lo < 1 ? 1 : rank_lo);
+  init.want_hi = static_cast<unsigned int>(rank_hi);
+  h2d(st, &init, sizeof(init), s_);
+  // a fresh bulk: counters for the per-block counts that the split pass starts to fill
+  ++w_iter_;
+  dev_zero(w_counters_, (4 + 768) * sizeof(unsigned int), s_);
+  OrderKeyCommon c;
+  c.err = z_err_;
+  c.entry_block = e_block_;
+  c.entry_slot = e_slot_;
+  c.last_index = d_last_index_;
+  c.max_err = d_max_err_;
+  c.weight = weights_;
+  c.direction = direction;
+  const int entries = static_cast<int>(num_entries_);
+  const size_t mid_cap_want = (rank_hi - (rank_lo < 1 ? 1 : rank_lo)) * 2 + 65536;
+  if (mid_cap_want > sel_cap_) {
+    stream_sync(s_);
+    if (d_sel_val_) { dev_free(d_sel_val_); d_sel_val_ = nullptr; }
+    if (d_sel_block_) { dev_free(d_sel_block_); d_sel_block_ = nullptr; }
+    sel_cap_ = mid_cap_want;
+    d_sel_val_ = static_cast<float*>(dev_alloc(sel_cap_ * sizeof(float)));
+    d_sel_block_ = static_cast<int*>(dev_alloc(sel_cap_ * sizeof(int)));
+  }
+  dev_zero(d_hist_, sizeof(unsigned int) * kOrderBins, s_);
+  dev_zero(w_sel2_, sizeof(unsigned int) * 2 * kOrderBins, s_);
+#if defined(GB200_HOSTSIM)
+  launch_1d(s_, OrderKeyHist{c, d_hist_, nullptr, 0}, entries, "order_key_hist");
+  launch_1d(s_, Select2Level0{d_hist_, st}, 1, "select2_level");
+  launch_1d(s_, Select2Hist1{c, w_sel2_, st}, entries, "select2_hist1");
+  launch_1d(s_, Select2Level1{w_sel2_, st}, 1, "select2_level");
+#else
+  launch_order_hist(s_, c, d_hist_, nullptr, 0, entries);
+  note_launch("select2_level", s_, kOrderBins);
+  k_select2_level0<<<1, 1024, 0, s_>>>(d_hist_, st);
+  note_launch_end("select2_level", s_);
+  {
+    int ctas = (entries + 256 * 8 - 1) / (256 * 8);
+    if (ctas < 1) ctas = 1;
+    if (ctas > 1184) ctas = 1184;
+    note_launch("select2_hist1", s_, entries);
+    k_select2_hist1<<<ctas, 256, 0, s_>>>(c, w_sel2_, st, entries);
+    note_launch_end("select2_hist1", s_);
+  }
+  note_launch("select2_level", s_, kOrderBins);
+  k_select2_level1<<<1, 1024, 0, s_>>>(w_sel2_, st);
+  note_launch_end("select2_level", s_);
+#endif
+  launch_1d(s_, Select2Split{c, st, w_cnt_, w_touched_, w_counters_, d_sel_val_, d_sel_block_,
+                             static_cast<unsigned int>(sel_cap_)},
+            entries, "select2_split");
+  Select2State got;
+  d2h(&got, st, sizeof(got), s_);
+  *total = got.total;
+  *before = got.before_lo;
+  const size_t n_mid = got.kept_hi >= got.before_lo ? got.kept_hi - got.before_lo : 0;
+  if (got.mid_count != n_mid) throw std::runtime_error("select2: middle count mismatch");
+  if (n_mid > sel_cap_) throw std::runtime_error("select2: middle list overflow");
+  sel_sorted_ = n_mid;
+  sort_selection(n_mid);
+  split_pending_ = true;
+  pending_bulk_extra_ = got.before_lo;
+  return n_mid;
+}
+
 size_t ImageContext::walk_select_sorted(int direction, size_t want, size_t* total) {
   OrderSelectState got;
   select_keys(direction, want, &got);
@@ -1362,7 +1544,7 @@ void ImageContext::walk_fetch_sorted(size_t first, size_t n, float* val, int* bl
   d2h(block, d_sel_block_ + first, n * sizeof(int), s_);
 }
 
-void ImageContext::walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, const int* host_blocks) {
+void ImageContext::walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, const int* host_blocks, bool after_split) {
   const int* entry_blocks = d_sel_block_;
   if (host_blocks != nullptr) {
     if (nbulk > w_acap_) {
@@ -1376,20 +1558,27 @@ void ImageContext::walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, c
   } else if (nbulk > sel_sorted_) {
     throw std::runtime_error("walk_bulk_apply: bulk larger than the selection");
   }
-  if (nbulk > w_log_cap_) {
+  const size_t log_need = nbulk + pending_bulk_extra_;
+  pending_bulk_extra_ = 0;
+  if (log_need > w_log_cap_) {
     stream_sync(s_);
     if (w_log_index_) { dev_free(w_log_index_); w_log_index_ = nullptr; }
     if (w_log_old_) { dev_free(w_log_old_); w_log_old_ = nullptr; }
-    w_log_cap_ = nbulk + nbulk / 2 + 4096;
+    w_log_cap_ = log_need + log_need / 2 + 4096;
     w_log_index_ = static_cast<int*>(dev_alloc(w_log_cap_ * sizeof(int)));
     w_log_old_ = static_cast<int16_t*>(dev_alloc(w_log_cap_ * sizeof(int16_t)));
   }
-  ++w_iter_;
-  dev_zero(w_counters_, (4 + 768) * sizeof(unsigned int), s_);
+  if (after_split != split_pending_) throw std::runtime_error("walk_bulk_apply: split state mismatch");
+  if (!after_split) {
+    ++w_iter_;
+    dev_zero(w_counters_, (4 + 768) * sizeof(unsigned int), s_);
+  }
+  split_pending_ = false;
   unsigned int host_counters[4 + 768];
   memset(host_counters, 0, sizeof(host_counters));
-  if (nbulk > 0) {
-    launch_1d(s_, BulkCount{entry_blocks, w_cnt_, w_touched_, w_counters_}, static_cast<int>(nbulk), "walk_bulk_count");
+  if (nbulk > 0 || after_split) {
+    if (nbulk > 0)
+      launch_1d(s_, BulkCount{entry_blocks, w_cnt_, w_touched_, w_counters_}, static_cast<int>(nbulk), "walk_bulk_count");
     unsigned int n_touched = 0;
     d2h(&n_touched, w_counters_, sizeof(unsigned int), s_);
     BulkApply a;

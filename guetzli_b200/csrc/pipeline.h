@@ -108,6 +108,10 @@ class ImageContext {
   void download_weights(float* out);
   // at least the `want` smallest keys of the order, sorted ascending, resident; -> how many
   size_t walk_select_sorted(int direction, size_t want, size_t* total);
+  // Two-rank select: entries certainly among the first `rank_lo` are counted into the pending
+  // bulk right away, the entries between the two ranks (the "middle") are left sorted in the
+  // resident selection.  *before = entries already counted, -> size of the middle.
+  size_t walk_select_split(int direction, size_t rank_lo, size_t rank_hi, size_t* before, size_t* total);
   void walk_fetch_sorted(size_t first, size_t n, float* val, int* block);
   struct BulkResult {
     int touched, logged, chroma_delta;
@@ -115,7 +119,9 @@ class ImageContext {
   };
   // consumes entries [0, nbulk) of the sorted selection on the device; host_blocks != nullptr:
   // the entries' blocks come from the host instead (prefix of the reference-ordered sort)
-  void walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, const int* host_blocks = nullptr);
+  // after_split: the counts of walk_select_split are pending and are consumed as well
+  void walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, const int* host_blocks = nullptr,
+                       bool after_split = false);
   void walk_bulk_undo(int direction);
   void walk_gather(const std::vector<int>& blocks, std::vector<int16_t>* coeffs, std::vector<int>* cursor,
                    std::vector<int>* in_bulk);
@@ -180,6 +186,9 @@ class ImageContext {
   int* d_sel_block2_ = nullptr;
   size_t sel2_cap_ = 0;
   size_t sel_sorted_ = 0;    // entries of the sorted resident selection
+  unsigned int* w_sel2_ = nullptr;  // two-rank select: level-1 histogram pair + Select2State
+  bool split_pending_ = false;      // walk_select_split has counted entries that no bulk has consumed yet
+  size_t pending_bulk_extra_ = 0;   // ... how many
   int w_iter_ = 0;
   int w_last_touched_ = 0, w_last_logged_ = 0;
   int pending_touched_ = 0;  // blocks the last bulk changed and compare() has not rendered yet

@@ -606,7 +606,9 @@ class Search {
     std::vector<std::pair<int, float> >& order = order_buf_;
     size_t base = 0, n_slice = 0, usable_end = 0;
     std::vector<int> bulk_blocks;
+    bool split_count = false;  // the device already holds per-block counts of the entries before `base`
     if (exact) {
+      Tick tk(&dt_[0]);
       size_t want = std::max(last_consumed, i0) + std::max<size_t>(i0 / 8, 1024), dev_total = 0;
       if (want > order_size) want = order_size;
       const size_t k_end = ctx_->exact_order_prefix_resident(direction, want, &order, &dev_total);
@@ -617,26 +619,42 @@ class Search {
       bulk_blocks.resize(i0);
       for (size_t i = 0; i < i0; ++i) bulk_blocks[i] = order[i].first;
     } else {
-      const size_t want = std::min(order_size, std::max(last_consumed, i0) + std::max<size_t>(i0 / 8, 1024));
-      size_t total = 0;
-      const size_t kept = ctx_->walk_select_sorted(direction, want, &total);
-      if (total != order_size) throw std::runtime_error("walk_select_sorted: entry count mismatch");
-      if (kept < i0 + 64 || kept >= order_size) {
+      Tick tk(&dt_[1]);
+      // two-rank select: everything certainly before position i0 - 64 is counted into the bulk
+      // on the device right away; the entries from there up to the rank the window may reach
+      // (the "middle") come back sorted -- their head completes the bulk, the rest is the window
+      const size_t pre = 64;
+      const size_t rank_hi = std::min(order_size, std::max(last_consumed, i0) + std::max<size_t>(i0 / 16, 1024));
+      size_t total = 0, before = 0;
+      const size_t n_mid = ctx_->walk_select_split(direction, i0 - pre, rank_hi, &before, &total);
+      split_count = true;
+      if (total != order_size) throw std::runtime_error("walk_select_split: entry count mismatch");
+      base = before;
+      n_slice = n_mid;
+      usable_end = n_slice;
+      if (before + pre > i0 || before + n_mid < i0 + 64 || before + n_mid >= order_size) {
+        // cannot use it: consume the pending counts and roll them back
+        ImageContext::BulkResult dummy;
+        ctx_->walk_bulk_apply(direction, 0, &dummy, nullptr, true);
+        ctx_->walk_bulk_undo(direction);
         st_->ms_sort += ms_since(t0);
         return -1;
       }
-      const size_t pre = std::min<size_t>(i0, 64);
-      base = i0 - pre;
-      n_slice = kept - base;
-      usable_end = n_slice;
       std::vector<float> val(n_slice);
       std::vector<int> blk(n_slice);
-      ctx_->walk_fetch_sorted(base, n_slice, val.data(), blk.data());
+      ctx_->walk_fetch_sorted(0, n_slice, val.data(), blk.data());
       order.resize(n_slice);
       for (size_t i = 0; i < n_slice; ++i) order[i] = std::make_pair(blk[i], val[i]);
     }
     ImageContext::BulkResult bulk;
-    ctx_->walk_bulk_apply(direction, i0, &bulk, exact ? bulk_blocks.data() : nullptr);
+    {
+      Tick tk(&dt_[2]);
+      if (exact) {
+        ctx_->walk_bulk_apply(direction, i0, &bulk, bulk_blocks.data());
+      } else {
+        ctx_->walk_bulk_apply(direction, i0 - base, &bulk, nullptr, split_count);
+      }
+    }
     st_->ms_sort += ms_since(t0);
     Clock::time_point tw = Clock::now();
     SymbolHistogram saved_h[3] = {m.ac_h[0], m.ac_h[1], m.ac_h[2]};
@@ -671,7 +689,11 @@ class Search {
       }
       std::vector<int16_t> gc;
       std::vector<int> gcur, gin;
-      ctx_->walk_gather(need, &gc, &gcur, &gin);
+      {
+        Tick tk(&dt_[3]);
+        ctx_->walk_gather(need, &gc, &gcur, &gin);
+      }
+      Tick tk4(&dt_[4]);
       for (size_t e = 0; e < need.size(); ++e) {
         const int b = need[e];
         for (int c = 0; c < 3; ++c)
@@ -698,6 +720,7 @@ class Search {
     if (ok && out.stopped && base + usable_end < order_size && out.consumed >= base + usable_end) ok = false;
     st_->ms_walk += ms_since(tw);
     if (ok) {
+      Tick tk(&dt_[5]);
       ++device_walks_;
       // device: cursors of the window's entries, the new max errors (the window's coefficient
       // edits follow with the common scatter)
@@ -790,6 +813,7 @@ class Search {
         int blocks_to_change = 0;
         for (int rblock = 1; rblock <= 4; ++rblock) {
           unsigned long long n_entries = 0, n_blocks = 0;
+          Tick tk(&dt_[6]);
           ctx_->walk_weights(direction, rblock, params_.butteraugli_target * target_mul, first_up_iter, &n_entries,
                              &n_blocks);
           order_size = static_cast<size_t>(n_entries);
@@ -834,6 +858,7 @@ class Search {
         }
         if (!done) {
           // host paths: they work on the host mirror of the candidate and of the cursors
+          Tick tk(&dt_[8]);
           if (!mirror_valid_) {
             ctx_->download_candidate(cand_.data());
             ctx_->walk_download_state(&m.last_indexes, &m.max_block_error);
@@ -1010,7 +1035,10 @@ class Search {
 
         ++st_->iterations;
         if (direction > 0) ++st_->iterations_up; else ++st_->iterations_down;
-        ctx_->scatter_coeffs(m.edit_index, m.edit_value);
+        {
+          Tick tk(&dt_[7]);
+          ctx_->scatter_coeffs(m.edit_index, m.edit_value);
+        }
         const size_t encoded = encoded_size(m.ac_h);
         logf("Iter %2d: %s(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
              st_->iterations, "f111111", 7, direction > 0 ? "up" : "down", static_cast<int>(out.consumed),
@@ -1022,7 +1050,10 @@ class Search {
       }
     }
     if (getenv("GB200_TIE_DEBUG"))
-      fprintf(stderr, "device walks %d; ", device_walks_);
+      fprintf(stderr,
+              "device walks %d; ms: exact prefix %.1f, select+sort+fetch %.1f, bulk %.1f, gather %.1f, window walk %.1f, "
+              "advance %.1f, weights+stats %.1f, scatter %.1f, mirror sync %.1f\n",
+              device_walks_, dt_[0], dt_[1], dt_[2], dt_[3], dt_[4], dt_[5], dt_[6], dt_[7], dt_[8]);
     if (getenv("GB200_TIE_DEBUG"))
       fprintf(stderr, "tie fallbacks %d: run-at-refresh %d, run-at-test %d, pair-at-refresh %d, pair-untestable %d, pair-decides %d; exact %d partial %d\n",
               tie_fallbacks_, tie_why_[1], tie_why_[2], tie_why_[3], tie_why_[4], tie_why_[5], st_->order_exact,
@@ -1049,6 +1080,13 @@ class Search {
   std::vector<std::pair<int, float> > order_buf_;
   int device_order_checked_ = 0;
   int device_walks_ = 0;
+  double dt_[16] = {0};  // GB200_TIE_DEBUG: wall ms per phase, see the report at the end of select_frequency_masking
+  struct Tick {
+    double* acc;
+    Clock::time_point t0;
+    explicit Tick(double* a) : acc(a), t0(Clock::now()) {}
+    ~Tick() { *acc += ms_since(t0); }
+  };
   bool device_done_ = false;   // the current iteration took the device path
   std::vector<char> fetched_;  // blocks whose state the host holds for the current iteration
   std::vector<int> fetched_list_;

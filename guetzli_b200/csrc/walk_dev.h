@@ -20,6 +20,7 @@
 #include "hd.h"
 #include "jpeg_dev.h"
 #include "jpeg_math.h"
+#include "kernels.h"
 
 namespace gb200 {
 
@@ -41,6 +42,111 @@ struct WalkStatsPartial {
     }
     out[2 * i] = n;
     out[2 * i + 1] = c;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Two-rank radix select over the order keys (same two-level scheme as OrderSelectState in
+// kernels.h, both ranks from the same two histogram passes).  lo = the rank a little before
+// the end of the bulk, hi = the rank the host window may reach.  After it:
+//   keys in 22-bit bins below lo22           -> in the bulk for sure: counted per block directly
+//   keys in bins lo22 .. hi22 (the "middle") -> compacted, sorted; the first entries complete the
+//                                               bulk, the rest is the window
+//   keys above                               -> not needed this iteration
+struct Select2State {
+  unsigned int want_lo, want_hi;
+  unsigned int bin0_lo, below0_lo, bin0_hi, below0_hi, total;
+  unsigned int lo22, before_lo;  // 22-bit bin holding rank want_lo; entries in bins below it
+  unsigned int hi22, kept_hi;    // 22-bit bin holding rank want_hi; entries in bins up to and including it
+  unsigned int mid_count;        // cursor of the middle list
+};
+
+// first bin whose cumulative count reaches `want` (>= 1); none: the last bin.  Serial form.
+GB_HD void rank_bin_serial(const unsigned int* hist, int nbins, unsigned int want, unsigned int* bin,
+                           unsigned int* before, unsigned int* total) {
+  unsigned int cum = 0, b = static_cast<unsigned int>(nbins - 1), at = 0;
+  bool found = false;
+  for (int i = 0; i < nbins; ++i) {
+    if (!found && cum + hist[i] >= want) {
+      b = static_cast<unsigned int>(i);
+      at = cum;
+      found = true;
+    }
+    cum += hist[i];
+  }
+  if (!found) at = cum - hist[nbins - 1];
+  *bin = b;
+  *before = at;
+  *total = cum;
+}
+
+struct Select2Level0 {  // one invocation
+  const unsigned int* hist;  // [2048]: bits 31..21 of every key
+  Select2State* st;
+  GB_HD void operator()(int) const {
+    unsigned int total;
+    rank_bin_serial(hist, kOrderBins, st->want_lo, &st->bin0_lo, &st->below0_lo, &total);
+    rank_bin_serial(hist, kOrderBins, st->want_hi, &st->bin0_hi, &st->below0_hi, &total);
+    st->total = total;
+  }
+};
+
+struct Select2Hist1 {  // over the entries: bits 20..10 of the keys in the two level-0 bins
+  OrderKeyCommon c;
+  unsigned int* hist;  // [2][2048]
+  const Select2State* st;
+  GB_HD void operator()(int entry) const {
+    float v;
+    int b;
+    if (!c.key(entry, &b, &v)) return;
+    const unsigned int u = hd_float_sortable(v);
+    const unsigned int top = u >> 21, mid = (u >> 10) & 0x7ffu;
+    if (top == st->bin0_lo) hd_atomic_add(&hist[mid], 1u);
+    if (top == st->bin0_hi) hd_atomic_add(&hist[kOrderBins + mid], 1u);
+  }
+};
+
+struct Select2Level1 {  // one invocation
+  const unsigned int* hist;  // [2][2048]
+  Select2State* st;
+  GB_HD void operator()(int) const {
+    unsigned int bin, before, total;
+    rank_bin_serial(hist, kOrderBins, st->want_lo > st->below0_lo ? st->want_lo - st->below0_lo : 1u, &bin, &before,
+                    &total);
+    st->lo22 = (st->bin0_lo << 11) | bin;
+    st->before_lo = st->below0_lo + before;
+    rank_bin_serial(hist + kOrderBins, kOrderBins, st->want_hi > st->below0_hi ? st->want_hi - st->below0_hi : 1u, &bin,
+                    &before, &total);
+    st->hi22 = (st->bin0_hi << 11) | bin;
+    st->kept_hi = st->below0_hi + before + hist[kOrderBins + bin];
+    st->mid_count = 0;
+  }
+};
+
+// classification pass: bulk-for-sure entries are counted per block (BulkCount), the middle is compacted
+struct Select2Split {
+  OrderKeyCommon c;
+  Select2State* st;
+  unsigned int* cnt;       // [nblocks]
+  int* touched;
+  unsigned int* n_touched;
+  float* mid_val;
+  int* mid_block;
+  unsigned int mid_cap;
+  GB_HD void operator()(int entry) const {
+    float v;
+    int b;
+    if (!c.key(entry, &b, &v)) return;
+    const unsigned int u22 = hd_float_sortable(v) >> 10;
+    if (u22 < st->lo22) {
+      if (hd_atomic_add(&cnt[b], 1u) == 0u) touched[hd_atomic_add(n_touched, 1u)] = b;
+    } else if (u22 <= st->hi22) {
+      const unsigned int at = hd_atomic_add(&st->mid_count, 1u);
+      if (at < mid_cap) {
+        mid_val[at] = v;
+        mid_block[at] = b;
+      }
+    }
   }
 };
 
