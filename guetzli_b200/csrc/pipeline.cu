@@ -1453,6 +1453,49 @@ void ImageContext::sort_selection(size_t n) {
 }
 #endif
 
+#if !defined(GB200_HOSTSIM)
+namespace {
+__global__ void __launch_bounds__(256) k_count_keys_below(OrderKeyCommon c, float limit, int entries, unsigned int* out) {
+  unsigned int n = 0;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < entries; e += gridDim.x * 256) {
+    float v;
+    int b;
+    if (c.key(e, &b, &v) && v < limit) ++n;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
+}
+}  // namespace
+#endif
+
+size_t ImageContext::walk_count_below(int direction, float limit) {
+  OrderKeyCommon c;
+  c.err = z_err_;
+  c.entry_block = e_block_;
+  c.entry_slot = e_slot_;
+  c.last_index = d_last_index_;
+  c.max_err = d_max_err_;
+  c.weight = weights_;
+  c.direction = direction;
+  unsigned int* out = reinterpret_cast<unsigned int*>(w_stats_);
+  dev_zero(out, sizeof(unsigned int), s_);
+  const int entries = static_cast<int>(num_entries_);
+#if defined(GB200_HOSTSIM)
+  launch_1d(s_, CountKeysBelow{c, limit, out}, entries, "count_keys_below");
+#else
+  int ctas = (entries + 256 * 8 - 1) / (256 * 8);
+  if (ctas < 1) ctas = 1;
+  if (ctas > 1184) ctas = 1184;
+  note_launch("count_keys_below", s_, entries);
+  k_count_keys_below<<<ctas, 256, 0, s_>>>(c, limit, entries, out);
+  note_launch_end("count_keys_below", s_);
+#endif
+  unsigned int n = 0;
+  d2h(&n, out, sizeof(n), s_);
+  return n;
+}
+
 size_t ImageContext::walk_select_split(int direction, size_t rank_lo, size_t rank_hi, size_t* before, size_t* total) {
   // d_hist_ holds 2048 bins + the old select state; the pair of level-1 histograms and the
   // two-rank state live in w_sel2_

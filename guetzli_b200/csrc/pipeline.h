@@ -106,6 +106,8 @@ class ImageContext {
   void walk_weights(int direction, int radius, double target_distance, bool zero_distmap,
                     unsigned long long* order_size, unsigned long long* blocks_to_change);
   void download_weights(float* out);
+  // entries of the order whose key is below `limit`
+  size_t walk_count_below(int direction, float limit);
   // at least the `want` smallest keys of the order, sorted ascending, resident; -> how many
   size_t walk_select_sorted(int direction, size_t want, size_t* total);
   // Two-rank select: entries certainly among the first `rank_lo` are counted into the pending

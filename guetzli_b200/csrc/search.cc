@@ -600,8 +600,12 @@ class Search {
   // out of entries; in the last two cases everything is as before the call.
   int device_walk(Sfm& m, bool exact, size_t order_size, int direction, int min_coeffs_to_change, double min_size_delta,
                   int prev_size, size_t last_consumed, WalkOutcome* result) {
-    const size_t i0 = static_cast<size_t>(10 * (min_coeffs_to_change / 10));
-    if (i0 < 256 || order_size < 2 * i0 + 4096) return -1;
+    // first entry after which the walk looks at its state: an entropy-code refresh needs
+    // gi % 10 == 0 and gi + 9 >= min(min_coeffs, n - 1); the stop test gi >= min_coeffs, the final
+    // estimate gi == n - 1
+    const size_t x_first = std::min<size_t>(static_cast<size_t>(std::max(min_coeffs_to_change, 0)), order_size - 1);
+    const size_t i0 = 10 * (x_first / 10);
+    if (i0 < 256) return -1;
     Clock::time_point t0 = Clock::now();
     std::vector<std::pair<int, float> >& order = order_buf_;
     size_t base = 0, n_slice = 0, usable_end = 0;
@@ -609,11 +613,12 @@ class Search {
     bool split_count = false;  // the device already holds per-block counts of the entries before `base`
     if (exact) {
       Tick tk(&dt_[0]);
-      size_t want = std::max(last_consumed, i0) + std::max<size_t>(i0 / 8, 1024), dev_total = 0;
+      size_t want = std::max(direction < 0 ? last_consumed : 0, i0) + std::min<size_t>(std::max<size_t>(i0 / 8, 1024), 16384),
+             dev_total = 0;
       if (want > order_size) want = order_size;
       const size_t k_end = ctx_->exact_order_prefix_resident(direction, want, &order, &dev_total);
       if (dev_total != order_size) throw std::runtime_error("exact_order_prefix: entry count mismatch");
-      if (k_end < i0 + 16) return -1;
+      if (k_end < i0 + 16 && k_end < order_size) return -1;
       n_slice = k_end;
       usable_end = k_end;
       bulk_blocks.resize(i0);
@@ -624,7 +629,8 @@ class Search {
       // on the device right away; the entries from there up to the rank the window may reach
       // (the "middle") come back sorted -- their head completes the bulk, the rest is the window
       const size_t pre = 64;
-      const size_t rank_hi = std::min(order_size, std::max(last_consumed, i0) + std::max<size_t>(i0 / 16, 1024));
+      const size_t rank_hi =
+          std::min(order_size, std::max(direction < 0 ? last_consumed : 0, i0) + std::min<size_t>(std::max<size_t>(i0 / 16, 1024), 8192));
       size_t total = 0, before = 0;
       const size_t n_mid = ctx_->walk_select_split(direction, i0 - pre, rank_hi, &before, &total);
       split_count = true;
@@ -632,7 +638,7 @@ class Search {
       base = before;
       n_slice = n_mid;
       usable_end = n_slice;
-      if (before + pre > i0 || before + n_mid < i0 + 64 || before + n_mid >= order_size) {
+      if (before + pre > i0 || (before + n_mid < i0 + 64 && before + n_mid < order_size)) {
         // cannot use it: consume the pending counts and roll them back
         ImageContext::BulkResult dummy;
         ctx_->walk_bulk_apply(direction, 0, &dummy, nullptr, true);
@@ -798,9 +804,16 @@ class Search {
     }
     fetched_.assign(num_blocks, 0);
     fetched_list_.clear();
-    static const bool kDeviceWalk = [] {
-      const char* e = getenv("GB200_WALK");  // GB200_WALK=host keeps every iteration on the host path
+    // GB200_WALK=host keeps every iteration on the host path, =device forces the device path.
+    // Default: device in the product; host in the CPU port, whose emulated kernels make the
+    // device path slow (tests/test_oracle_cpu.py::test_port_device_walk turns it on).
+    const bool kDeviceWalk = [] {
+      const char* e = getenv("GB200_WALK");
+#if defined(GB200_HOSTSIM)
+      return e != nullptr && e[0] == 'd';
+#else
       return !(e != nullptr && e[0] == 'h');
+#endif
     }();
 
     bool first_up_iter = true;
@@ -840,15 +853,21 @@ class Search {
         // radix-selected order (equal keys in arbitrary arrangement, tie analysis on); if that
         // is ambiguous, on the prefix of the reference-ordered sort (device replay of std::sort).
         bool skip_partial = false;
-        if (kDeviceWalk && direction < 0 && order_size > 16384) {
-          const int r = device_walk(m, false, order_size, direction, min_coeffs_to_change, min_size_delta, prev_size,
+        if (kDeviceWalk && order_size > 16384) {
+          int min_coeffs = min_coeffs_to_change;
+          if (first_up_iter) {
+            // partition_point of the sorted order (:690-698) == number of keys below the limit
+            const size_t below = ctx_->walk_count_below(direction, 0.75f * params_.butteraugli_target);
+            min_coeffs = std::max<int>(min_coeffs, static_cast<int>(below));
+          }
+          const int r = device_walk(m, false, order_size, direction, min_coeffs, min_size_delta, prev_size,
                                     last_consumed, &out);
           if (r == 1) {
             done = true;
             ++st_->order_partial;
           } else if (r == 0) {
             skip_partial = true;  // the host's partial order would stumble over the same equal keys
-            const int r2 = device_walk(m, true, order_size, direction, min_coeffs_to_change, min_size_delta, prev_size,
+            const int r2 = device_walk(m, true, order_size, direction, min_coeffs, min_size_delta, prev_size,
                                        last_consumed, &out);
             if (r2 == 1) {
               done = true;

@@ -123,6 +123,19 @@ struct Select2Level1 {  // one invocation
   }
 };
 
+// number of order keys below a limit (the partition_point of g/processor.cc:690-698)
+struct CountKeysBelow {
+  OrderKeyCommon c;
+  float limit;
+  unsigned int* out;
+  GB_HD void operator()(int entry) const {
+    float v;
+    int b;
+    if (!c.key(entry, &b, &v)) return;
+    if (v < limit) hd_atomic_add(out, 1u);
+  }
+};
+
 // classification pass: bulk-for-sure entries are counted per block (BulkCount), the middle is compacted
 struct Select2Split {
   OrderKeyCommon c;

@@ -94,6 +94,18 @@ def test_partial_order_is_arrangement_independent(port_lib, ref, monkeypatch):
         assert trace == rtrace and jpeg == rjpeg
 
 
+def test_port_device_walk(port_lib, ref, monkeypatch):
+    """The device half of the selection walk (walk_dev.h: two-rank radix select, bulk applied
+    as a set, host loop on the window only) through the CPU port's emulated kernels, with the
+    device's symbol histograms checked against the host's every iteration."""
+    monkeypatch.setenv("GB200_WALK", "device")
+    monkeypatch.setenv("GB200_CHECK_HOST_HIST", "1")
+    for rgb, q in ((synth.noise(160, 224, 77), 95), (synth.gradnoise(192, 256, 5), 90)):
+        rok, rjpeg, rtrace, _, _ = ref.process_rgb(rgb, q)
+        ok, jpeg, trace, st = parity.run_process(port_lib, rgb, q)
+        assert ok == rok and trace == rtrace and jpeg == rjpeg
+
+
 def test_process_is_reentrant(port_lib):
     """Process() from several host threads at once (one context + stream per call, the
     batch mode of bench.py): every result equals the sequential one."""
