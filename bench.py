@@ -317,7 +317,9 @@ def run_tiled(args, wl, name, gb, dist, rank, world, local, steps, warmup):
            "output_sha256": sorted(shas)[0], "deterministic": len(shas) == 1,
            "matches_reference_golden": (sorted(shas)[0] == want) if want else None,
            "timers_ms_rank0": {k: round(st.device[k], 1) for k in
-                               ("ms_total", "ms_compare", "ms_zeroing", "ms_jpeg", "ms_sort", "ms_walk")},
+                               ("ms_total", "ms_device_setup", "ms_compare", "ms_zeroing", "ms_jpeg", "ms_sort", "ms_walk")},
+           "gpu_launches_rank0": st.device["gpu_launches"], "h2d_bytes_rank0": st.device["h2d_bytes"],
+           "d2h_bytes_rank0": st.device["d2h_bytes"],
            "iterations": st.counters["number of iterations"]}
     if world > 1:
         gb.dist_shutdown()
@@ -560,6 +562,10 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roofline,
         "single_image": single,
+        # the library's wall timers of the images of the last timed step (mean over the batch): where a
+        # Process() call spends its time when `batch_per_gpu` of them share the GPU and the host cores
+        "batch_breakdown_ms": {k: round(float(np.mean([s.device[k] for s in stats_list])), 1) for k in
+                               ("ms_total", "ms_compare", "ms_zeroing", "ms_jpeg", "ms_sort", "ms_walk")},
         "single_image_gpu_kernel_ms": round(gpu_ms, 2),
         "top_kernels": [{"name": k["name"], "ms": round(k["ms"], 2), "launches": k["launches"]} for k in kernels[:30]],
         "tiled": tiled,

@@ -270,6 +270,19 @@ void note_launch_end(const char* name, Stream s) {
   }
 }
 
+bool profiling_on() {
+  Prof& p = prof();
+  std::lock_guard<std::mutex> lock(p.mu);
+  return p.on;
+}
+
+// kernels executed by a CUDA graph launch (or, negative, recorded during a capture without running)
+void add_launches(long n) {
+  Prof& p = prof();
+  std::lock_guard<std::mutex> lock(p.mu);
+  p.launches += n;
+}
+
 long total_launches() {
   Prof& p = prof();
   std::lock_guard<std::mutex> lock(p.mu);

@@ -14,6 +14,8 @@
 #include "walk_dev.h"
 #if !defined(GB200_HOSTSIM)
 #include <map>
+#include <mutex>
+#include <set>
 #include <tuple>
 
 #include "tiled_kernels.cuh"
@@ -45,6 +47,8 @@ long long d2h_bytes_total();
 void profiling_enable(bool on);
 std::vector<KernelStat> profiling_snapshot();
 void profiling_reset();
+bool profiling_on();
+void add_launches(long n);
 #endif
 
 namespace {
@@ -107,6 +111,14 @@ void ImageContext::gather_blocks(void* dev_buf, size_t elem_bytes_per_block) {
 struct ImageContext::Fused {
   typedef std::tuple<const float*, int, int, int> Key;  // base, planes, box w, box h
   std::map<Key, CUtensorMap> maps;
+  // the Compare chain as a CUDA graph: same kernels, same arguments every call (all buffers
+  // live as long as the context), one driver call instead of sixteen
+  cudaGraphExec_t compare_graph = nullptr;
+  long compare_graph_kernels = 0;
+  int compare_calls = 0;
+  ~Fused() {
+    if (compare_graph) cudaGraphExecDestroy(compare_graph);
+  }
   const CUtensorMap& map(const float* base, int nplanes, int box_w, int box_h, const Geom& g) {
     const Key key(base, nplanes, box_w, box_h);
     std::map<Key, CUtensorMap>::iterator it = maps.find(key);
@@ -135,9 +147,18 @@ BlurK<R> make_blurk(const HostTables& ht, int id) {
   return k;
 }
 
+// opt-in to more than 48 KB of dynamic shared memory: once per (device, kernel)
 template <class K>
 void allow_smem(K kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*> > done;
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  const std::pair<int, const void*> key(dev, reinterpret_cast<const void*>(kernel));
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count(key)) return;
   GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  done.insert(key);
 }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -274,8 +295,66 @@ void ImageContext::fused_blur(const float* in, float* out, int nplanes, int id) 
 #undef GB_BLUR_CASE
 }
 
+namespace {
+bool graphs_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("GB200_GRAPH");  // GB200_GRAPH=0: plain launches
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+}  // namespace
+
 // S1..S13 on the linear RGB planes in lin_ (butteraugli::ButteraugliComparator::Diffmap).
 float ImageContext::fused_compare_tail() {
+  const bool strips = comm_ && comm_->world() > 1;
+  // First call: plain launches (creates the tensor maps, sets the kernel attributes).  Second
+  // call: the same sequence is captured into a graph; from then on it is replayed.
+  const bool use_graph = graphs_enabled() && !strips && !profiling_on();
+  if (use_graph && fused_->compare_graph != nullptr) {
+    GB_CUDA(cudaGraphLaunch(fused_->compare_graph, s_));
+    add_launches(fused_->compare_graph_kernels);
+  } else if (use_graph && fused_->compare_calls >= 1) {
+    const long before = total_launches();
+    GB_CUDA(cudaStreamBeginCapture(s_, cudaStreamCaptureModeThreadLocal));
+    cudaGraph_t graph = nullptr;
+    try {
+      fused_compare_launches();
+    } catch (...) {
+      cudaStreamEndCapture(s_, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    GB_CUDA(cudaStreamEndCapture(s_, &graph));
+    const long recorded = total_launches() - before;
+    add_launches(-recorded);  // recorded, not run
+    cudaError_t e = cudaGraphInstantiate(&fused_->compare_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+    fused_->compare_graph_kernels = recorded;
+    GB_CUDA(cudaGraphLaunch(fused_->compare_graph, s_));
+    add_launches(recorded);
+  } else {
+    fused_compare_launches();
+  }
+  ++fused_->compare_calls;
+  if (strips) {
+    gather_blocks(block_max_, sizeof(float));  // strip mode: one float per block crosses NVLink
+    const int lanes = 1024;
+    launch_1d(s_, PartialMax{block_max_, partial_, g_.nblocks, lanes}, lanes, "partial_max");
+    float part[1024];
+    d2h(part, partial_, sizeof(part), s_);
+    float m = 0.0f;
+    for (int i = 0; i < lanes; ++i) m = std::max(m, part[i]);
+    return m;
+  }
+  float m = 0.0f;
+  d2h(&m, d_gmax_, sizeof(float), s_);
+  return m;
+}
+
+// the stream work of one Compare after the render: no host synchronisation inside
+void ImageContext::fused_compare_launches() {
   const PlaneGeom pg{g_.w, g_.h, g_.pitch, g_.plane, cr_lo_, cr_hi_};
   const size_t P = g_.plane;
   const int rows = cr_hi_ - cr_lo_;
@@ -338,19 +417,6 @@ float ImageContext::fused_compare_tail() {
     launch_tma_2d<GB_R_FINAL, 1>(s_, fused_->map(dm_ + P, 1, C::SWI, C::HI, g_), t_.blur[kBlurFinal], pg, ht_, kBlurFinal, ef,
                                  "final_fused");
   }
-  if (strips) {
-    gather_blocks(block_max_, sizeof(float));  // strip mode: one float per block crosses NVLink
-    const int lanes = 1024;
-    launch_1d(s_, PartialMax{block_max_, partial_, g_.nblocks, lanes}, lanes, "partial_max");
-    float part[1024];
-    d2h(part, partial_, sizeof(part), s_);
-    float m = 0.0f;
-    for (int i = 0; i < lanes; ++i) m = std::max(m, part[i]);
-    return m;
-  }
-  float m = 0.0f;
-  d2h(&m, d_gmax_, sizeof(float), s_);
-  return m;
 }
 #endif  // !GB200_HOSTSIM
 

@@ -207,6 +207,7 @@ class ImageContext {
   void fused_separate(const float* xyb, float* ps, bool with_diffs);
   void fused_blur(const float* in, float* out, int nplanes, int id);
   float fused_compare_tail();
+  void fused_compare_launches();
   void fused_sup0();
   void guarded_init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int h, bool prepare_now);
   void release();

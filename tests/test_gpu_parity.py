@@ -146,6 +146,27 @@ def test_batch64_matches_golden(cuda_lib):
         assert ok and size == g["jpeg_size"] and sha == g["jpeg_sha256"] and iters == g["iterations"][0], names[i]
 
 
+def test_tiled_nccl_two_ranks():
+    """BASELINE configs[3] plumbing on real hardware: ONE image over two ranks (one process per
+    GPU, torchrun, the library's NCCL communicator), bytes equal to the reference's golden answer.
+    Needs two GPUs; tests/run_tiled_nccl.py is the per-rank program."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29537", os.path.join(here, "run_tiled_nccl.py"), "bees"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["world"] == 2 and out["bit_exact_vs_reference"]
+
+
 AB_IMAGES = [("noise", 40, 33, 2), ("gradnoise", 70, 51, 3), ("noise", 136, 200, 4), ("gradnoise", 32, 300, 5),
              ("noise", 300, 32, 6), ("gradnoise", 260, 410, 8)]
 
