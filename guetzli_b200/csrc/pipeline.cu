@@ -668,6 +668,7 @@ void ImageContext::release() {
   if (x_i32_) { dev_free(x_i32_); x_i32_ = nullptr; }
   if (x_small_) { dev_free(x_small_); x_small_ = nullptr; }
   if (j_words_) { dev_free(j_words_); j_words_ = nullptr; }
+  if (j_best_words_) { dev_free(j_best_words_); j_best_words_ = nullptr; }
   if (d_edit_i_) { dev_free(d_edit_i_); d_edit_i_ = nullptr; }
   if (d_edit_v_) { dev_free(d_edit_v_); d_edit_v_ = nullptr; }
   if (e_block_) { dev_free(e_block_); e_block_ = nullptr; }
@@ -969,30 +970,41 @@ void ImageContext::zeroing_orders(float block_error_limit, int lookahead, bool n
   gather_blocks(d_idx, 192);
   gather_blocks(d_err, 192 * sizeof(float));
   gather_blocks(d_cnt, sizeof(int));
-  idx->resize(slots);
-  err->resize(slots);
   count->resize(g_.nblocks);
-  d2h(idx->data(), d_idx, slots, s_);
-  d2h(err->data(), d_err, slots * sizeof(float), s_);
   d2h(count->data(), d_cnt, sizeof(int) * g_.nblocks, s_);
-  // compact (block, slot) list of all candidates for the order-key kernels
-  std::vector<int> eb;
-  std::vector<uint8_t> es;
-  for (int b = 0; b < g_.nblocks; ++b)
-    for (int i = 0; i < (*count)[b]; ++i) {
-      eb.push_back(b);
-      es.push_back(static_cast<uint8_t>(i));
-    }
-  num_entries_ = eb.size();
-  if (e_block_) { dev_free(e_block_); e_block_ = nullptr; }
-  if (e_slot_) { dev_free(e_slot_); e_slot_ = nullptr; }
-  e_block_ = static_cast<int*>(dev_alloc(sizeof(int) * (num_entries_ + 1)));
-  e_slot_ = static_cast<uint8_t*>(dev_alloc(num_entries_ + 1));
-  if (num_entries_) {
-    h2d(e_block_, eb.data(), sizeof(int) * num_entries_, s_);
-    h2d(e_slot_, es.data(), num_entries_, s_);
-    stream_sync(s_);
+  // compact (block, slot) list of all candidates for the order-key kernels, built on the device
+  // from an exclusive scan of the counts
+  if (e_offset_ == nullptr) {
+    e_offset_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * (g_.nblocks + 1)));
+    owned_.push_back(e_offset_);
   }
+  unsigned long long total = 0;
+  exclusive_scan(reinterpret_cast<const unsigned int*>(d_cnt), e_offset_, g_.nblocks, &total);
+  num_entries_ = static_cast<size_t>(total);
+  if (num_entries_ + 1 > e_cap_) {
+    stream_sync(s_);
+    if (e_block_) { dev_free(e_block_); e_block_ = nullptr; }
+    if (e_slot_) { dev_free(e_slot_); e_slot_ = nullptr; }
+    e_cap_ = num_entries_ + 1;
+    e_block_ = static_cast<int*>(dev_alloc(sizeof(int) * e_cap_));
+    e_slot_ = static_cast<uint8_t*>(dev_alloc(e_cap_));
+  }
+  launch_1d(s_, FillEntries{d_cnt, e_offset_, e_block_, e_slot_}, g_.nblocks, "fill_entries");
+  if (idx != nullptr) {
+    idx->resize(slots);
+    d2h(idx->data(), d_idx, slots, s_);
+  }
+  if (err != nullptr) {
+    err->resize(slots);
+    d2h(err->data(), d_err, slots * sizeof(float), s_);
+  }
+}
+
+// the candidate errors alone (host paths of the selection walk fetch them on first use)
+void ImageContext::download_zeroing_err(std::vector<float>* err) {
+  const size_t slots = static_cast<size_t>(g_.nblocks) * 192;
+  err->resize(slots);
+  d2h(err->data(), z_err_, slots * sizeof(float), s_);
 }
 
 // Two-level radix select of the k-th smallest key, entirely on the device, then the
@@ -2083,6 +2095,32 @@ void ImageContext::jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint1
   j_nbytes_ = static_cast<size_t>((total_bits + 7) >> 3);
   *nbytes = j_nbytes_;
   *num_ff = ff;
+}
+
+void ImageContext::jpeg_keep_scan() {
+  const size_t nwords = (j_nbytes_ + 3) / 4;
+  if (nwords > j_best_cap_) {
+    stream_sync(s_);
+    if (j_best_words_) { dev_free(j_best_words_); j_best_words_ = nullptr; }
+    j_best_cap_ = nwords + nwords / 4 + 1024;
+    j_best_words_ = static_cast<unsigned int*>(dev_alloc(j_best_cap_ * sizeof(unsigned int)));
+  }
+  if (nwords) d2d(j_best_words_, j_words_, nwords * sizeof(unsigned int), s_);
+  j_best_nbytes_ = j_nbytes_;
+}
+
+void ImageContext::jpeg_fetch_kept_scan(std::vector<uint8_t>* scan) {
+  std::swap(j_words_, j_best_words_);
+  std::swap(j_nbytes_, j_best_nbytes_);
+  try {
+    jpeg_fetch_scan(scan);
+  } catch (...) {
+    std::swap(j_words_, j_best_words_);
+    std::swap(j_nbytes_, j_best_nbytes_);
+    throw;
+  }
+  std::swap(j_words_, j_best_words_);
+  std::swap(j_nbytes_, j_best_nbytes_);
 }
 
 void ImageContext::jpeg_fetch_scan(std::vector<uint8_t>* scan) {

@@ -87,8 +87,10 @@ class ImageContext {
 
   // a13+a14: greedy zeroing order of every block of the current candidate.
   // idx/err are [nblocks][192] slots, count[nblocks] valid entries each.
+  // idx / err may be null: the lists then stay on the device (download_zeroing_err later)
   void zeroing_orders(float block_error_limit, int lookahead, bool new_model, std::vector<uint8_t>* idx,
                       std::vector<float>* err, std::vector<int>* count);
+  void download_zeroing_err(std::vector<float>* err);
 
   // a16: the entries of the walk order whose keys are among (at least) the k
   // smallest, unsorted.  Needs zeroing_orders() and the weights of the latest
@@ -139,6 +141,10 @@ class ImageContext {
   // bytes among them; the bytes stay on the device until jpeg_fetch_scan().
   void jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint16_t* code, size_t* nbytes, size_t* num_ff);
   void jpeg_fetch_scan(std::vector<uint8_t>* scan);  // nbytes raw (unstuffed, padded) bytes
+  // keeps a device-side copy of the scan just encoded (the best output so far); the bytes
+  // cross PCIe once, when the search is over
+  void jpeg_keep_scan();
+  void jpeg_fetch_kept_scan(std::vector<uint8_t>* scan);
 
   // test hooks: run single stages on caller-provided planes (packed [n][h][w]).
   void debug_blur(const float* in, float* out, int id);
@@ -277,6 +283,8 @@ class ImageContext {
   int* e_block_ = nullptr;      // [entries] block of every candidate (compact list)
   uint8_t* e_slot_ = nullptr;   // [entries] its slot
   size_t num_entries_ = 0;
+  size_t e_cap_ = 0;
+  unsigned int* e_offset_ = nullptr;  // [nblocks] exclusive scan of z_cnt_
   int* d_edit_i_ = nullptr;
   int16_t* d_edit_v_ = nullptr;
   size_t edit_cap_ = 0;
@@ -294,6 +302,9 @@ class ImageContext {
   unsigned int* j_words_ = nullptr;     // scan bits, big-endian 32-bit words
   size_t j_words_cap_ = 0;
   size_t j_nbytes_ = 0;
+  unsigned int* j_best_words_ = nullptr;
+  size_t j_best_cap_ = 0;
+  size_t j_best_nbytes_ = 0;
   void exclusive_scan(const unsigned int* in, unsigned int* out, int n, unsigned long long* total);
   // same with caller-provided scratch for the per-CTA sums (n / 1024 + 8 words)
   void exclusive_scan_with(const unsigned int* in, unsigned int* out, int n, unsigned long long* total,

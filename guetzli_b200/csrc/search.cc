@@ -196,7 +196,16 @@ class Search {
         for (int k = 0; k < 64; ++k) best_q[c][k] = 1;
     }
     set_global_quant(best_q);
-    select_frequency_masking(1.0);
+    try {
+      select_frequency_masking(1.0);
+    } catch (...) {
+      try {
+        finish_output();  // like the reference, leave the best output found so far
+      } catch (...) {
+      }
+      throw;
+    }
+    finish_output();
     (void)target;
   }
 
@@ -274,6 +283,18 @@ class Search {
     memcpy(sfm_dc_hist_, hist, sizeof(sfm_dc_hist_));
   }
 
+  // the best candidate's bytes: kept scan + its headers (g/processor.cc:139-148 keeps the string)
+  void finish_output() {
+    if (!have_best_) return;
+    Clock::time_point t0 = Clock::now();
+    std::vector<uint8_t> scan;
+    ctx_->jpeg_fetch_kept_scan(&scan);
+    *best_ = assemble_jpeg(best_plan_, scan.data(), scan.size());
+    have_best_ = false;
+    st_->ms_jpeg += ms_since(t0);
+    if (best_->size() != best_bytes_) throw std::runtime_error("device JPEG size mismatch");
+  }
+
   std::string fetch_encoded() {
     Clock::time_point t0 = Clock::now();
     std::vector<uint8_t> scan;
@@ -299,8 +320,12 @@ class Search {
     const double score = score_jpeg(distance_, static_cast<int>(encoded_bytes), params_.butteraugli_target);
     logf(" Score[%.4f]", score);
     if (score < best_score_ || best_score_ < 0) {
-      *best_ = fetch_encoded();
-      if (best_->size() != encoded_bytes) throw std::runtime_error("device JPEG size mismatch");
+      // the scan stays on the device (one device-to-device copy); it is fetched and wrapped
+      // into the file once, by finish_output()
+      ctx_->jpeg_keep_scan();
+      best_plan_ = plan_;
+      best_bytes_ = encoded_bytes;
+      have_best_ = true;
       best_score_ = score;
       logf(" (*)");
     }
@@ -634,6 +659,8 @@ class Search {
       size_t total = 0, before = 0;
       const size_t n_mid = ctx_->walk_select_split(direction, i0 - pre, rank_hi, &before, &total);
       split_count = true;
+      dbg_n_[1] += n_mid;
+      if (n_mid > dbg_mid_max_) dbg_mid_max_ = n_mid;
       if (total != order_size) throw std::runtime_error("walk_select_split: entry count mismatch");
       base = before;
       n_slice = n_mid;
@@ -762,19 +789,18 @@ class Search {
     {
       Clock::time_point t0 = Clock::now();
       std::vector<uint8_t> idx;
-      std::vector<float> err;
-      ctx_->zeroing_orders(params_.butteraugli_target, params_.zeroing_greedy_lookahead, params_.new_zeroing_model, &idx, &err,
-                           &count);
+      // the candidate errors stay on the device; only the host paths of the walk want them
+      ctx_->zeroing_orders(params_.butteraugli_target, params_.zeroing_greedy_lookahead, params_.new_zeroing_model, &idx,
+                           nullptr, &count);
       size_t total = 0;
       for (int b = 0; b < num_blocks; ++b) total += count[b];
       m.cand_idx.reserve(total);
-      m.cand_err.reserve(total);
       for (int b = 0; b < num_blocks; ++b) {
         m.offsets[b] = static_cast<int>(m.cand_idx.size());
         m.cand_idx.insert(m.cand_idx.end(), &idx[static_cast<size_t>(b) * 192], &idx[static_cast<size_t>(b) * 192] + count[b]);
-        m.cand_err.insert(m.cand_err.end(), &err[static_cast<size_t>(b) * 192], &err[static_cast<size_t>(b) * 192] + count[b]);
       }
       m.offsets[num_blocks] = static_cast<int>(m.cand_idx.size());
+      m.cand_err.clear();
       st_->ms_zeroing += ms_since(t0);
     }
 
@@ -885,6 +911,14 @@ class Search {
           }
           ctx_->download_weights(block_weight.data());
           have_weights = true;
+          if (m.cand_err.empty() && !m.cand_idx.empty()) {
+            std::vector<float> err;
+            ctx_->download_zeroing_err(&err);
+            m.cand_err.reserve(m.cand_idx.size());
+            for (int b = 0; b < num_blocks; ++b)
+              m.cand_err.insert(m.cand_err.end(), &err[static_cast<size_t>(b) * 192],
+                                &err[static_cast<size_t>(b) * 192] + (m.offsets[b + 1] - m.offsets[b]));
+          }
         }
         const bool device_done = device_done_;
         // Fast path ("down" iterations consume a tiny prefix of the order): fetch only
@@ -1071,8 +1105,8 @@ class Search {
     if (getenv("GB200_TIE_DEBUG"))
       fprintf(stderr,
               "device walks %d; ms: exact prefix %.1f, select+sort+fetch %.1f, bulk %.1f, gather %.1f, window walk %.1f, "
-              "advance %.1f, weights+stats %.1f, scatter %.1f, mirror sync %.1f\n",
-              device_walks_, dt_[0], dt_[1], dt_[2], dt_[3], dt_[4], dt_[5], dt_[6], dt_[7], dt_[8]);
+              "advance %.1f, weights+stats %.1f, scatter %.1f, mirror sync %.1f; middle lists: %zu entries in all, largest %zu\n",
+              device_walks_, dt_[0], dt_[1], dt_[2], dt_[3], dt_[4], dt_[5], dt_[6], dt_[7], dt_[8], dbg_n_[1], dbg_mid_max_);
     if (getenv("GB200_TIE_DEBUG"))
       fprintf(stderr, "tie fallbacks %d: run-at-refresh %d, run-at-test %d, pair-at-refresh %d, pair-untestable %d, pair-decides %d; exact %d partial %d\n",
               tie_fallbacks_, tie_why_[1], tie_why_[2], tie_why_[3], tie_why_[4], tie_why_[5], st_->order_exact,
@@ -1095,6 +1129,9 @@ class Search {
   CoeffImage img_;
   std::vector<int16_t> cand_;
   JpegPlan plan_;
+  JpegPlan best_plan_;
+  size_t best_bytes_ = 0;
+  bool have_best_ = false;
   size_t scan_bytes_ = 0;
   std::vector<std::pair<int, float> > order_buf_;
   int device_order_checked_ = 0;
@@ -1115,6 +1152,7 @@ class Search {
   int tie_why_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double dbg_ms_[4] = {0, 0, 0, 0};   // GB200_TIE_DEBUG: device top-K fetch, exact-order build
   size_t dbg_n_[2] = {0, 0};
+  size_t dbg_mid_max_ = 0;
   unsigned int sfm_dc_hist_[3][257];
   bool jpeg_source_ = false;
   int q_in_[3][64];

@@ -123,6 +123,22 @@ struct Select2Level1 {  // one invocation
   }
 };
 
+// compact list of all candidates: entry offset[b] + i  ->  (block b, slot i), i < cnt[b]
+struct FillEntries {
+  const int* cnt;
+  const unsigned int* offset;
+  int* entry_block;
+  uint8_t* entry_slot;
+  GB_HD void operator()(int b) const {
+    const int n = cnt[b];
+    const unsigned int o = offset[b];
+    for (int i = 0; i < n; ++i) {
+      entry_block[o + i] = b;
+      entry_slot[o + i] = static_cast<uint8_t>(i);
+    }
+  }
+};
+
 // number of order keys below a limit (the partition_point of g/processor.cc:690-698)
 struct CountKeysBelow {
   OrderKeyCommon c;

@@ -9,6 +9,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 # every frequency-masking iteration also runs the device histogram pass and checks the
 # host-maintained symbol histograms against it (search.cc, encoded_size)
 os.environ.setdefault("GB200_CHECK_HOST_HIST", "1")
+# The CPU port runs its emulated kernels as OpenMP loops, thousands of tiny parallel regions per
+# image: with spinning waits they crawl whenever the box is busy (another job on one core is
+# enough), so the workers sleep instead and the team stays small.
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+os.environ.setdefault("OMP_NUM_THREADS", str(max(1, min(4, len(os.sched_getaffinity(0))))))
 
 
 def pytest_configure(config):
