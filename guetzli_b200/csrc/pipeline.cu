@@ -1574,6 +1574,8 @@ size_t ImageContext::walk_count_below(int direction, float limit) {
   return n;
 }
 
+static const size_t kMiddleSortMax = 65536;
+
 size_t ImageContext::walk_select_split(int direction, size_t rank_lo, size_t rank_hi, size_t* before, size_t* total) {
   // d_hist_ holds 2048 bins + the old select state; the pair of level-1 histograms and the
   // two-rank state live in w_sel2_
@@ -1641,12 +1643,28 @@ size_t ImageContext::walk_select_split(int direction, size_t rank_lo, size_t ran
   *before = got.before_lo;
   const size_t n_mid = got.kept_hi >= got.before_lo ? got.kept_hi - got.before_lo : 0;
   if (got.mid_count != n_mid) throw std::runtime_error("select2: middle count mismatch");
-  if (n_mid > sel_cap_) throw std::runtime_error("select2: middle list overflow");
-  sel_sorted_ = n_mid;
-  sort_selection(n_mid);
+  if (n_mid > sel_cap_ && n_mid <= kMiddleSortMax) throw std::runtime_error("select2: middle list overflow");
   split_pending_ = true;
   pending_bulk_extra_ = got.before_lo;
+  if (n_mid > kMiddleSortMax) {
+    // a huge run of equal keys sits on one of the two ranks: the caller cannot use this
+    // selection (it takes the reference-ordered path) and must cancel it
+    sel_sorted_ = 0;
+    return n_mid;
+  }
+  sel_sorted_ = n_mid;
+  sort_selection(n_mid);
   return n_mid;
+}
+
+// drops the per-block counts of a walk_select_split that no bulk will consume
+void ImageContext::walk_split_cancel() {
+  if (!split_pending_) return;
+  unsigned int n_touched = 0;
+  d2h(&n_touched, w_counters_, sizeof(unsigned int), s_);
+  if (n_touched) launch_1d(s_, ResetCounts{w_touched_, w_cnt_}, static_cast<int>(n_touched), "walk_split_cancel");
+  split_pending_ = false;
+  pending_bulk_extra_ = 0;
 }
 
 size_t ImageContext::walk_select_sorted(int direction, size_t want, size_t* total) {

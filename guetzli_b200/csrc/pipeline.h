@@ -116,6 +116,8 @@ class ImageContext {
   // bulk right away, the entries between the two ranks (the "middle") are left sorted in the
   // resident selection.  *before = entries already counted, -> size of the middle.
   size_t walk_select_split(int direction, size_t rank_lo, size_t rank_hi, size_t* before, size_t* total);
+  static size_t walk_middle_max() { return 65536; }  // larger middles come back unsorted: cancel them
+  void walk_split_cancel();
   void walk_fetch_sorted(size_t first, size_t n, float* val, int* block);
   struct BulkResult {
     int touched, logged, chroma_delta;

@@ -665,11 +665,15 @@ class Search {
       base = before;
       n_slice = n_mid;
       usable_end = n_slice;
+      if (n_mid > ImageContext::walk_middle_max()) {
+        // a huge run of equal keys around the end of the bulk: only the reference's own
+        // arrangement can split it
+        ctx_->walk_split_cancel();
+        st_->ms_sort += ms_since(t0);
+        return 0;
+      }
       if (before + pre > i0 || (before + n_mid < i0 + 64 && before + n_mid < order_size)) {
-        // cannot use it: consume the pending counts and roll them back
-        ImageContext::BulkResult dummy;
-        ctx_->walk_bulk_apply(direction, 0, &dummy, nullptr, true);
-        ctx_->walk_bulk_undo(direction);
+        ctx_->walk_split_cancel();
         st_->ms_sort += ms_since(t0);
         return -1;
       }

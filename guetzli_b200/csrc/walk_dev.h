@@ -179,6 +179,12 @@ struct Select2Split {
   }
 };
 
+struct ResetCounts {
+  const int* touched;
+  unsigned int* cnt;
+  GB_HD void operator()(int j) const { cnt[touched[j]] = 0u; }
+};
+
 // how many of the first `n` sorted entries belong to each block; first toucher lists the block
 struct BulkCount {
   const int* sel_block;
