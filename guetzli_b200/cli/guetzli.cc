@@ -38,7 +38,11 @@ struct Options {
       "                 Default value is %d.\n"
       "  --memlimit M - Memory limit in MB. Guetzli will fail if unable to stay under\n"
       "                 the limit. Default limit is %d MB.\n"
-      "  --nomemlimit - Do not limit memory usage.\n";
+      "  --nomemlimit - Do not limit memory usage.\n"
+      "\n"
+      "This build (guetzli_b200) encodes YUV444 only: JPEG input with 4:2:0 chroma\n"
+      "subsampling is refused (\"YUV420 JPEG input is outside the B200 hot path\");\n"
+      "convert such files to PNG first.\n";
   const Options defaults;
   fprintf(stderr, kText, defaults.quality, defaults.memlimit_mb);
   exit(1);

@@ -70,6 +70,12 @@ inline bool ReadPNGRGBA(const std::string& data, int* xsize, int* ysize, std::ve
     if (pos + 12 + static_cast<size_t>(len) > data.size()) return false;
     const uint8_t* type = p + pos + 4;
     const uint8_t* body = p + pos + 8;
+    // libpng treats a CRC mismatch in a critical chunk (upper-case first letter) as an error
+    if ((type[0] & 0x20) == 0) {
+      const uint32_t want_crc = be32(body + len);
+      const uint32_t got_crc = static_cast<uint32_t>(crc32(crc32(0L, Z_NULL, 0), type, static_cast<uInt>(len + 4)));
+      if (want_crc != got_crc) return false;
+    }
     if (!memcmp(type, "IHDR", 4)) {
       if (len != 13) return false;
       w = be32(body);
@@ -91,7 +97,9 @@ inline bool ReadPNGRGBA(const std::string& data, int* xsize, int* ysize, std::ve
     }
     pos += 12 + len;
   }
-  if (!seen_iend || w == 0 || h == 0 || w > (1u << 24) || h > (1u << 24) || interlace > 1) return false;
+  // Guetzli itself refuses 65536 pixels and more per side (g/jpeg_data_encoder.cc:68): nothing
+  // larger is ever decoded, whatever the header claims
+  if (!seen_iend || w == 0 || h == 0 || w > 65535u || h > 65535u || interlace > 1) return false;
   int channels;
   switch (ctype) {
     case 0: channels = 1; break;
@@ -107,7 +115,21 @@ inline bool ReadPNGRGBA(const std::string& data, int* xsize, int* ysize, std::ve
   const int bits_pp = channels * depth;
   const int bpp = (bits_pp + 7) / 8;
 
-  // inflate
+  // size of the filtered image data the header promises (per Adam7 pass when interlaced)
+  size_t expect_raw = 0;
+  if (!interlace) {
+    expect_raw = static_cast<size_t>(h) * ((static_cast<size_t>(w) * bits_pp + 7) / 8 + 1);
+  } else {
+    static const int xs0[7] = {0, 4, 0, 2, 0, 1, 0}, ys0[7] = {0, 0, 4, 0, 2, 0, 1};
+    static const int dxs0[7] = {8, 8, 4, 4, 2, 2, 1}, dys0[7] = {8, 8, 8, 4, 4, 2, 2};
+    for (int pass = 0; pass < 7; ++pass) {
+      const long pw = (static_cast<long>(w) - xs0[pass] + dxs0[pass] - 1) / dxs0[pass];
+      const long ph = (static_cast<long>(h) - ys0[pass] + dys0[pass] - 1) / dys0[pass];
+      if (pw <= 0 || ph <= 0) continue;
+      expect_raw += static_cast<size_t>(ph) * ((static_cast<size_t>(pw) * bits_pp + 7) / 8 + 1);
+    }
+  }
+  // inflate, never past the promised size (a small file must not expand without bound)
   std::vector<uint8_t> raw;
   {
     z_stream zs;
@@ -126,9 +148,14 @@ inline bool ReadPNGRGBA(const std::string& data, int* xsize, int* ysize, std::ve
         return false;
       }
       raw.insert(raw.end(), buf, buf + (sizeof(buf) - zs.avail_out));
+      if (raw.size() > expect_raw) {
+        inflateEnd(&zs);
+        return false;
+      }
     } while (rc != Z_STREAM_END);
     inflateEnd(&zs);
   }
+  if (raw.size() != expect_raw) return false;  // before any image-sized allocation
 
   // samples[y][x][ch] as 16-bit values at native depth
   std::vector<uint16_t> samples(static_cast<size_t>(w) * h * channels);
@@ -205,10 +232,13 @@ inline bool ReadPNGRGBA(const std::string& data, int* xsize, int* ysize, std::ve
       }
       case 3: {
         const size_t idx = s[0];
-        if (3 * idx + 2 >= plte.size() + 0 && 3 * idx + 2 >= plte.size()) return false;
-        r = plte[3 * idx];
-        g = plte[3 * idx + 1];
-        b = plte[3 * idx + 2];
+        if (3 * idx + 2 < plte.size()) {
+          r = plte[3 * idx];
+          g = plte[3 * idx + 1];
+          b = plte[3 * idx + 2];
+        } else {
+          r = g = b = 0;  // libpng: its 256-entry palette is zero-filled beyond PLTE (it only warns)
+        }
         if (have_trns && idx < trns.size()) a = trns[idx];
         break;
       }

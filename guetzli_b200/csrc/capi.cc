@@ -24,6 +24,7 @@ namespace gb200 {
 struct ThreadGroup;
 ThreadGroup* thread_group_create(int world);
 void thread_group_destroy(ThreadGroup* g);
+void thread_group_abort(ThreadGroup* g);
 Comm* thread_comm_create(ThreadGroup* g, int rank);
 #if !defined(GB200_HOSTSIM)
 void nccl_unique_id(uint8_t out[128]);
@@ -333,6 +334,7 @@ int gb200_process_rgb_tiled_threads(const gb200_params* params, const uint8_t* r
         } catch (const std::exception& e) {
           what[r] = e.what();
           oks[r] = -1;
+          gb200::thread_group_abort(group);  // the other ranks leave their barriers with an error
         }
         delete comm;
       });
@@ -377,6 +379,8 @@ gb200_image* gb200_image_create2(const uint8_t* rgb, int w, int h, int device, i
   gb200_image* img = nullptr;
   guarded([&]() {
     if (!rgb || w <= 0 || h <= 0 || w >= 65536 || h >= 65536) throw std::runtime_error("bad image size");
+    std::string why;
+    if (!gb200::image_size_supported(w, h, &why)) throw std::runtime_error(why);
     gb200::ImageContext* ctx = new gb200::ImageContext(rgb, w, h, device, prepare != 0);
     img = new gb200_image;
     img->ctx = ctx;

@@ -26,15 +26,24 @@ struct ThreadGroup {
   long generation = 0;
   std::vector<void*> bufs;
   explicit ThreadGroup(int w) : world(w), bufs(w, nullptr) {}
+  bool aborted = false;
+  // a rank that failed calls this so that the others do not wait for it forever
+  void abort() {
+    std::lock_guard<std::mutex> lock(mu);
+    aborted = true;
+    cv.notify_all();
+  }
   void barrier() {
     std::unique_lock<std::mutex> lock(mu);
+    if (aborted) throw std::runtime_error("strip mode: another rank failed");
     const long gen = generation;
     if (++arrived == world) {
       arrived = 0;
       ++generation;
       cv.notify_all();
     } else {
-      cv.wait(lock, [&] { return generation != gen; });
+      cv.wait(lock, [&] { return generation != gen || aborted; });
+      if (generation == gen) throw std::runtime_error("strip mode: another rank failed");
     }
   }
 };
@@ -64,6 +73,7 @@ class ThreadComm : public Comm {
 };
 
 ThreadGroup* thread_group_create(int world) { return new ThreadGroup(world); }
+void thread_group_abort(ThreadGroup* g) { g->abort(); }
 void thread_group_destroy(ThreadGroup* g) { delete g; }
 Comm* thread_comm_create(ThreadGroup* g, int rank) { return new ThreadComm(g, rank); }
 

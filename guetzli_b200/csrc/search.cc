@@ -1182,6 +1182,22 @@ static bool check_params(const SearchParams& params, std::string* err) {
   return true;
 }
 
+// Flat coefficient indices and the candidate-list offsets are 32-bit: refuse larger images up
+// front with a clear message instead of overflowing after all device memory is allocated.
+// (The scan's 32-bit bit offsets are checked where the scan size is known, jpeg_encode_scan.)
+bool image_size_supported(int w, int h, std::string* err) {
+  const long long nblocks = static_cast<long long>((w + 7) / 8) * ((h + 7) / 8);
+  if (nblocks * 192 >= (1ll << 31)) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "guetzli_b200: image too large (%d x %d): at most %lld 8x8 blocks are supported\n", w, h,
+             (1ll << 31) / 192 - 1);
+    *err = buf;
+    fputs(buf, stderr);
+    return false;
+  }
+  return true;
+}
+
 namespace {
 // What process_jpeg knows about its input beyond the coefficients.
 struct JpegSource {
@@ -1280,6 +1296,7 @@ bool process_jpeg(const SearchParams& params, const uint8_t* data, size_t len, i
   if (!jpg.is_444())
     return fail("guetzli_b200: YUV420 JPEG input is outside the B200 hot path (DESIGN.md); provide 4:4:4 or PNG\n");
 
+  if (!image_size_supported(jpg.width, jpg.height, err)) return false;
   Clock::time_point t0 = Clock::now();
   const long long h2d0 = h2d_bytes_total();
   JpegSource src;
@@ -1336,6 +1353,7 @@ bool process_rgb_tiled(const SearchParams& params, const uint8_t* rgb, int w, in
     fputs(err->c_str(), stderr);
     return false;
   }
+  if (!image_size_supported(w, h, err)) return false;
   Clock::time_point t0 = Clock::now();
   const long long h2d0 = h2d_bytes_total();
   ImageContext ctx(rgb, w, h, device, false, comm);

@@ -58,6 +58,9 @@ bool process_jpeg(const SearchParams& params, const uint8_t* data, size_t len, i
 bool process_rgb(const SearchParams& params, const uint8_t* rgb, int w, int h, int device, LogSink log,
                  void* log_user, std::string* jpeg_out, SearchStats* stats, std::string* err);
 
+// false + message when the image needs more than the 32-bit indices of the device lists
+bool image_size_supported(int w, int h, std::string* err);
+
 // ScoreJPEG (g/score.cc:23).
 double score_jpeg(double distance, int size, double target);
 

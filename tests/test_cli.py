@@ -67,6 +67,48 @@ def test_png_reader_matches_pil(tmp_path, port_lib):
     assert subprocess.run([PNG_DUMP, os.devnull]).returncode != 0
 
 
+def _png_chunk(kind, body):
+    import zlib
+    return struct.pack(">I", len(body)) + kind + body + struct.pack(">I", zlib.crc32(kind + body) & 0xffffffff)
+
+
+def test_png_reader_rejects_hostile_files(tmp_path, port_lib):
+    """The hand-written PNG reader must fail cleanly, before any image-sized allocation, on a
+    header that promises more than the data delivers, on data that inflates past what the
+    header promises, on oversized dimensions and on a corrupted critical chunk."""
+    import zlib
+    magic = b"\x89PNG\r\n\x1a\n"
+
+    def png(w, h, raw, ctype=2, depth=8):
+        ihdr = struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0)
+        return magic + _png_chunk(b"IHDR", ihdr) + _png_chunk(b"IDAT", zlib.compress(raw)) + _png_chunk(b"IEND", b"")
+
+    row = lambda w: b"\x00" + bytes(3 * w)
+    cases = {
+        "ok": (png(4, 3, row(4) * 3), True),
+        "huge_header_tiny_data": (png(60000, 60000, row(4) * 3), False),   # would be 10.8 GB of samples
+        "zip_bomb": (png(4, 3, bytes(50 * 1024 * 1024)), False),           # inflates far past 39 bytes
+        "too_wide": (png(70000, 1, b"\x00" + bytes(3 * 70000)), False),
+        "short_data": (png(4, 3, row(4) * 2), False),
+    }
+    good = png(4, 3, row(4) * 3)
+    bad_crc = bytearray(good)
+    bad_crc[8 + 8 + 3] ^= 1  # a byte of IHDR's body: CRC no longer matches
+    cases["bad_crc"] = (bytes(bad_crc), False)
+    for name, (data, ok) in cases.items():
+        p = tmp_path / f"{name}.png"
+        p.write_bytes(data)
+        r = subprocess.run([PNG_DUMP, str(p)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+        assert (r.returncode == 0) == ok, name
+    # palette index beyond PLTE: libpng keeps a zero-filled 256-entry palette, i.e. black
+    ihdr = struct.pack(">IIBBBBB", 2, 1, 8, 3, 0, 0, 0)
+    pal = magic + _png_chunk(b"IHDR", ihdr) + _png_chunk(b"PLTE", bytes([10, 20, 30])) + \
+        _png_chunk(b"IDAT", zlib.compress(b"\x00\x00\x05")) + _png_chunk(b"IEND", b"")
+    p = tmp_path / "pal_oob.png"
+    p.write_bytes(pal)
+    assert np.array_equal(dump(str(p)), np.array([[[10, 20, 30], [0, 0, 0]]], dtype=np.uint8))
+
+
 @pytest.mark.gpu
 def test_cli_smoke_matrix(tmp_path, cuda_lib):
     bees = parity.golden_input("bees_444x258_q95")

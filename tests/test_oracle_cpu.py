@@ -2,6 +2,8 @@
 path (oracle/_build/libguetzli_port.so, same kernel bodies as the CUDA product)
 is checked against the unmodified reference (oracle/_ref) stage by stage and
 end to end, and against the committed golden answers."""
+import os
+
 import numpy as np
 import pytest
 
@@ -92,6 +94,33 @@ def test_partial_order_is_arrangement_independent(port_lib, ref, monkeypatch):
         ok, jpeg, trace, st = parity.run_process(port_lib, rgb, 95)
         assert st.device["order_partial"] > 50
         assert trace == rtrace and jpeg == rjpeg
+
+
+def test_refusals_are_pinned(port_lib, capfd):
+    """What this implementation refuses although the reference accepts it (YUV420, DESIGN.md
+    "Out of scope") and what it refuses for its own limits, with the exact messages the CLI
+    usage text and README quote."""
+    import guetzli_b200 as gb
+    rgb = synth.gradnoise(40, 40, 1)
+    for kw in ({"try_420": True}, {"force_420": True}):
+        p = gb.Params(butteraugli_target=1.0, **kw)
+        ok, jpeg = gb.process(p, None, rgb, 40, 40, lib=port_lib)
+        assert not ok and jpeg == b""
+        assert "guetzli_b200: YUV420 is outside the B200 hot path (DESIGN.md)" in capfd.readouterr().err
+    jpg420 = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg", "sub420.jpg"), "rb").read()
+    ok, jpeg = gb.process_jpeg(gb.Params(butteraugli_target=1.0), None, jpg420, lib=port_lib)
+    assert not ok and jpeg == b""
+    assert "YUV420 JPEG input is outside the B200 hot path" in capfd.readouterr().err
+    # 32-bit device indices: refused up front, nothing allocated
+    big = np.zeros(3 * 65535 * 4, dtype=np.uint8)  # the size check comes before the buffer is read
+    import ctypes as C
+    from guetzli_b200.api import _CParams, _CStats, _LOG_FN
+    cp = _CParams(1.0, 1, 0, 0, 0, 3, 1)
+    out, out_len, cs = C.POINTER(C.c_uint8)(), C.c_size_t(), _CStats()
+    ok = port_lib.gb200_process_rgb(C.byref(cp), big.ctypes.data, 65535, 65535, 0, C.cast(None, _LOG_FN), None,
+                                    C.byref(out), C.byref(out_len), C.byref(cs))
+    assert not ok and out_len.value == 0
+    assert "image too large (65535 x 65535)" in capfd.readouterr().err
 
 
 def test_port_device_walk(port_lib, ref, monkeypatch):
