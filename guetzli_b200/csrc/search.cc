@@ -654,23 +654,32 @@ class Search {
       // on the device right away; the entries from there up to the rank the window may reach
       // (the "middle") come back sorted -- their head completes the bulk, the rest is the window
       const size_t pre = 64;
-      const size_t rank_hi =
-          std::min(order_size, std::max(direction < 0 ? last_consumed : 0, i0) + std::min<size_t>(std::max<size_t>(i0 / 16, 1024), 8192));
-      size_t total = 0, before = 0;
-      const size_t n_mid = ctx_->walk_select_split(direction, i0 - pre, rank_hi, &before, &total);
+      size_t total = 0, before = 0, n_mid = 0;
+      // A long run of (nearly) equal keys just behind the window would drag all of its entries
+      // into the middle list: shrink the upper rank until the middle is small.  (A run that
+      // reaches position i0 itself cannot be avoided: the reference-ordered path then.)
+      const size_t margins[3] = {std::min<size_t>(std::max<size_t>(i0 / 16, 1024), 8192), 256, 64};
+      bool usable = false;
+      for (int attempt = 0; attempt < 3 && !usable; ++attempt) {
+        const size_t rank_hi =
+            std::min(order_size, std::max(direction < 0 && attempt == 0 ? last_consumed : 0, i0) + margins[attempt]);
+        n_mid = ctx_->walk_select_split(direction, i0 - pre, rank_hi, &before, &total);
+        if (total != order_size) throw std::runtime_error("walk_select_split: entry count mismatch");
+        dbg_n_[1] += n_mid;
+        if (n_mid > dbg_mid_max_) dbg_mid_max_ = n_mid;
+        if (n_mid > ImageContext::walk_middle_max()) {
+          ctx_->walk_split_cancel();
+        } else {
+          usable = true;
+        }
+      }
       split_count = true;
-      dbg_n_[1] += n_mid;
-      if (n_mid > dbg_mid_max_) dbg_mid_max_ = n_mid;
-      if (total != order_size) throw std::runtime_error("walk_select_split: entry count mismatch");
       base = before;
       n_slice = n_mid;
       usable_end = n_slice;
-      if (n_mid > ImageContext::walk_middle_max()) {
-        // a huge run of equal keys around the end of the bulk: only the reference's own
-        // arrangement can split it
-        ctx_->walk_split_cancel();
+      if (!usable) {
         st_->ms_sort += ms_since(t0);
-        return 0;
+        return 0;  // as if ambiguous: only the reference's own arrangement can split such a run
       }
       if (before + pre > i0 || (before + n_mid < i0 + 64 && before + n_mid < order_size)) {
         ctx_->walk_split_cancel();
@@ -781,7 +790,9 @@ class Search {
     m.edit_index.clear();
     m.edit_value.clear();
     m.edit_old.clear();
-    return out.ambiguous ? 0 : -1;
+    // ambiguous, or the fetched entries ran out: worth another try on the reference-ordered
+    // prefix (which fetches more); from there the host paths take over
+    return exact ? -1 : 0;
   }
 
   void select_frequency_masking(const double target_mul) {
