@@ -340,8 +340,16 @@ size_t estimate_dc_bytes(const CoeffImage& img) {
   return cluster_histograms(h, &num, index, depth);
 }
 
-size_t jpeg_header_bytes(const CoeffImage& img) {
-  const int ncomp = num_output_components(img);
+size_t estimate_dc_bytes_of(SymbolHistogram* dc_h, int ncomp) {
+  size_t num = ncomp;
+  int index[4];
+  uint8_t depth[3 * SymbolHistogram::kSize];
+  return cluster_histograms(dc_h, &num, index, depth);
+}
+
+size_t jpeg_header_bytes(const CoeffImage& img) { return jpeg_header_bytes(img, num_output_components(img)); }
+
+size_t jpeg_header_bytes(const CoeffImage& img, int ncomp) {
   const QuantSet qs = dedup_quant(img, ncomp);
   size_t n = 2;  // SOI
   if (img.meta == nullptr || img.meta->strip) {

@@ -86,6 +86,10 @@ void ac_symbols_of_range(const int16_t* dq_block, const int* q, int a, int b, in
 void build_ac_histograms(const CoeffImage& img, SymbolHistogram* h3);  // g/jpeg_data_writer.cc:258
 size_t estimate_dc_bytes(const CoeffImage& img);                        // g/processor.cc:528
 size_t jpeg_header_bytes(const CoeffImage& img);                        // g/jpeg_data_writer.cc:269
+// the same two when the caller already knows the component count / holds the DC histograms
+// (device symbol counts): no pass over the coefficients
+size_t jpeg_header_bytes(const CoeffImage& img, int ncomp);
+size_t estimate_dc_bytes_of(SymbolHistogram* dc_h, int ncomp);
 // g/processor.cc:497: per-component depths [3][257] + header bytes of the clustered codes.
 size_t compute_entropy_codes(const SymbolHistogram* h3, uint8_t* depths);
 size_t entropy_coded_bytes(const SymbolHistogram* h3, const uint8_t* depths);  // g/processor.cc:518

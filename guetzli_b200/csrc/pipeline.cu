@@ -1296,6 +1296,20 @@ void ImageContext::walk_weights(int direction, int radius, double target_distanc
 #endif
 }
 
+size_t ImageContext::count_nonzero_chroma() {
+  const int lanes = 8192;
+  void* buf = dev_alloc(sizeof(unsigned long long) * lanes);
+  const size_t per = static_cast<size_t>(g_.nblocks) * 64;
+  launch_1d(s_, CountNonzeroPartial{d_cand_ + per, 2 * per, lanes, static_cast<unsigned long long*>(buf)}, lanes,
+            "count_nonzero");
+  std::vector<unsigned long long> part(lanes);
+  d2h(part.data(), buf, sizeof(unsigned long long) * lanes, s_);
+  dev_free(buf);
+  unsigned long long n = 0;
+  for (int i = 0; i < lanes; ++i) n += part[i];
+  return static_cast<size_t>(n);
+}
+
 void ImageContext::download_weights(float* out) { d2h(out, weights_, sizeof(float) * g_.nblocks, s_); }
 
 #if defined(GB200_HOSTSIM)

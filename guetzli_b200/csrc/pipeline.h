@@ -108,6 +108,8 @@ class ImageContext {
   void walk_weights(int direction, int radius, double target_distance, bool zero_distmap,
                     unsigned long long* order_size, unsigned long long* blocks_to_change);
   void download_weights(float* out);
+  // nonzero coefficients of the candidate's two chroma components
+  size_t count_nonzero_chroma();
   // entries of the order whose key is below `limit`
   size_t walk_count_below(int direction, float limit);
   // at least the `want` smallest keys of the order, sorted ascending, resident; -> how many

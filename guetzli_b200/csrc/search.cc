@@ -332,17 +332,12 @@ class Search {
     logf("\n");
   }
 
-  // candidate := Quantize(original, q) on both sides of the bus
+  // candidate := Quantize(original, q) on the device; the host mirror of the candidate goes
+  // stale (the host paths of the walk refresh it when they need it)
   void set_global_quant(const int q[3][64]) {
-    const std::vector<int16_t>& orig = ctx_->orig_coeffs();
-    const size_t per = static_cast<size_t>(img_.nblocks) * 64;
-    for (int c = 0; c < 3; ++c) {
-      const int16_t* src = &orig[c * per];
-      int16_t* dst = &cand_[c * per];
-      for (size_t i = 0; i < per; ++i) dst[i] = static_cast<int16_t>(quantize_coeff(src[i], q[c][i & 63]));
-    }
     memcpy(img_.q, q, sizeof(img_.q));
     ctx_->apply_global_quant(&q[0][0]);
+    mirror_valid_ = false;
   }
 
   QuantTrial try_quant_matrix(const float target_mul, int q[3][64]) {
@@ -537,9 +532,13 @@ class Search {
           !(order[i].second < order[i + 1].second)) {
         const float key = order[i].second;
         size_t lo = i, hi = i + 1;
-        while (lo > 0 && !(order[lo - 1].second < key)) --lo;
-        while (hi + 1 < n_avail && !(key < order[hi + 1].second)) ++hi;
-        for (size_t j = lo + 1; j <= hi; ++j)
+        // a block has at most 189 entries: a run longer than that holds several blocks, no
+        // need to walk to its ends (long runs are common on smooth images)
+        const size_t kRunCap = 256;
+        while (lo > 0 && i - lo < kRunCap && !(order[lo - 1].second < key)) --lo;
+        while (hi + 1 < n_avail && hi - i < kRunCap && !(key < order[hi + 1].second)) ++hi;
+        if (i - lo >= kRunCap || hi - i >= kRunCap) straddle = true;
+        for (size_t j = lo + 1; j <= hi && !straddle; ++j)
           if (order[j].first != order[lo].first) straddle = true;
         // the run may continue beyond the fetched prefix, or begin before the fetched slice
         if (hi + 1 == n_avail && base + n_avail < n_order) straddle = true;
@@ -819,10 +818,24 @@ class Search {
       st_->ms_zeroing += ms_since(t0);
     }
 
-    m.header_size = static_cast<int>(jpeg_header_bytes(img_));
-    m.dc_size = static_cast<int>(estimate_dc_bytes(img_));
-    build_ac_histograms(img_, m.ac_h);
-    capture_dc_histograms();
+    // symbol counts of the candidate from the device (no pass over the coefficients on the host):
+    // header size, EstimateDCSize, the AC histograms the walk keeps up to date
+    {
+      unsigned int hist[6][257];
+      bool chroma = false;
+      ctx_->jpeg_histograms(&hist[0][0], &chroma);
+      memcpy(sfm_dc_hist_, hist, sizeof(sfm_dc_hist_));
+      const int ncomp0 = chroma ? 3 : 1;  // num_output_components (g/output_image.cc:357)
+      m.header_size = static_cast<int>(jpeg_header_bytes(img_, ncomp0));
+      SymbolHistogram dc_h[3];
+      for (int c = 0; c < ncomp0; ++c)
+        for (int i = 0; i < 256; ++i) dc_h[c].counts[i] = 2 * hist[c][i];
+      m.dc_size = static_cast<int>(estimate_dc_bytes_of(dc_h, ncomp0));
+      for (int c = 0; c < 3; ++c) m.ac_h[c].clear();
+      for (int c = 0; c < ncomp0; ++c)
+        for (int i = 0; i < 256; ++i) m.ac_h[c].counts[i] = 2 * hist[3 + c][i];
+      chroma_nz_ = static_cast<long long>(ctx_->count_nonzero_chroma());
+    }
     m.ac_depths.resize(3 * SymbolHistogram::kSize);
     m.ac_histogram_size = static_cast<int>(compute_entropy_codes(m.ac_h, m.ac_depths.data()));
     const int base_size = m.header_size + m.dc_size + m.ac_histogram_size +
@@ -837,12 +850,6 @@ class Search {
     // The candidate cursors and max errors also live on the device (walk_dev.h); the host
     // copies above (and cand_) are a mirror that iterations on the device path leave stale.
     ctx_->walk_begin();
-    mirror_valid_ = true;
-    {
-      const size_t per = static_cast<size_t>(img_.nblocks) * 64;
-      chroma_nz_ = 0;
-      for (size_t i = per; i < 3 * per; ++i) chroma_nz_ += cand_[i] != 0 ? 1 : 0;
-    }
     fetched_.assign(num_blocks, 0);
     fetched_list_.clear();
     // GB200_WALK=host keeps every iteration on the host path, =device forces the device path.

@@ -123,6 +123,19 @@ struct Select2Level1 {  // one invocation
   }
 };
 
+// nonzero coefficients of a coefficient range, summed by `lanes` lanes
+struct CountNonzeroPartial {
+  const int16_t* coeffs;
+  size_t n;
+  int lanes;
+  unsigned long long* out;
+  GB_HD void operator()(int i) const {
+    unsigned long long c = 0;
+    for (size_t k = static_cast<size_t>(i); k < n; k += static_cast<size_t>(lanes)) c += coeffs[k] != 0 ? 1u : 0u;
+    out[i] = c;
+  }
+};
+
 // compact list of all candidates: entry offset[b] + i  ->  (block b, slot i), i < cnt[b]
 struct FillEntries {
   const int* cnt;
