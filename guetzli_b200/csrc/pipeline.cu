@@ -1199,6 +1199,122 @@ __global__ void __launch_bounds__(1024) k_select2_level1(const unsigned int* his
   }
 }
 
+// BulkApply (walk_dev.h), one WARP per touched block.  The nonzero pattern of the block's 64
+// coefficients in zig-zag order is a 64-bit mask (two ballots), so the neighbours of the edited
+// coefficient are bit scans and the symbols of the affected range -- it holds at most two nonzero
+// coefficients -- follow in closed form; lane 0 does that scalar part.  Same effects as the
+// functor (symbol deltas, undo log, cursor, chroma count), which stays the CPU port's version;
+// the symbol deltas are privatised per CTA.
+__device__ __forceinline__ void warp_emit_run_symbol(unsigned int* h, int run, int value_over_q, unsigned int weight) {
+  while (run > 15) {
+    atomicAdd(&h[0xf0], weight);
+    run -= 16;
+  }
+  const int nbits = 32 - __clz(static_cast<unsigned int>(value_over_q < 0 ? -value_over_q : value_over_q));
+  atomicAdd(&h[(run << 4) + nbits], weight);
+}
+
+// symbols of zig-zag positions (za, zb] given the coefficient at zp (0 = none) and at zb (if zb < 64)
+__device__ __forceinline__ void warp_range_symbols(unsigned int* h, int za, int zp, int zb, int at_zp_over_q,
+                                                   int at_zb_over_q, unsigned int weight) {
+  int last_nz = za;
+  if (at_zp_over_q != 0) {
+    warp_emit_run_symbol(h, zp - za - 1, at_zp_over_q, weight);
+    last_nz = zp;
+  }
+  if (zb < 64) {
+    warp_emit_run_symbol(h, zb - last_nz - 1, at_zb_over_q, weight);
+  } else if (63 - last_nz > 0) {
+    atomicAdd(&h[0], weight);  // end of block
+  }
+}
+
+__global__ void __launch_bounds__(128) k_bulk_apply_warp(BulkApply a, int n) {
+  __shared__ unsigned int sh[3 * 256 + 1];
+  for (int i = threadIdx.x; i < 3 * 256 + 1; i += 128) sh[i] = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (j < n) {
+    const int b = a.touched[j];
+    const int count = static_cast<int>(a.cnt[b]);
+    const size_t per = static_cast<size_t>(a.s.nblocks) * 64;
+    const int z0 = lane, z1 = lane + 32;                    // this lane's two zig-zag positions
+    const int n0 = a.s.zz2nat[z0], n1 = a.s.zz2nat[z1];     // ... and their natural indices
+    int li = a.s.last_index[b];
+    for (int t = 0; t < count; ++t) {
+      const int idx = a.s.z_idx[static_cast<size_t>(b) * 192 + li + (a.direction < 0 ? -1 : 0)];
+      const int c = idx >> 6, k = idx & 63;
+      const int* qc = a.s.q + 64 * c;
+      const int16_t* ob = a.s.orig + c * per + static_cast<size_t>(b) * 64;
+      int16_t* blk = a.s.cand + c * per + static_cast<size_t>(b) * 64;
+      const int v0 = blk[n0], v1 = blk[n1];
+      const unsigned int m_lo = __ballot_sync(0xffffffffu, v0 != 0), m_hi = __ballot_sync(0xffffffffu, v1 != 0);
+      const unsigned long long mask = (static_cast<unsigned long long>(m_hi) << 32) | m_lo;
+      const int zp = a.s.nat2zz[k];
+      // neighbours: highest nonzero below zp (never the DC position 0), lowest above
+      const unsigned long long below = mask & ((1ull << zp) - 1ull) & ~1ull;
+      const int za = below ? 63 - __clzll(static_cast<long long>(below)) : 0;
+      const unsigned long long above = zp < 63 ? (mask >> (zp + 1)) : 0ull;
+      const int zb = above ? zp + 1 + (__ffsll(static_cast<long long>(above)) - 1) : 64;
+      // precious rule (g/processor.cc:722-733): sum of |original| over the high frequencies
+      bool precious = false;
+      if (k == 1 || k == 8) {
+        int s = 0;
+        {
+          const int i0 = lane, i1 = lane + 32;  // natural indices 0..63
+          if (i0 >= 3 && !((i0 & 7) < 3 && i0 < 24)) {
+            const int v = ob[i0];
+            s += v < 0 ? -v : v;
+          }
+          if (!((i1 & 7) < 3 && i1 < 24)) {
+            const int v = ob[i1];
+            s += v < 0 ? -v : v;
+          }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        const int limit = s < 60 ? 4 : 8;
+        const int ok = ob[k];
+        precious = (ok < 0 ? -ok : ok) >= limit;
+      }
+      if (lane == 0) {
+        const int newval = a.direction > 0 ? 0 : quantize_coeff(ob[k], qc[k]);
+        const bool store = !precious || newval != 0;
+        const int old = blk[k];
+        const int at_zb = zb < 64 ? blk[a.s.zz2nat[zb]] / qc[a.s.zz2nat[zb]] : 0;
+        unsigned int* h = sh + 256 * c;
+        warp_range_symbols(h, za, zp, zb, old != 0 ? old / qc[k] : 0, at_zb, 0xffffffffu);
+        int now = old;
+        if (store) {
+          const unsigned int at = atomicAdd(a.n_log, 1u);
+          a.log_index[at] = static_cast<int>(c * per + static_cast<size_t>(b) * 64 + k);
+          a.log_old[at] = static_cast<int16_t>(old);
+          blk[k] = static_cast<int16_t>(newval);
+          now = newval;
+          if (c > 0) {
+            const int d = (newval != 0 ? 1 : 0) - (old != 0 ? 1 : 0);
+            if (d != 0) atomicAdd(&sh[768], static_cast<unsigned int>(d));
+          }
+        }
+        warp_range_symbols(h, za, zp, zb, now != 0 ? now / qc[k] : 0, at_zb, 1u);
+      }
+      li += a.direction;
+      __syncwarp();  // lane 0's store is visible to the loads of the next entry
+    }
+    if (lane == 0) {
+      a.cnt[b] = 0u;
+      a.done[b] = count;
+      a.stamp[b] = a.iter;
+      a.s.last_index[b] = li;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * 256; i += 128)
+    if (sh[i]) atomicAdd(&a.delta_hist[i], sh[i]);
+  if (threadIdx.x == 0 && sh[768]) atomicAdd(a.chroma_nz, sh[768]);
+}
+
 // BulkApply (walk_dev.h) with the symbol-count deltas privatised per CTA: the symbols cluster
 // in a few bins, global atomics on them would serialise the whole kernel.
 __global__ void __launch_bounds__(128) k_bulk_apply(BulkApply a, int n) {
@@ -1758,7 +1874,12 @@ void ImageContext::walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, c
     launch_1d(s_, a, static_cast<int>(n_touched), "walk_bulk_apply");
 #else
     note_launch("walk_bulk_apply", s_, n_touched);
-    k_bulk_apply<<<(n_touched + 127) / 128, 128, 0, s_>>>(a, static_cast<int>(n_touched));
+    static const bool kThreadPerBlock = getenv("GB200_BULK_THREAD") != nullptr;  // A/B: the functor form
+    if (kThreadPerBlock) {
+      k_bulk_apply<<<(n_touched + 127) / 128, 128, 0, s_>>>(a, static_cast<int>(n_touched));
+    } else {
+      k_bulk_apply_warp<<<(n_touched + 3) / 4, 128, 0, s_>>>(a, static_cast<int>(n_touched));
+    }
     note_launch_end("walk_bulk_apply", s_);
 #endif
     d2h(host_counters, w_counters_, sizeof(host_counters), s_);
