@@ -1,4 +1,9 @@
-// Hand-tiled sm_100a kernels for the stages that dominate Compare (a10).  They
+// Hand-tiled sm_100a kernels of the STAGED Compare chain (round 1: one kernel per stage).  The
+// product runs the TMA-staged fused chain of fused_kernels.cuh; this chain stays in the library
+// behind GB200_COMPARE=staged as the second implementation that the fused one is checked
+// against on the GPU (tests/test_gpu_parity.py::test_fused_matches_staged), and it shares the
+// Malta line-sum window code, the JPEG histogram and the order-select kernels with it.
+// Original note: hand-tiled kernels for the stages that dominate Compare (a10).  They
 // compute exactly what the generic per-pixel functors in kernels.h compute (same
 // helper arithmetic from ba_math.h, same tap order) but stage tiles in shared
 // memory and keep partial results in registers instead of round-tripping planes
@@ -33,64 +38,7 @@ struct MaltaChannelArgs {
   int y0, nrows;         // rows [y0, y0 + nrows) are produced
 };
 
-// Variant 0: tile 32 x 16, a thread makes the two pixels (tx, ty) and (tx, ty + 8) and
-// reads every line-sum term from shared memory.
-#define GB_MALTA0_TILE_W 32
-#define GB_MALTA0_TILE_H 16
-#define GB_MALTA0_SW (GB_MALTA0_TILE_W + 8)
-#define GB_MALTA0_SH (GB_MALTA0_TILE_H + 8)
-
-__global__ void __launch_bounds__(256) k_malta_channel_v0(MaltaChannelArgs a) {
-  __shared__ float tile[GB_MALTA0_SH * GB_MALTA0_SW];
-  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
-  const int x0 = blockIdx.x * GB_MALTA0_TILE_W, y0 = a.y0 + blockIdx.y * GB_MALTA0_TILE_H;
-  const int y_end = a.y0 + a.nrows < a.g.h ? a.y0 + a.nrows : a.g.h;
-  const int tid = ty * 32 + tx;
-  float r0 = 0.0f, r1 = 0.0f;
-#pragma unroll 1
-  for (int band = 0; band < 3; ++band) {
-    const float* l0 = a.lum0[band];
-    const float* l1 = a.lum1[band];
-    const MaltaParams mp = a.mp[band];
-    __syncthreads();
-    for (int i = tid; i < GB_MALTA0_SH * GB_MALTA0_SW; i += 256) {
-      const int sy = i / GB_MALTA0_SW, sx = i - sy * GB_MALTA0_SW;
-      const int x = x0 + sx - 4, y = y0 + sy - 4;
-      float v = 0.0f;
-      if (x >= 0 && x < a.g.w && y >= 0 && y < a.g.h) {
-        const size_t o = static_cast<size_t>(y) * a.g.pitch + x;
-        v = malta_diff(l0[o], l1[o], mp);
-      }
-      tile[i] = v;
-    }
-    __syncthreads();
-    float u0 = 0.0f, u1 = 0.0f;
-    const float* c0 = tile + (ty + 4) * GB_MALTA0_SW + tx + 4;
-    const float* c1 = c0 + 8 * GB_MALTA0_SW;
-#define GB_T0(dx, dy) c0[(dy) * GB_MALTA0_SW + (dx)]
-#define GB_T1(dx, dy) c1[(dy) * GB_MALTA0_SW + (dx)]
-    if (band == 0) {
-      GB_MALTA_HF_SUMS(GB_T0, u0)
-      GB_MALTA_HF_SUMS(GB_T1, u1)
-    } else {
-      GB_MALTA_LF_SUMS(GB_T0, u0)
-      GB_MALTA_LF_SUMS(GB_T1, u1)
-    }
-#undef GB_T0
-#undef GB_T1
-    r0 = r0 + u0;
-    r1 = r1 + u1;
-  }
-  const int x = x0 + tx;
-  if (x < a.g.w) {
-    const int ya = y0 + ty, yb = y0 + ty + 8;
-    if (ya < y_end) a.acc[static_cast<size_t>(ya) * a.g.pitch + x] = r0;
-    if (yb < y_end) a.acc[static_cast<size_t>(yb) * a.g.pitch + x] = r1;
-  }
-}
-
-
-// Variants 1 and 2: tile 64 x 32 outputs per CTA (256 threads = 16 column groups x 16
+// Tile 64 x 32 outputs per CTA (256 threads = 16 column groups x 16
 // rows); a thread makes 4 ADJACENT pixels of a row, for rows ty and ty + 16.  Its 9 x 12
 // sample window comes from shared memory as 27 float4 loads and then lives in registers:
 // every sample is loaded once per 4 pixels instead of once per line-sum term.
@@ -163,41 +111,7 @@ __device__ __forceinline__ void malta_store(const MaltaChannelArgs& a, int x0, i
   }
 }
 
-// Variant 1: pre-pass fused (diffs computed into the tile by the CTA itself).
-__global__ void __launch_bounds__(256, 2) k_malta_channel_v1(MaltaChannelArgs a) {
-  __shared__ __align__(16) float tile[GB_MALTA_SH * GB_MALTA_SW];
-  const int tx = threadIdx.x, ty = threadIdx.y;  // 16 x 16
-  const int x0 = blockIdx.x * GB_MALTA_TILE_W, y0 = a.y0 + blockIdx.y * GB_MALTA_TILE_H;
-  const int y_end = a.y0 + a.nrows < a.g.h ? a.y0 + a.nrows : a.g.h;
-  const int tid = ty * 16 + tx;
-  float r[2][4];
-#pragma unroll
-  for (int k = 0; k < 2; ++k)
-#pragma unroll
-    for (int p = 0; p < 4; ++p) r[k][p] = 0.0f;
-#pragma unroll 1
-  for (int band = 0; band < 3; ++band) {
-    const float* l0 = a.lum0[band];
-    const float* l1 = a.lum1[band];
-    const MaltaParams mp = a.mp[band];
-    __syncthreads();
-    for (int i = tid; i < GB_MALTA_SH * GB_MALTA_SW; i += 256) {
-      const int sy = i / GB_MALTA_SW, sx = i - sy * GB_MALTA_SW;
-      const int x = x0 + sx - 4, y = y0 + sy - 4;
-      float v = 0.0f;
-      if (x >= 0 && x < a.g.w && y >= 0 && y < a.g.h) {
-        const size_t o = static_cast<size_t>(y) * a.g.pitch + x;
-        v = malta_diff(l0[o], l1[o], mp);
-      }
-      tile[i] = v;
-    }
-    __syncthreads();
-    malta_window_sums(tile, tx, ty, band == 0, r);
-  }
-  malta_store(a, x0, y0, y_end, tx, ty, r);
-}
-
-// Variant 2: the pre-pass is its own elementwise kernel (three diffs planes, zero in
+// The pre-pass is its own elementwise kernel (three diffs planes, zero in
 // the pad columns), and the line-sum kernel only copies tiles (cp.async, double
 // buffered over the bands, zero fill outside the plane).
 __global__ void __launch_bounds__(256) k_malta_pre3(MaltaChannelArgs a, float* diffs, int r0) {
@@ -256,33 +170,14 @@ __global__ void __launch_bounds__(256, 2) k_malta_sums(MaltaChannelArgs a, const
   malta_store(a, x0, y0, y_end, tx, ty, r);
 }
 
-// GB200_MALTA = 0 | 1 | 2 selects the variant (measurement aid; all three produce the same bits).
-inline int malta_variant() {
-  static const int v = [] {
-    const char* e = getenv("GB200_MALTA");
-    return e ? atoi(e) : 2;
-  }();
-  return v;
-}
-
 inline void launch_malta_channel(Stream s, const MaltaChannelArgs& a, float* scratch3) {
-  const int variant = malta_variant();
   note_launch("malta_channel", s, static_cast<double>(a.g.w) * a.nrows);
-  if (variant == 0) {
-    dim3 block(32, 8), grid((a.g.w + GB_MALTA0_TILE_W - 1) / GB_MALTA0_TILE_W, (a.nrows + GB_MALTA0_TILE_H - 1) / GB_MALTA0_TILE_H);
-    k_malta_channel_v0<<<grid, block, 0, s>>>(a);
-  } else {
-    dim3 block(16, 16), grid((a.g.w + GB_MALTA_TILE_W - 1) / GB_MALTA_TILE_W, (a.nrows + GB_MALTA_TILE_H - 1) / GB_MALTA_TILE_H);
-    if (variant == 1) {
-      k_malta_channel_v1<<<grid, block, 0, s>>>(a);
-    } else {
-      const int r0 = a.y0 - 4 > 0 ? a.y0 - 4 : 0;
-      const int r1 = a.y0 + a.nrows + 4 < a.g.h ? a.y0 + a.nrows + 4 : a.g.h;
-      dim3 pgrid((a.g.pitch + 255) / 256, r1 - r0, 3);
-      k_malta_pre3<<<pgrid, 256, 0, s>>>(a, scratch3, r0);
-      k_malta_sums<<<grid, block, 0, s>>>(a, scratch3);
-    }
-  }
+  dim3 block(16, 16), grid((a.g.w + GB_MALTA_TILE_W - 1) / GB_MALTA_TILE_W, (a.nrows + GB_MALTA_TILE_H - 1) / GB_MALTA_TILE_H);
+  const int r0 = a.y0 - 4 > 0 ? a.y0 - 4 : 0;
+  const int r1 = a.y0 + a.nrows + 4 < a.g.h ? a.y0 + a.nrows + 4 : a.g.h;
+  dim3 pgrid((a.g.pitch + 255) / 256, r1 - r0, 3);
+  k_malta_pre3<<<pgrid, 256, 0, s>>>(a, scratch3, r0);
+  k_malta_sums<<<grid, block, 0, s>>>(a, scratch3);
   note_launch_end("malta_channel", s);
 }
 
