@@ -100,27 +100,26 @@ struct BlurXCfg {
   static constexpr int SW = GBX_TW - 4 + 4 * XTile<R>::NQ;  // tile row length (box width), multiple of 4
 };
 
+// body of the x pass for one tile; `tile` holds GBX_TH * BlurXCfg<R>::SW floats, `bar` one mbarrier
 template <int R>
-__global__ void __launch_bounds__(128) k_tma_blur_x(const __grid_constant__ CUtensorMap in_map, float* out,
-                                                    const float* scale_x, PlaneGeom g, BlurK<R> k) {
+__device__ __forceinline__ void blur_x_tile(float* tile, uint64_t* bar, const CUtensorMap* in_map, float* out,
+                                            const float* scale_x, const PlaneGeom& g, const BlurK<R>& k, int pl) {
   constexpr int SW = BlurXCfg<R>::SW, RP = XTile<R>::RP;
-  __shared__ __align__(128) float tile[GBX_TH * SW];
-  __shared__ __align__(8) uint64_t bar;
-  const int x0 = blockIdx.x * GBX_TW, yb = g.y0 + blockIdx.y * GBX_TH, pl = blockIdx.z;
+  const int x0 = blockIdx.x * GBX_TW, yb = g.y0 + blockIdx.y * GBX_TH;
   if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(bar, 1);
     mbar_fence_init();
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(&bar, GBX_TH * SW * 4);
-    tma_load_box(tile, &in_map, &bar, x0 - RP, yb, pl);
+    mbar_expect_tx(bar, GBX_TH * SW * 4);
+    tma_load_box(tile, in_map, bar, x0 - RP, yb, pl);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool edge = (x0 < R) || (x0 + GBX_TW + R > g.w);  // some output of this tile takes the border rule
   const int xb = x0 + 4 * lane;
   float* oplane = out + static_cast<size_t>(pl) * g.plane;
-  mbar_wait(&bar, 0);
+  mbar_wait(bar, 0);
 #pragma unroll 1
   for (int r = warp; r < GBX_TH; r += 4) {
     const int y = yb + r;
@@ -141,6 +140,45 @@ __global__ void __launch_bounds__(128) k_tma_blur_x(const __grid_constant__ CUte
       if (x >= g.w) continue;
       orow[x] = (x < R || x + R >= g.w) ? raw[o] * scale_x[x] : acc[o];
     }
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(128) k_tma_blur_x(const __grid_constant__ CUtensorMap in_map, float* out,
+                                                    const float* scale_x, PlaneGeom g, BlurK<R> k) {
+  __shared__ __align__(128) float tile[GBX_TH * BlurXCfg<R>::SW];
+  __shared__ __align__(8) uint64_t bar;
+  blur_x_tile<R>(tile, &bar, &in_map, out, scale_x, g, k, blockIdx.z);
+}
+
+// Four single-plane x passes with different kernels in one launch (blockIdx.z picks the blur):
+// the noise blur and the three mask blurs all become ready after hf_fused / mask_pre, and each
+// alone is a one-wave launch whose ramp and tail cost as much as its arithmetic.
+template <int R0, int R1, int R2, int R3>
+struct BlurX4Args {
+  float* out[4];
+  const float* scale_x[4];
+  BlurK<R0> k0;
+  BlurK<R1> k1;
+  BlurK<R2> k2;
+  BlurK<R3> k3;
+};
+
+template <int R0, int R1, int R2, int R3>
+__global__ void __launch_bounds__(128) k_tma_blur_x4(const __grid_constant__ CUtensorMap m0,
+                                                     const __grid_constant__ CUtensorMap m1,
+                                                     const __grid_constant__ CUtensorMap m2,
+                                                     const __grid_constant__ CUtensorMap m3, PlaneGeom g,
+                                                     const __grid_constant__ BlurX4Args<R0, R1, R2, R3> a) {
+  constexpr int RMAX = R0 > R1 ? (R0 > R2 ? (R0 > R3 ? R0 : R3) : (R2 > R3 ? R2 : R3))
+                               : (R1 > R2 ? (R1 > R3 ? R1 : R3) : (R2 > R3 ? R2 : R3));
+  __shared__ __align__(128) float tile[GBX_TH * BlurXCfg<RMAX>::SW];
+  __shared__ __align__(8) uint64_t bar;
+  switch (blockIdx.z) {  // uniform per CTA
+    case 0: blur_x_tile<R0>(tile, &bar, &m0, a.out[0], a.scale_x[0], g, a.k0, 0); break;
+    case 1: blur_x_tile<R1>(tile, &bar, &m1, a.out[1], a.scale_x[1], g, a.k1, 0); break;
+    case 2: blur_x_tile<R2>(tile, &bar, &m2, a.out[2], a.scale_x[2], g, a.k2, 0); break;
+    default: blur_x_tile<R3>(tile, &bar, &m3, a.out[3], a.scale_x[3], g, a.k3, 0); break;
   }
 }
 

@@ -360,6 +360,38 @@ void ImageContext::fused_compare_launches() {
   const int rows = cr_hi_ - cr_lo_;
   fused_opsin(lin_, xyb_);
   fused_separate(xyb_, ps1_, true);
+  // S10 mask: DiffPrecompute against the original's resident neighbour sums
+  {
+    dim3 block(32, 8), grid(cdiv(g_.w, 32), cdiv(rows, 8));
+    note_launch("mask_pre", s_, static_cast<double>(g_.w) * rows);
+    k_mask_pre<<<grid, block, 0, s_>>>(ps1_, sup0_, mpre_, pg);
+    note_launch_end("mask_pre", s_);
+  }
+  // x passes of the noise blur (S8) and of the three mask blurs in one launch:
+  //   noise_ -> blr_[0] (r 23);  mpre[X] -> tmp_[0] (r 20);  mpre[Y] -> tmp_[1] (r 20);  mpre[Y] -> tmp_[2] (r 5)
+  // (blr_ is a plane group of the staged chain, free here)
+  {
+    BlurX4Args<GB_R_NOISE, GB_R_MASKX, GB_R_MASKY1, GB_R_MASKY0> xa;
+    xa.out[0] = blr_;
+    xa.out[1] = tmp_;
+    xa.out[2] = tmp_ + P;
+    xa.out[3] = tmp_ + 2 * P;
+    xa.scale_x[0] = t_.blur[kBlurNoise].scale_x;
+    xa.scale_x[1] = t_.blur[kBlurMaskX].scale_x;
+    xa.scale_x[2] = t_.blur[kBlurMaskY1].scale_x;
+    xa.scale_x[3] = t_.blur[kBlurMaskY0].scale_x;
+    xa.k0 = make_blurk<GB_R_NOISE>(ht_, kBlurNoise);
+    xa.k1 = make_blurk<GB_R_MASKX>(ht_, kBlurMaskX);
+    xa.k2 = make_blurk<GB_R_MASKY1>(ht_, kBlurMaskY1);
+    xa.k3 = make_blurk<GB_R_MASKY0>(ht_, kBlurMaskY0);
+    dim3 grid(cdiv(g_.w, GBX_TW), cdiv(rows, GBX_TH), 4);
+    note_launch("tma_blur_x", s_, 4.0 * g_.w * rows);
+    k_tma_blur_x4<GB_R_NOISE, GB_R_MASKX, GB_R_MASKY1, GB_R_MASKY0><<<grid, 128, 0, s_>>>(
+        fused_->map(noise_, 1, BlurXCfg<GB_R_NOISE>::SW, GBX_TH, g_), fused_->map(mpre_, 1, BlurXCfg<GB_R_MASKX>::SW, GBX_TH, g_),
+        fused_->map(mpre_ + P, 1, BlurXCfg<GB_R_MASKY1>::SW, GBX_TH, g_),
+        fused_->map(mpre_ + P, 1, BlurXCfg<GB_R_MASKY0>::SW, GBX_TH, g_), pg, xa);
+    note_launch_end("tma_blur_x", s_);
+  }
   // S7 Malta line sums of both channels: ac[ch] = ((0 + uhf) + hf) + mf
   {
     dim3 block(16, 16), grid(cdiv(g_.w, GB_MALTA_TILE_W), cdiv(rows, GB_MALTA_TILE_H), 2);
@@ -367,33 +399,10 @@ void ImageContext::fused_compare_launches() {
     k_tma_malta_sums<<<grid, block, 0, s_>>>(fused_->map(diffs6_, 6, GB_MALTA_SW, GB_MALTA_SH, g_), ac_, pg);
     note_launch_end("malta_sums", s_);
   }
-  // S8 + S9 on block_diff_ac[Y]: blurred noise difference, asymmetric L2 of hf[Y]
-  launch_tma_x<GB_R_NOISE>(s_, fused_->map(noise_, 1, BlurXCfg<GB_R_NOISE>::SW, GBX_TH, g_), tmp_, 1, t_.blur[kBlurNoise], pg,
-                           ht_, kBlurNoise);
-  launch_tma_y<GB_R_NOISE, 1>(s_, fused_->map(tmp_, 1, GBY_TW, GBY_TH + 2 * GB_R_NOISE, g_), 1, t_.blur[kBlurNoise], pg, ht_,
+  // S8 tail + S9 on block_diff_ac[Y]: blurred noise difference, asymmetric L2 of hf[Y]
+  launch_tma_y<GB_R_NOISE, 1>(s_, fused_->map(blr_, 1, GBY_TW, GBY_TH + 2 * GB_R_NOISE, g_), 1, t_.blur[kBlurNoise], pg, ht_,
                               kBlurNoise, EpiNoise{ps0_ + kHfY * P, ps1_ + kHfY * P, ac_ + P, asym_w0_, asym_w1_, g_.pitch},
                               "noise_fused_y");
-  // S10 mask: DiffPrecompute against the original's resident neighbour sums, x passes
-  {
-    dim3 block(32, 8), grid(cdiv(g_.w, 32), cdiv(rows, 8));
-    note_launch("mask_pre", s_, static_cast<double>(g_.w) * rows);
-    k_mask_pre<<<grid, block, 0, s_>>>(ps1_, sup0_, mpre_, pg);
-    note_launch_end("mask_pre", s_);
-  }
-  static_assert(GB_R_MASKX == GB_R_MASKY1, "the X and the wide Y mask blur share one x-pass launch");
-  // tmp_[0] = x pass of mpre[X] (r 20), tmp_[1] = x pass of mpre[Y] (r 20), tmp_[2] = x pass of mpre[Y] (r 5)
-  if (ht_.blur_taps[kBlurMaskX] != ht_.blur_taps[kBlurMaskY1]) {
-    // different sigmas (9.24 vs 9.04): same radius, different taps -> two launches
-    launch_tma_x<GB_R_MASKX>(s_, fused_->map(mpre_, 1, BlurXCfg<GB_R_MASKX>::SW, GBX_TH, g_), tmp_, 1, t_.blur[kBlurMaskX], pg,
-                             ht_, kBlurMaskX);
-    launch_tma_x<GB_R_MASKY1>(s_, fused_->map(mpre_ + P, 1, BlurXCfg<GB_R_MASKY1>::SW, GBX_TH, g_), tmp_ + P, 1,
-                              t_.blur[kBlurMaskY1], pg, ht_, kBlurMaskY1);
-  } else {
-    launch_tma_x<GB_R_MASKX>(s_, fused_->map(mpre_, 2, BlurXCfg<GB_R_MASKX>::SW, GBX_TH, g_), tmp_, 2, t_.blur[kBlurMaskX], pg,
-                             ht_, kBlurMaskX);
-  }
-  launch_tma_x<GB_R_MASKY0>(s_, fused_->map(mpre_ + P, 1, BlurXCfg<GB_R_MASKY0>::SW, GBX_TH, g_), tmp_ + 2 * P, 1,
-                            t_.blur[kBlurMaskY0], pg, ht_, kBlurMaskY0);
   // y passes + S11 CombineChannels + first half of S12 -> dm_[1]
   {
     typedef MaskYCfg<GB_R_MASKX, GB_R_MASKY0, GB_R_MASKY1> C;

@@ -715,7 +715,7 @@ class Search {
     for (size_t i = 0; i < fetched_list_.size(); ++i) fetched_[fetched_list_[i]] = 0;
     fetched_list_.clear();
     if (fetched_.size() != static_cast<size_t>(img_.nblocks)) fetched_.assign(img_.nblocks, 0);
-    size_t pos = i0 - base, chunk = 512;
+    size_t pos = i0 - base, chunk = 64;  // the walk usually stops a few entries after i0
     size_t changed = static_cast<size_t>(bulk.touched);
     WalkOutcome out;
     bool ok = true;
