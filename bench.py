@@ -207,7 +207,7 @@ def _ref_worker(args):
     return secs
 
 
-def run_reference(args, wl, name):
+def run_reference(args, wl, name, emit):
     """Reference arm: the unmodified reference (oracle/_ref) on the host cores this process
     may use, one single-threaded Process() per core (the reference's own parallelism idiom,
     tests/golden_test.sh:25).  Each step = one bounded crop-sized sample of the workload's
@@ -218,7 +218,7 @@ def run_reference(args, wl, name):
     import multiprocessing as mp
     import reflib
     if not reflib.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libguetzli_ref.so not built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libguetzli_ref.so not built"})
         return
     cores, how = usable_cores()
     cores = max(1, min(cores, 64))
@@ -249,7 +249,7 @@ def run_reference(args, wl, name):
         "e2e": {"value": value, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def cached_reference_timing(wl):
@@ -326,7 +326,23 @@ def run_tiled(args, wl, name, gb, dist, rank, world, local, steps, warmup):
     return out
 
 
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner
+    when NCCL_DEBUG is set on the box, warnings of child processes): everything this process and
+    its libraries write to fd 1 goes to stderr instead; the line is written to the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    real_stdout = claim_stdout()
+
+    def emit(line):
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
@@ -346,7 +362,7 @@ def main():
     wl = WORKLOADS[args.workload]
 
     if args.impl == "reference":
-        run_reference(args, wl, args.workload)
+        run_reference(args, wl, args.workload, emit)
         return
 
     from concurrent.futures import ThreadPoolExecutor
@@ -392,7 +408,7 @@ def main():
                         "d2h_bytes_per_step": int((b1 - b0) / max(1, args.steps + args.warmup)),
                         "note": "the tiled call takes HOST buffers: value and e2e are the same measurement"},
                 "gpu_launches": int((n1 - n0) * args.steps / max(1, args.steps + args.warmup)), "tiled": res}
-        print(json.dumps(line))
+        emit(line)
         return
 
     M = args.batch
@@ -585,8 +601,7 @@ def main():
                 "full_size_cached": cached_reference_timing(wl)}
     if rehearsal:
         line["rehearsal_cpu_port"] = True  # plumbing check only, not a measurement
-    print(json.dumps(line))
-    sys.stdout.flush()
+    emit(line)
     if hung:
         os._exit(0)
 

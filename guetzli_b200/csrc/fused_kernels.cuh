@@ -232,10 +232,43 @@ __global__ void __launch_bounds__(256, NP == 1 ? 3 : 2) k_tma_blur_y(const __gri
       }
     }
   }
+  constexpr int CH = Epi::kChunk;
+  if (NP > 1) {
+    // Multi-plane epilogues are long (EpiMf: two Malta pre-passes per pixel): 16 unrolled copies
+    // do not fit the instruction cache.  The blurred values go back to shared memory (over the
+    // input tiles, dead once every thread has finished its passes; each thread reads only its own
+    // slots again) and the epilogue becomes a rolled loop over chunks.
+    static_assert(NP == 1 || GBY_G * 256 <= (GBY_TH + 2 * R) * GBY_TW, "stash must fit in the tiles");
+    __syncthreads();
+    float* stash = dyn_smem + threadIdx.x;  // [NP][GBY_G][256]
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+      for (int o = 0; o < GBY_G; ++o) stash[(p * GBY_G + o) * 256] = res[p][o];
+    if (x >= g.w) return;
+#pragma unroll 1
+    for (int o0 = 0; o0 < GBY_G; o0 += CH) {
+      typename Epi::Pre pre[CH];
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int y = yg + o0 + i;
+        if (y < g.y_end) epi.load(x, y, pz, pre[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int y = yg + o0 + i;
+        if (y >= g.y_end) continue;
+        float v[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) v[p] = stash[(p * GBY_G + o0 + i) * 256];
+        epi.apply(x, y, pz, v, pre[i]);
+      }
+    }
+    return;
+  }
   if (x >= g.w) return;
   // Epilogue in chunks: first every global operand of the chunk's pixels (read-only path,
   // all loads in flight together), then the arithmetic and the stores.
-  constexpr int CH = Epi::kChunk;
 #pragma unroll
   for (int o0 = 0; o0 < GBY_G; o0 += CH) {
     typename Epi::Pre pre[CH];

@@ -26,13 +26,25 @@ GB_HD int hd_floor_log2_nz(unsigned int n) {
 #endif
 }
 
+// Quotient of a candidate coefficient by its quant step.  The candidate holds exact multiples of
+// q (Quantize, g/quantize.h:24; coefficients of a JPEG input times their own step), |c| < 2^15, so
+// on the device float(c) * rcp(float(q)) is off by less than 0.004 from the integer quotient and
+// rounds to it: three instructions instead of an integer division per nonzero coefficient.
+GB_HD int div_exact_multiple(int c, int q) {
+#if defined(__CUDA_ARCH__)
+  return __float2int_rn(__int2float_rn(c) * __frcp_rn(__int2float_rn(q)));
+#else
+  return c / q;
+#endif
+}
+
 // Visits the entropy-coding symbols of one 8x8 block in scan order
 // (EncodeDCTBlockSequential, g/jpeg_data_writer.cc:455): v.dc(nbits, extra),
 // v.ac(symbol, nbits, extra).  dq = dequantised coefficients, q = quant table,
 // prev_dc = quantised DC of the previous block of the same component.
 template <class V>
 GB_HD void visit_block_symbols(const int16_t* dq, const int* q, int prev_dc, const int* zigzag, V& v) {
-  const int16_t dc = static_cast<int16_t>(dq[0] / q[0]);
+  const int16_t dc = static_cast<int16_t>(div_exact_multiple(dq[0], q[0]));
   int16_t diff = static_cast<int16_t>(dc - prev_dc);
   int16_t low = diff;
   if (diff < 0) {
@@ -50,7 +62,7 @@ GB_HD void visit_block_symbols(const int16_t* dq, const int* q, int prev_dc, con
       ++run;
       continue;
     }
-    c /= q[nat];
+    c = div_exact_multiple(c, q[nat]);
     int m = c, lo = c;
     if (c < 0) {
       m = -c;
@@ -84,7 +96,7 @@ struct JpegHistAcc {  // 1D over 3*nblocks: i = c*nblocks + b
     const int c = i / nblocks, b = i - c * nblocks;
     const int16_t* blk = cand + static_cast<size_t>(i) * 64;
     const int* qc = q + 64 * c;
-    const int prev = b > 0 ? (blk - 64)[0] / qc[0] : 0;
+    const int prev = b > 0 ? div_exact_multiple((blk - 64)[0], qc[0]) : 0;
     unsigned int* base = hist + static_cast<size_t>(b & (kHistCopies - 1)) * kHistStride;
     Visitor v{base + c * 257, base + (3 + c) * 257};
     visit_block_symbols(blk, qc, prev, zigzag, v);
@@ -131,7 +143,7 @@ struct JpegUnitBits {  // 1D over nblocks * ncomp
     const int b = u / ncomp, c = u - b * ncomp;
     const int16_t* blk = cand + (static_cast<size_t>(c) * nblocks + b) * 64;
     const int* qc = q + 64 * c;
-    const int prev = b > 0 ? (blk - 64)[0] / qc[0] : 0;
+    const int prev = b > 0 ? div_exact_multiple((blk - 64)[0], qc[0]) : 0;
     Visitor v{codes.depth + c * 256, codes.depth + (3 + c) * 256, 0u};
     visit_block_symbols(blk, qc, prev, zigzag, v);
     bits[u] = v.n;
@@ -196,7 +208,7 @@ struct JpegEmit {  // 1D over nblocks * ncomp
     const int b = u / ncomp, c = u - b * ncomp;
     const int16_t* blk = cand + (static_cast<size_t>(c) * nblocks + b) * 64;
     const int* qc = q + 64 * c;
-    const int prev = b > 0 ? (blk - 64)[0] / qc[0] : 0;
+    const int prev = b > 0 ? div_exact_multiple((blk - 64)[0], qc[0]) : 0;
     Visitor v{codes.depth + c * 256, codes.code + c * 256, codes.depth + (3 + c) * 256,
               codes.code + (3 + c) * 256, BitCursor()};
     v.cur.start(words, offset[u]);

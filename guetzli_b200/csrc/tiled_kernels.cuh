@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) k_jpeg_hist(const int16_t* cand, const in
     const int c = i / nblocks, b = i - c * nblocks;
     const int16_t* blk = cand + static_cast<size_t>(i) * 64;
     const int* qc = sq + 64 * c;
-    const int prev = b > 0 ? (blk - 64)[0] / qc[0] : 0;
+    const int prev = b > 0 ? div_exact_multiple((blk - 64)[0], qc[0]) : 0;
     JpegHistAcc::Visitor v{sh + c * 257, sh + (3 + c) * 257};
     visit_block_symbols(blk, qc, prev, szz, v);
     if (c > 0) {
