@@ -75,6 +75,11 @@ COMPARE_FLOP_PER_PX = 2500.0  # un-fused FP32 instructions per
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu
 # --set full captures (profiles/), bytes; None until captured.
 NCU_TRAFFIC = {
+    # profiles/r02_ncu_fused.csv (noise1080p, per launch: dram read + write)
+    "hf_fused": 74.76e6 + 47.16e6, "mf_fused_y": 58.22e6 + 12.7e6, "mask_y_combine": 74.77e6 + 3.22e6,
+    "malta_sums": 49.82e6 + 3.18e6, "opsin_fused": 24.96e6 + 0.08e6, "lf_fused_y": 49.82e6 + 10.12e6,
+    "noise_fused_y": 33.26e6, "final_fused": 8.32e6, "mask_pre": 41.48e6 + 0.33e6,
+    # profiles/r01_final2_ncu_full.csv / r01_ncu_full_malta_blur.csv (staged chain)
     "malta_channel": 49.8e6 + 1.7e6 + 24.9e6,
     "blur_x": 8.33e6, "blur_y": 8.32e6,
 }

@@ -1935,7 +1935,7 @@ void ImageContext::walk_gather(const std::vector<int>& blocks, std::vector<int16
   h2d(w_gblocks_, blocks.data(), n * sizeof(int), s_);
   launch_1d(s_, GatherBlockState{w_gblocks_, d_cand_, d_last_index_, w_stamp_, w_iter_, g_.nblocks, w_gcoeffs_, w_gcursor_,
                                  w_ginbulk_},
-            static_cast<int>(3 * n), "walk_gather");
+            static_cast<int>(24 * n), "walk_gather");
   d2h(coeffs->data(), w_gcoeffs_, n * 192 * sizeof(int16_t), s_);
   d2h(cursor->data(), w_gcursor_, n * sizeof(int), s_);
   d2h(in_bulk->data(), w_ginbulk_, n * sizeof(int), s_);

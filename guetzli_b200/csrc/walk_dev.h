@@ -340,13 +340,14 @@ struct GatherBlockState {
   int16_t* out_coeffs;  // [n][3][64]
   int* out_cursor;      // [n]
   int* out_in_bulk;     // [n]
-  GB_HD void operator()(int i) const {  // i over n * 3
-    const int e = i / 3, c = i - 3 * e;
+  GB_HD void operator()(int i) const {  // i over n * 3 * 8: one row of 8 coefficients each
+    const int row = i & 7, ec = i >> 3;
+    const int e = ec / 3, c = ec - 3 * e;
     const int b = blocks[e];
-    const int16_t* src = cand + (static_cast<size_t>(c) * nblocks + b) * 64;
-    int16_t* dst = out_coeffs + static_cast<size_t>(i) * 64;
-    for (int k = 0; k < 64; ++k) dst[k] = src[k];
-    if (c == 0) {
+    const int16_t* src = cand + (static_cast<size_t>(c) * nblocks + b) * 64 + 8 * row;
+    int16_t* dst = out_coeffs + static_cast<size_t>(ec) * 64 + 8 * row;
+    for (int k = 0; k < 8; ++k) dst[k] = src[k];
+    if (c == 0 && row == 0) {
       out_cursor[e] = last_index[b];
       out_in_bulk[e] = stamp[b] == iter ? 1 : 0;
     }
