@@ -663,12 +663,11 @@ void ImageContext::release() {
   }
   if (d_sel_val2_) { dev_free(d_sel_val2_); d_sel_val2_ = nullptr; }
   if (d_sel_block2_) { dev_free(d_sel_block2_); d_sel_block2_ = nullptr; }
+  if (d_sel_pairs_) { dev_free(d_sel_pairs_); d_sel_pairs_ = nullptr; }
   if (w_log_index_) { dev_free(w_log_index_); w_log_index_ = nullptr; }
   if (w_log_old_) { dev_free(w_log_old_); w_log_old_ = nullptr; }
   if (w_gblocks_) { dev_free(w_gblocks_); w_gblocks_ = nullptr; }
   if (w_gcoeffs_) { dev_free(w_gcoeffs_); w_gcoeffs_ = nullptr; }
-  if (w_gcursor_) { dev_free(w_gcursor_); w_gcursor_ = nullptr; }
-  if (w_ginbulk_) { dev_free(w_ginbulk_); w_ginbulk_ = nullptr; }
   if (w_ablocks_) { dev_free(w_ablocks_); w_ablocks_ = nullptr; }
   if (d_sel_val_) { dev_free(d_sel_val_); d_sel_val_ = nullptr; }
   if (d_sel_block_) { dev_free(d_sel_block_); d_sel_block_ = nullptr; }
@@ -1238,7 +1237,8 @@ __device__ __forceinline__ void warp_range_symbols(unsigned int* h, int za, int 
   }
 }
 
-__global__ void __launch_bounds__(128) k_bulk_apply_warp(BulkApply a, int n) {
+__global__ void __launch_bounds__(128) k_bulk_apply_warp(BulkApply a, const unsigned int* n_touched) {
+  const int n = static_cast<int>(*n_touched);
   __shared__ unsigned int sh[3 * 256 + 1];
   for (int i = threadIdx.x; i < 3 * 256 + 1; i += 128) sh[i] = 0u;
   __syncthreads();
@@ -1326,7 +1326,8 @@ __global__ void __launch_bounds__(128) k_bulk_apply_warp(BulkApply a, int n) {
 
 // BulkApply (walk_dev.h) with the symbol-count deltas privatised per CTA: the symbols cluster
 // in a few bins, global atomics on them would serialise the whole kernel.
-__global__ void __launch_bounds__(128) k_bulk_apply(BulkApply a, int n) {
+__global__ void __launch_bounds__(128) k_bulk_apply(BulkApply a, const unsigned int* n_touched) {
+  const int n = static_cast<int>(*n_touched);
   __shared__ unsigned int sh[3 * 256 + 1];
   for (int i = threadIdx.x; i < 3 * 256 + 1; i += 128) sh[i] = 0u;
   __syncthreads();
@@ -1443,9 +1444,16 @@ void ImageContext::sort_selection(size_t n) {
   for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(d_sel_val_[i], d_sel_block_[i]);
   std::stable_sort(v.begin(), v.end(),
                    [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first < b.first; });
+  if (n > pairs_cap_) {
+    if (d_sel_pairs_) dev_free(d_sel_pairs_);
+    pairs_cap_ = n + n / 2 + 4096;
+    d_sel_pairs_ = dev_alloc(pairs_cap_ * 8);
+  }
+  std::pair<int, float>* pairs = static_cast<std::pair<int, float>*>(d_sel_pairs_);
   for (size_t i = 0; i < n; ++i) {
     d_sel_val_[i] = v[i].first;
     d_sel_block_[i] = v[i].second;
+    pairs[i] = std::make_pair(v[i].second, v[i].first);
   }
 }
 #else
@@ -1539,7 +1547,7 @@ __global__ void __launch_bounds__(1024) k_sort_pairs(float* k0, int* v0, float* 
 constexpr int kSortSmemMax = 14336;
 constexpr int kSortSmemSmall = 3072;
 template <int CAP, int NT>
-__global__ void __launch_bounds__(NT) k_sort_pairs_smem(float* keys, int* vals, int n) {
+__global__ void __launch_bounds__(NT) k_sort_pairs_smem(float* keys, int* vals, int2* pairs, int n) {
   extern __shared__ unsigned int dyn_sort[];
   unsigned int* ka = dyn_sort;                                       // [CAP]
   unsigned int* kb = ka + CAP;                                       // [CAP]
@@ -1632,17 +1640,34 @@ __global__ void __launch_bounds__(NT) k_sort_pairs_smem(float* keys, int* vals, 
     if (i < n) {
       vals[i] = pay[r];
       keys[i] = key[r];
+      pairs[i] = make_int2(pay[r], __float_as_int(key[r]));  // std::pair<int, float> of the host's order
     }
   }
 }
+
+// (block, key) pairs in the host's layout for selections sorted by the global-memory kernel
+__global__ void __launch_bounds__(256) k_make_pairs(const float* keys, const int* vals, int2* pairs, int n) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) pairs[i] = make_int2(vals[i], __float_as_int(keys[i]));
+}
 }  // namespace
 
+int2* ImageContext::sel_pairs(size_t n) {
+  if (n > pairs_cap_) {
+    stream_sync(s_);
+    if (d_sel_pairs_) { dev_free(d_sel_pairs_); d_sel_pairs_ = nullptr; }
+    pairs_cap_ = n + n / 2 + 4096;
+    d_sel_pairs_ = dev_alloc(pairs_cap_ * 8);
+  }
+  return static_cast<int2*>(d_sel_pairs_);
+}
+
 void ImageContext::sort_selection(size_t n) {
-  if (n < 2) return;
+  if (n == 0) return;
   if (n <= kSortSmemSmall) {
     const size_t smem = kSortSmemSmall * 12 + 16 * 256 * sizeof(unsigned short);  // 44 KB
     note_launch("sort_pairs", s_, static_cast<double>(n));
-    k_sort_pairs_smem<kSortSmemSmall, 256><<<1, 256, smem, s_>>>(d_sel_val_, d_sel_block_, static_cast<int>(n));
+    k_sort_pairs_smem<kSortSmemSmall, 256><<<1, 256, smem, s_>>>(d_sel_val_, d_sel_block_, sel_pairs(n), static_cast<int>(n));
     note_launch_end("sort_pairs", s_);
     return;
   }
@@ -1651,7 +1676,7 @@ void ImageContext::sort_selection(size_t n) {
     GB_CUDA(cudaFuncSetAttribute(k_sort_pairs_smem<kSortSmemMax, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
     note_launch("sort_pairs", s_, static_cast<double>(n));
-    k_sort_pairs_smem<kSortSmemMax, 1024><<<1, 1024, smem, s_>>>(d_sel_val_, d_sel_block_, static_cast<int>(n));
+    k_sort_pairs_smem<kSortSmemMax, 1024><<<1, 1024, smem, s_>>>(d_sel_val_, d_sel_block_, sel_pairs(n), static_cast<int>(n));
     note_launch_end("sort_pairs", s_);
     return;
   }
@@ -1666,6 +1691,7 @@ void ImageContext::sort_selection(size_t n) {
   GB_CUDA(cudaFuncSetAttribute(k_sort_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   note_launch("sort_pairs", s_, static_cast<double>(n));
   k_sort_pairs<<<1, 1024, smem, s_>>>(d_sel_val_, d_sel_block_, d_sel_val2_, d_sel_block2_, static_cast<int>(n));
+  k_make_pairs<<<static_cast<unsigned int>((n + 255) / 256), 256, 0, s_>>>(d_sel_val_, d_sel_block_, sel_pairs(n), static_cast<int>(n));
   note_launch_end("sort_pairs", s_);
 }
 #endif
@@ -1815,6 +1841,14 @@ size_t ImageContext::walk_select_sorted(int direction, size_t want, size_t* tota
   return sel_sorted_;
 }
 
+// the sorted selection as (block, key) pairs, one copy
+void ImageContext::walk_fetch_pairs(size_t n, std::pair<int, float>* out) {
+  static_assert(sizeof(std::pair<int, float>) == 8, "pair<int,float> layout");
+  if (n > sel_sorted_) throw std::runtime_error("walk_fetch_pairs: range outside the selection");
+  if (n == 0) return;
+  d2h(out, d_sel_pairs_, n * 8, s_);
+}
+
 void ImageContext::walk_fetch_sorted(size_t first, size_t n, float* val, int* block) {
   if (first + n > sel_sorted_) throw std::runtime_error("walk_fetch_sorted: range outside the selection");
   if (n == 0) return;
@@ -1837,6 +1871,8 @@ void ImageContext::walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, c
     throw std::runtime_error("walk_bulk_apply: bulk larger than the selection");
   }
   const size_t log_need = nbulk + pending_bulk_extra_;
+  const size_t pending_extra_for_grid = pending_bulk_extra_;
+  (void)pending_extra_for_grid;
   pending_bulk_extra_ = 0;
   if (log_need > w_log_cap_) {
     stream_sync(s_);
@@ -1857,8 +1893,15 @@ void ImageContext::walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, c
   if (nbulk > 0 || after_split) {
     if (nbulk > 0)
       launch_1d(s_, BulkCount{entry_blocks, w_cnt_, w_touched_, w_counters_}, static_cast<int>(nbulk), "walk_bulk_count");
+#if defined(GB200_HOSTSIM)
     unsigned int n_touched = 0;
     d2h(&n_touched, w_counters_, sizeof(unsigned int), s_);
+#else
+    // no round trip for the number of touched blocks: the grid covers its upper bound, the
+    // kernel reads the count
+    const unsigned int n_touched =
+        static_cast<unsigned int>(std::min<size_t>(static_cast<size_t>(g_.nblocks), nbulk + pending_extra_for_grid));
+#endif
     BulkApply a;
     a.s.orig = d_orig_;
     a.s.cand = d_cand_;
@@ -1882,14 +1925,16 @@ void ImageContext::walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, c
 #if defined(GB200_HOSTSIM)
     launch_1d(s_, a, static_cast<int>(n_touched), "walk_bulk_apply");
 #else
-    note_launch("walk_bulk_apply", s_, n_touched);
-    static const bool kThreadPerBlock = getenv("GB200_BULK_THREAD") != nullptr;  // A/B: the functor form
-    if (kThreadPerBlock) {
-      k_bulk_apply<<<(n_touched + 127) / 128, 128, 0, s_>>>(a, static_cast<int>(n_touched));
-    } else {
-      k_bulk_apply_warp<<<(n_touched + 3) / 4, 128, 0, s_>>>(a, static_cast<int>(n_touched));
+    if (n_touched > 0) {
+      note_launch("walk_bulk_apply", s_, n_touched);
+      static const bool kThreadPerBlock = getenv("GB200_BULK_THREAD") != nullptr;  // A/B: the functor form
+      if (kThreadPerBlock) {
+        k_bulk_apply<<<(n_touched + 127) / 128, 128, 0, s_>>>(a, w_counters_);
+      } else {
+        k_bulk_apply_warp<<<(n_touched + 3) / 4, 128, 0, s_>>>(a, w_counters_);
+      }
+      note_launch_end("walk_bulk_apply", s_);
     }
-    note_launch_end("walk_bulk_apply", s_);
 #endif
     d2h(host_counters, w_counters_, sizeof(host_counters), s_);
   }
@@ -1924,21 +1969,23 @@ void ImageContext::walk_gather(const std::vector<int>& blocks, std::vector<int16
     stream_sync(s_);
     if (w_gblocks_) { dev_free(w_gblocks_); w_gblocks_ = nullptr; }
     if (w_gcoeffs_) { dev_free(w_gcoeffs_); w_gcoeffs_ = nullptr; }
-    if (w_gcursor_) { dev_free(w_gcursor_); w_gcursor_ = nullptr; }
-    if (w_ginbulk_) { dev_free(w_ginbulk_); w_ginbulk_ = nullptr; }
     w_gcap_ = n + n / 2 + 1024;
     w_gblocks_ = static_cast<int*>(dev_alloc(w_gcap_ * sizeof(int)));
-    w_gcoeffs_ = static_cast<int16_t*>(dev_alloc(w_gcap_ * 192 * sizeof(int16_t)));
-    w_gcursor_ = static_cast<int*>(dev_alloc(w_gcap_ * sizeof(int)));
-    w_ginbulk_ = static_cast<int*>(dev_alloc(w_gcap_ * sizeof(int)));
+    // one buffer, one copy back: [cap][192] int16 | [cap] cursors | [cap] flags
+    w_gcoeffs_ = static_cast<int16_t*>(dev_alloc(w_gcap_ * (192 * sizeof(int16_t) + 2 * sizeof(int))));
   }
+  int* d_cursor = reinterpret_cast<int*>(w_gcoeffs_ + n * 192);
+  int* d_inbulk = d_cursor + n;
   h2d(w_gblocks_, blocks.data(), n * sizeof(int), s_);
-  launch_1d(s_, GatherBlockState{w_gblocks_, d_cand_, d_last_index_, w_stamp_, w_iter_, g_.nblocks, w_gcoeffs_, w_gcursor_,
-                                 w_ginbulk_},
+  launch_1d(s_, GatherBlockState{w_gblocks_, d_cand_, d_last_index_, w_stamp_, w_iter_, g_.nblocks, w_gcoeffs_, d_cursor,
+                                 d_inbulk},
             static_cast<int>(24 * n), "walk_gather");
-  d2h(coeffs->data(), w_gcoeffs_, n * 192 * sizeof(int16_t), s_);
-  d2h(cursor->data(), w_gcursor_, n * sizeof(int), s_);
-  d2h(in_bulk->data(), w_ginbulk_, n * sizeof(int), s_);
+  const size_t bytes = n * (192 * sizeof(int16_t) + 2 * sizeof(int));
+  gather_host_.resize(bytes);
+  d2h(gather_host_.data(), w_gcoeffs_, bytes, s_);
+  memcpy(coeffs->data(), gather_host_.data(), n * 192 * sizeof(int16_t));
+  memcpy(cursor->data(), gather_host_.data() + n * 192 * sizeof(int16_t), n * sizeof(int));
+  memcpy(in_bulk->data(), gather_host_.data() + n * 192 * sizeof(int16_t) + n * sizeof(int), n * sizeof(int));
 }
 
 void ImageContext::walk_advance(const std::vector<int>& blocks, int direction) {
@@ -2230,13 +2277,77 @@ void ImageContext::jpeg_histograms(unsigned int* hist, bool* chroma_nonzero) {
   *chroma_nonzero = buf[kHistStride] != 0;
 }
 
+#if !defined(GB200_HOSTSIM)
+namespace {
+// JpegUnitBits / JpegEmit (jpeg_dev.h) with the coefficient blocks staged in shared memory: a
+// CTA copies 128 consecutive blocks of one component with fully coalesced 16-byte loads (all
+// in flight together) into rows padded to 33 words -- a warp that walks its 32 blocks in
+// lock-step then hits 32 different banks -- and every thread visits the symbols of its block
+// from there.  Same visitors, same results as the functors.
+constexpr int kJpegRowWords = 33;  // 64 int16 = 32 words + 1 pad
+
+__device__ __forceinline__ const int16_t* jpeg_stage_blocks(unsigned int* smem, const int16_t* cand, int c, int b0,
+                                                            int nblocks) {
+  const int16_t* base = cand + (static_cast<size_t>(c) * nblocks + b0) * 64;
+  const int rows = min(128, nblocks - b0);
+  for (int j = threadIdx.x; j < rows * 8; j += 128) {
+    const int row = j >> 3, part = j & 7;
+    const int4 v = *reinterpret_cast<const int4*>(base + static_cast<size_t>(row) * 64 + part * 8);
+    unsigned int* d = smem + row * kJpegRowWords + part * 4;
+    d[0] = static_cast<unsigned int>(v.x);
+    d[1] = static_cast<unsigned int>(v.y);
+    d[2] = static_cast<unsigned int>(v.z);
+    d[3] = static_cast<unsigned int>(v.w);
+  }
+  __syncthreads();
+  return reinterpret_cast<const int16_t*>(smem + threadIdx.x * kJpegRowWords);
+}
+
+// grid (ceil(nblocks / 128), ncomp)
+__global__ void __launch_bounds__(128) k_jpeg_unit_bits(JpegUnitBits f) {
+  __shared__ unsigned int smem[128 * kJpegRowWords];
+  const int c = blockIdx.y, b0 = blockIdx.x * 128, b = b0 + threadIdx.x;
+  const int16_t* blk = jpeg_stage_blocks(smem, f.cand, c, b0, f.nblocks);
+  if (b >= f.nblocks) return;
+  const int* qc = f.q + 64 * c;
+  const int prev =
+      b > 0 ? div_exact_multiple(f.cand[(static_cast<size_t>(c) * f.nblocks + b - 1) * 64], qc[0]) : 0;
+  JpegUnitBits::Visitor v{f.codes.depth + c * 256, f.codes.depth + (3 + c) * 256, 0u};
+  visit_block_symbols(blk, qc, prev, f.zigzag, v);
+  f.bits[b * f.ncomp + c] = v.n;
+}
+
+__global__ void __launch_bounds__(128) k_jpeg_emit(JpegEmit f) {
+  __shared__ unsigned int smem[128 * kJpegRowWords];
+  const int c = blockIdx.y, b0 = blockIdx.x * 128, b = b0 + threadIdx.x;
+  const int16_t* blk = jpeg_stage_blocks(smem, f.cand, c, b0, f.nblocks);
+  if (b >= f.nblocks) return;
+  const int* qc = f.q + 64 * c;
+  const int prev =
+      b > 0 ? div_exact_multiple(f.cand[(static_cast<size_t>(c) * f.nblocks + b - 1) * 64], qc[0]) : 0;
+  JpegEmit::Visitor v{f.codes.depth + c * 256, f.codes.code + c * 256, f.codes.depth + (3 + c) * 256,
+                      f.codes.code + (3 + c) * 256, BitCursor()};
+  v.cur.start(f.words, f.offset[b * f.ncomp + c]);
+  visit_block_symbols(blk, qc, prev, f.zigzag, v);
+  v.cur.finish();
+}
+}  // namespace
+#endif
+
 void ImageContext::jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint16_t* code, size_t* nbytes,
                                     size_t* num_ff) {
   h2d(j_depth_, depth, 6 * 256, s_);
   h2d(j_code_, code, 6 * 256 * sizeof(uint16_t), s_);
   JpegCodes codes{j_depth_, j_code_};
   const int units = g_.nblocks * ncomp;
+#if defined(GB200_HOSTSIM)
   launch_1d(s_, JpegUnitBits{d_cand_, d_q_, t_.zigzag, codes, j_bits_, g_.nblocks, ncomp}, units, "jpeg_unit_bits");
+#else
+  const dim3 jgrid((g_.nblocks + 127) / 128, ncomp);
+  note_launch("jpeg_unit_bits", s_, units);
+  k_jpeg_unit_bits<<<jgrid, 128, 0, s_>>>(JpegUnitBits{d_cand_, d_q_, t_.zigzag, codes, j_bits_, g_.nblocks, ncomp});
+  note_launch_end("jpeg_unit_bits", s_);
+#endif
   unsigned long long total_bits = 0;
   exclusive_scan(j_bits_, j_offset_, units, &total_bits);
   if (total_bits >= (1ull << 32)) throw std::runtime_error("jpeg scan exceeds 2^32 bits");
@@ -2247,8 +2358,14 @@ void ImageContext::jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint1
     j_words_ = static_cast<unsigned int*>(dev_alloc(j_words_cap_ * sizeof(unsigned int)));
   }
   dev_zero(j_words_, (nwords + 1) * sizeof(unsigned int), s_);
+#if defined(GB200_HOSTSIM)
   launch_1d(s_, JpegEmit{d_cand_, d_q_, t_.zigzag, codes, j_offset_, j_words_, g_.nblocks, ncomp}, units,
             "jpeg_emit");
+#else
+  note_launch("jpeg_emit", s_, units);
+  k_jpeg_emit<<<jgrid, 128, 0, s_>>>(JpegEmit{d_cand_, d_q_, t_.zigzag, codes, j_offset_, j_words_, g_.nblocks, ncomp});
+  note_launch_end("jpeg_emit", s_);
+#endif
   unsigned int* counter = j_hist_ + static_cast<size_t>(kHistCopies + 1) * kHistStride + 1;
   dev_zero(counter, sizeof(unsigned int), s_);
   launch_1d(s_, JpegCountFF{j_words_, total_bits, counter}, static_cast<int>(nwords), "jpeg_count_ff");

@@ -121,6 +121,7 @@ class ImageContext {
   static size_t walk_middle_max() { return 65536; }  // larger middles come back unsorted: cancel them
   void walk_split_cancel();
   void walk_fetch_sorted(size_t first, size_t n, float* val, int* block);
+  void walk_fetch_pairs(size_t n, std::pair<int, float>* out);
   struct BulkResult {
     int touched, logged, chroma_delta;
     int delta_hist[3][256];
@@ -189,8 +190,9 @@ class ImageContext {
   size_t w_log_cap_ = 0;
   int* w_gblocks_ = nullptr;
   int16_t* w_gcoeffs_ = nullptr;
-  int* w_gcursor_ = nullptr;
-  int* w_ginbulk_ = nullptr;
+  std::vector<char> gather_host_;
+  void* d_sel_pairs_ = nullptr;  // the sorted selection as std::pair<int, float> (block, key)
+  size_t pairs_cap_ = 0;
   size_t w_gcap_ = 0;
   int* w_ablocks_ = nullptr;
   size_t w_acap_ = 0;
@@ -206,6 +208,9 @@ class ImageContext {
   int pending_touched_ = 0;  // blocks the last bulk changed and compare() has not rendered yet
   void select_keys(int direction, size_t k, OrderSelectState* got);
   void sort_selection(size_t n);
+#if defined(__CUDACC__)
+  int2* sel_pairs(size_t n);
+#endif
   // TMA-staged fused Compare chain (fused_kernels.cuh; CUDA build only)
   struct Fused;
   Fused* fused_ = nullptr;

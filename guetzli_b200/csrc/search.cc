@@ -685,11 +685,8 @@ class Search {
         st_->ms_sort += ms_since(t0);
         return -1;
       }
-      std::vector<float> val(n_slice);
-      std::vector<int> blk(n_slice);
-      ctx_->walk_fetch_sorted(0, n_slice, val.data(), blk.data());
       order.resize(n_slice);
-      for (size_t i = 0; i < n_slice; ++i) order[i] = std::make_pair(blk[i], val[i]);
+      ctx_->walk_fetch_pairs(n_slice, order.data());
     }
     ImageContext::BulkResult bulk;
     {
