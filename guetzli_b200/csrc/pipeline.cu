@@ -664,6 +664,7 @@ void ImageContext::release() {
   if (d_sel_val2_) { dev_free(d_sel_val2_); d_sel_val2_ = nullptr; }
   if (d_sel_block2_) { dev_free(d_sel_block2_); d_sel_block2_ = nullptr; }
   if (d_sel_pairs_) { dev_free(d_sel_pairs_); d_sel_pairs_ = nullptr; }
+  if (w_keys_) { dev_free(w_keys_); w_keys_ = nullptr; }
   if (w_log_index_) { dev_free(w_log_index_); w_log_index_ = nullptr; }
   if (w_log_old_) { dev_free(w_log_old_); w_log_old_ = nullptr; }
   if (w_gblocks_) { dev_free(w_gblocks_); w_gblocks_ = nullptr; }
@@ -1108,6 +1109,78 @@ __global__ void __launch_bounds__(256) k_walk_stats(const int* last_index, const
     }
     if (tm) atomicAdd(&out[0], tm);
     if (tc) atomicAdd(&out[1], tc);
+  }
+}
+
+// The two-rank select reads every order key three times (two histogram levels, the split).
+// The first pass computes the keys -- five dependent loads per entry -- and leaves their
+// order-preserving integer images in a key array; the other two passes stream that array.
+// 0xffffffff (the image of a NaN, never a key) marks entries that are not in the order.
+__device__ __forceinline__ float sortable_to_float(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+}
+
+__global__ void __launch_bounds__(256) k_order_hist0_keys(OrderKeyCommon c, unsigned int* hist, unsigned int* keys,
+                                                          int entries) {
+  __shared__ unsigned int sh[kOrderBins];
+  for (int i = threadIdx.x; i < kOrderBins; i += 256) sh[i] = 0;
+  __syncthreads();
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < entries; e += gridDim.x * 256) {
+    float v;
+    int b;
+    unsigned int u = 0xffffffffu;
+    if (c.key(e, &b, &v)) {
+      u = hd_float_sortable(v);
+      atomicAdd(&sh[u >> 21], 1u);
+    }
+    keys[e] = u;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kOrderBins; i += 256) {
+    const unsigned int n = sh[i];
+    if (n) atomicAdd(&hist[i], n);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_select2_hist1_keys(const unsigned int* keys, unsigned int* hist,
+                                                            const Select2State* st, int entries) {
+  __shared__ unsigned int sh[2 * kOrderBins];
+  for (int i = threadIdx.x; i < 2 * kOrderBins; i += 256) sh[i] = 0;
+  __syncthreads();
+  const unsigned int b_lo = st->bin0_lo, b_hi = st->bin0_hi;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < entries; e += gridDim.x * 256) {
+    const unsigned int u = keys[e];
+    if (u == 0xffffffffu) continue;
+    const unsigned int top = u >> 21, mid = (u >> 10) & 0x7ffu;
+    if (top == b_lo) atomicAdd(&sh[mid], 1u);
+    if (top == b_hi) atomicAdd(&sh[kOrderBins + mid], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * kOrderBins; i += 256) {
+    const unsigned int n = sh[i];
+    if (n) atomicAdd(&hist[i], n);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_select2_split_keys(const unsigned int* keys, const int* entry_block,
+                                                            Select2State* st, unsigned int* cnt, int* touched,
+                                                            unsigned int* n_touched, float* mid_val, int* mid_block,
+                                                            unsigned int mid_cap, int entries) {
+  const unsigned int lo22 = st->lo22, hi22 = st->hi22;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < entries; e += gridDim.x * 256) {
+    const unsigned int u = keys[e];
+    if (u == 0xffffffffu) continue;
+    const unsigned int u22 = u >> 10;
+    if (u22 < lo22) {
+      const int b = entry_block[e];
+      if (atomicAdd(&cnt[b], 1u) == 0u) touched[atomicAdd(n_touched, 1u)] = b;
+    } else if (u22 <= hi22) {
+      const unsigned int at = atomicAdd(&st->mid_count, 1u);
+      if (at < mid_cap) {
+        mid_val[at] = sortable_to_float(u);
+        mid_block[at] = entry_block[e];
+      }
+    }
   }
 }
 
@@ -1783,25 +1856,37 @@ size_t ImageContext::walk_select_split(int direction, size_t rank_lo, size_t ran
   launch_1d(s_, Select2Hist1{c, w_sel2_, st}, entries, "select2_hist1");
   launch_1d(s_, Select2Level1{w_sel2_, st}, 1, "select2_level");
 #else
-  launch_order_hist(s_, c, d_hist_, nullptr, 0, entries);
+  if (static_cast<size_t>(entries) > keys_cap_) {
+    stream_sync(s_);
+    if (w_keys_) { dev_free(w_keys_); w_keys_ = nullptr; }
+    keys_cap_ = static_cast<size_t>(entries) + 1024;
+    w_keys_ = static_cast<unsigned int*>(dev_alloc(keys_cap_ * sizeof(unsigned int)));
+  }
+  int ctas = (entries + 256 * 8 - 1) / (256 * 8);
+  if (ctas < 1) ctas = 1;
+  if (ctas > 1184) ctas = 1184;  // 148 SMs x 8 resident CTAs
+  note_launch("order_key_hist", s_, entries);
+  k_order_hist0_keys<<<ctas, 256, 0, s_>>>(c, d_hist_, w_keys_, entries);
+  note_launch_end("order_key_hist", s_);
   note_launch("select2_level", s_, kOrderBins);
   k_select2_level0<<<1, 1024, 0, s_>>>(d_hist_, st);
   note_launch_end("select2_level", s_);
-  {
-    int ctas = (entries + 256 * 8 - 1) / (256 * 8);
-    if (ctas < 1) ctas = 1;
-    if (ctas > 1184) ctas = 1184;
-    note_launch("select2_hist1", s_, entries);
-    k_select2_hist1<<<ctas, 256, 0, s_>>>(c, w_sel2_, st, entries);
-    note_launch_end("select2_hist1", s_);
-  }
+  note_launch("select2_hist1", s_, entries);
+  k_select2_hist1_keys<<<ctas, 256, 0, s_>>>(w_keys_, w_sel2_, st, entries);
+  note_launch_end("select2_hist1", s_);
   note_launch("select2_level", s_, kOrderBins);
   k_select2_level1<<<1, 1024, 0, s_>>>(w_sel2_, st);
   note_launch_end("select2_level", s_);
+  note_launch("select2_split", s_, entries);
+  k_select2_split_keys<<<ctas, 256, 0, s_>>>(w_keys_, e_block_, st, w_cnt_, w_touched_, w_counters_, d_sel_val_, d_sel_block_,
+                                             static_cast<unsigned int>(sel_cap_), entries);
+  note_launch_end("select2_split", s_);
 #endif
+#if defined(GB200_HOSTSIM)
   launch_1d(s_, Select2Split{c, st, w_cnt_, w_touched_, w_counters_, d_sel_val_, d_sel_block_,
                              static_cast<unsigned int>(sel_cap_)},
             entries, "select2_split");
+#endif
   Select2State got;
   d2h(&got, st, sizeof(got), s_);
   *total = got.total;

@@ -200,6 +200,8 @@ class ImageContext {
   int* d_sel_block2_ = nullptr;
   size_t sel2_cap_ = 0;
   size_t sel_sorted_ = 0;    // entries of the sorted resident selection
+  unsigned int* w_keys_ = nullptr;  // order-preserving integer images of all order keys (two-rank select)
+  size_t keys_cap_ = 0;
   unsigned int* w_sel2_ = nullptr;  // two-rank select: level-1 histogram pair + Select2State
   bool split_pending_ = false;      // walk_select_split has counted entries that no bulk has consumed yet
   size_t pending_bulk_extra_ = 0;   // ... how many
