@@ -243,4 +243,43 @@ struct JpegCountFF {
   }
 };
 
+// ---- f1: the complete file on the device ---------------------------------------------
+// The scan leaves JpegEmit / JpegCountFF as padded, un-stuffed bytes in big-endian words.  The
+// file is  prefix | stuffed scan | trailer  (g/jpeg_data_writer.cc:52-128,540-553; a zero byte
+// after every 0xFF of the scan, g/jpeg_bit_writer.h:62-77).  JpegWordFF counts the 0xFF bytes
+// of every word, an exclusive scan turns the counts into the shift of each word, JpegStuffBytes
+// writes every byte to its final position.  1D over the words of the scan.
+struct JpegWordFF {
+  const unsigned int* words;
+  unsigned long long nbytes;
+  unsigned int* count;
+  GB_HD void operator()(int w) const {
+    const unsigned int v = words[w];
+    unsigned int n = 0;
+    for (int k = 0; k < 4; ++k) {
+      const unsigned long long byte_index = (static_cast<unsigned long long>(w) << 2) + k;
+      if (byte_index < nbytes && ((v >> (24 - 8 * k)) & 0xffu) == 0xffu) ++n;
+    }
+    count[w] = n;
+  }
+};
+
+struct JpegStuffBytes {
+  const unsigned int* words;
+  const unsigned int* ff_before;  // exclusive scan of JpegWordFF
+  unsigned long long nbytes;
+  uint8_t* out;  // first byte of the scan inside the file buffer
+  GB_HD void operator()(int w) const {
+    const unsigned int v = words[w];
+    unsigned long long pos = (static_cast<unsigned long long>(w) << 2) + ff_before[w];
+    for (int k = 0; k < 4; ++k) {
+      const unsigned long long byte_index = (static_cast<unsigned long long>(w) << 2) + k;
+      if (byte_index >= nbytes) break;
+      const unsigned int b = (v >> (24 - 8 * k)) & 0xffu;
+      out[pos++] = static_cast<uint8_t>(b);
+      if (b == 0xffu) out[pos++] = 0;
+    }
+  }
+};
+
 }  // namespace gb200

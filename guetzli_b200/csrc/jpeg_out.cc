@@ -47,41 +47,81 @@ bool assign_depths(const TreeNode* pool, int root, int limit, uint8_t* depth) {
 
 }  // namespace
 
+// Length-limited code lengths as g/entropy_encode.cc:73 builds them: Huffman tree over the
+// counts raised to a floor; whenever a leaf ends up deeper than `limit` the floor doubles and
+// the tree is rebuilt.  The reference re-sorts the leaves for every floor.  Raising the floor
+// only changes the order among the leaves at or below it (they become equal and then go by
+// larger symbol first), and those are a prefix of the list sorted once by (count, larger
+// symbol first) -- so each further attempt is a linear pass.  Same trees, same depths.
 void huffman_code_lengths(const uint32_t* counts, int n, int limit, uint8_t* depth) {
-  std::vector<TreeNode> tree(2 * n + 2);
+  const int kMaxN = 512;
+  if (n > kMaxN) abort();  // 257 everywhere (SymbolHistogram::kSize)
+  uint64_t keys[kMaxN];
+  // nodes: [0, leaves) the leaves in merge order, [leaves] a sentinel, (leaves, 2 leaves) the parents
+  uint32_t count[2 * kMaxN + 2];
+  int16_t left[2 * kMaxN + 2], right[2 * kMaxN + 2];  // leaves: right = symbol
+  uint8_t level[2 * kMaxN + 2];
+  int leaves = 0;
+  for (int i = n - 1; i >= 0; --i)
+    if (counts[i]) keys[leaves++] = (static_cast<uint64_t>(counts[i]) << 32) | static_cast<uint32_t>(0x7fffffff - i);
+  if (leaves == 0) return;
+  if (leaves == 1) {
+    depth[0x7fffffff - static_cast<int>(keys[0] & 0xffffffffu)] = 1;
+    return;
+  }
+  // least frequent first; equal counts: larger symbol first
+  std::sort(keys, keys + leaves);
+  for (int i = 0; i < leaves; ++i) {
+    count[i] = static_cast<uint32_t>(keys[i] >> 32);
+    right[i] = static_cast<int16_t>(0x7fffffff - static_cast<int>(keys[i] & 0xffffffffu));
+  }
+  int below = 0;  // leaves whose count is <= the floor: keys[0, below)
+  const uint32_t kSentinel = ~static_cast<uint32_t>(0);
   for (uint32_t floor_count = 1;; floor_count *= 2) {
-    int leaves = 0;
-    for (int i = n - 1; i >= 0; --i) {
-      if (counts[i]) {
-        TreeNode t = {std::max<uint32_t>(counts[i], floor_count), -1, static_cast<int16_t>(i)};
-        tree[leaves++] = t;
+    const int below_before = below;
+    while (below < leaves && static_cast<uint32_t>(keys[below] >> 32) <= floor_count) ++below;
+    if (floor_count > 1 && below > 0) {
+      // the raised leaves, larger symbol first (the list beyond them keeps its order)
+      if (below != below_before || floor_count == 2) {
+        uint8_t raised[kMaxN / 8] = {0};
+        for (int i = 0; i < below; ++i) {
+          const int sym = 0x7fffffff - static_cast<int>(keys[i] & 0xffffffffu);
+          raised[sym >> 3] |= static_cast<uint8_t>(1u << (sym & 7));
+        }
+        int m = 0;
+        for (int sym = n - 1; sym >= 0; --sym)
+          if (raised[sym >> 3] & (1u << (sym & 7))) right[m++] = static_cast<int16_t>(sym);
       }
+      for (int i = 0; i < below; ++i) count[i] = floor_count;
     }
-    if (leaves == 1) {
-      depth[tree[0].right_or_value] = 1;
-      return;
-    }
-    // least frequent first; equal counts: larger symbol first
-    std::sort(tree.begin(), tree.begin() + leaves, [](const TreeNode& a, const TreeNode& b) {
-      if (a.count != b.count) return a.count < b.count;
-      return a.right_or_value > b.right_or_value;
-    });
     // two-queue merge: leaves in [0,leaves), parents appended from leaves+1
-    const TreeNode sentinel = {~static_cast<uint32_t>(0), -1, -1};
-    tree[leaves] = sentinel;
-    tree[leaves + 1] = sentinel;
+    count[leaves] = kSentinel;
+    count[leaves + 1] = kSentinel;
     int i = 0, j = leaves + 1;
     for (int k = leaves - 1; k != 0; --k) {
-      int left, right;
-      if (tree[i].count <= tree[j].count) left = i++; else left = j++;
-      if (tree[i].count <= tree[j].count) right = i++; else right = j++;
+      int l, r;
+      if (count[i] <= count[j]) l = i++; else l = j++;
+      if (count[i] <= count[j]) r = i++; else r = j++;
       const int parent = 2 * leaves - k;
-      tree[parent].count = tree[left].count + tree[right].count;
-      tree[parent].left = static_cast<int16_t>(left);
-      tree[parent].right_or_value = static_cast<int16_t>(right);
-      tree[parent + 1] = sentinel;
+      count[parent] = count[l] + count[r];
+      left[parent] = static_cast<int16_t>(l);
+      right[parent] = static_cast<int16_t>(r);
+      count[parent + 1] = kSentinel;
     }
-    if (assign_depths(tree.data(), 2 * leaves - 1, limit, depth)) return;
+    // a parent has a larger index than its children: levels top-down in one sweep
+    const int root = 2 * leaves - 1;
+    level[root] = 0;
+    for (int p = root; p > leaves; --p) {
+      const uint8_t l = static_cast<uint8_t>(level[p] + 1);
+      level[left[p]] = l;
+      level[right[p]] = l;
+    }
+    int deepest = 0;
+    for (int k = 0; k < leaves; ++k) deepest = level[k] > deepest ? level[k] : deepest;
+    if (deepest <= limit) {
+      for (int k = 0; k < leaves; ++k) depth[right[k]] = level[k];
+      return;
+    }
   }
 }
 

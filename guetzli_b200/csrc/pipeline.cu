@@ -307,6 +307,12 @@ bool graphs_enabled() {
 
 // S1..S13 on the linear RGB planes in lin_ (butteraugli::ButteraugliComparator::Diffmap).
 float ImageContext::fused_compare_tail() {
+  fused_compare_submit();
+  return fused_compare_result();
+}
+
+// the launches (no host round trip) / the distance (one)
+void ImageContext::fused_compare_submit() {
   const bool strips = comm_ && comm_->world() > 1;
   // First call: plain launches (creates the tensor maps, sets the kernel attributes).  Second
   // call: the same sequence is captured into a graph; from then on it is replayed.
@@ -338,6 +344,10 @@ float ImageContext::fused_compare_tail() {
     fused_compare_launches();
   }
   ++fused_->compare_calls;
+}
+
+float ImageContext::fused_compare_result() {
+  const bool strips = comm_ && comm_->world() > 1;
   if (strips) {
     gather_blocks(block_max_, sizeof(float));  // strip mode: one float per block crosses NVLink
     const int lanes = 1024;
@@ -560,6 +570,12 @@ void ImageContext::init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int
   edit_cap_ = 0;
   j_words_ = nullptr;
   j_words_cap_ = 0;
+  j_wsums_ = nullptr;
+  j_wsums_cap_ = 0;
+  j_file_ = nullptr;
+  j_file_cap_ = 0;
+  j_file_scratch_ = nullptr;
+  j_file_scratch_cap_ = 0;
   j_nbytes_ = 0;
 
   ps0_ = planes(kPsychoPlanes);
@@ -677,6 +693,9 @@ void ImageContext::release() {
   if (x_i32_) { dev_free(x_i32_); x_i32_ = nullptr; }
   if (x_small_) { dev_free(x_small_); x_small_ = nullptr; }
   if (j_words_) { dev_free(j_words_); j_words_ = nullptr; }
+  if (j_wsums_) { dev_free(j_wsums_); j_wsums_ = nullptr; }
+  if (j_file_) { dev_free(j_file_); j_file_ = nullptr; }
+  if (j_file_scratch_) { dev_free(j_file_scratch_); j_file_scratch_ = nullptr; }
   if (j_best_words_) { dev_free(j_best_words_); j_best_words_ = nullptr; }
   if (d_edit_i_) { dev_free(d_edit_i_); d_edit_i_ = nullptr; }
   if (d_edit_v_) { dev_free(d_edit_v_); d_edit_v_ = nullptr; }
@@ -779,6 +798,36 @@ void ImageContext::download_candidate(int16_t* coeffs) {
 }
 
 float ImageContext::compare() {
+  compare_render();
+  return compare_tail();
+}
+
+// compare() in two halves, so that the caller can put its own host work (and further stream
+// work) between the launches and the wait for the distance.
+void ImageContext::compare_begin() {
+  compare_render();
+#if !defined(GB200_HOSTSIM)
+  if (use_fused_ && !(comm_ && comm_->world() > 1)) {
+    fused_compare_submit();
+    compare_pending_ = true;
+    return;
+  }
+#endif
+  compare_stash_ = compare_tail();
+  compare_pending_ = false;
+}
+
+float ImageContext::compare_end() {
+#if !defined(GB200_HOSTSIM)
+  if (compare_pending_) {
+    compare_pending_ = false;
+    return fused_compare_result();
+  }
+#endif
+  return compare_stash_;
+}
+
+void ImageContext::compare_render() {
   bind();
   // S0 render (only blocks edited since the last render), S1 opsin, S2-S6 frequency split
   const int rb_lo = cr_lo_ / 8, rb_hi = (cr_hi_ + 7) / 8;  // block rows that intersect the computed rows
@@ -824,7 +873,6 @@ float ImageContext::compare() {
   render_all_ = false;
   for (size_t i = 0; i < dirty_list_.size(); ++i) dirty_flag_[dirty_list_[i]] = 0;
   dirty_list_.clear();
-  return compare_tail();
 }
 
 // S1..S13 on the linear RGB planes in lin_ (butteraugli::ButteraugliComparator::Diffmap).
@@ -2082,9 +2130,11 @@ void ImageContext::walk_advance(const std::vector<int>& blocks, int direction) {
     w_acap_ = n + n / 2 + 4096;
     w_ablocks_ = static_cast<int*>(dev_alloc(w_acap_ * sizeof(int)));
   }
-  h2d(w_ablocks_, blocks.data(), n * sizeof(int), s_);
+  // no wait here: the copy reads a buffer that lives until the next call (a pageable source is
+  // staged before cudaMemcpyAsync returns in any case)
+  advance_host_.assign(blocks.begin(), blocks.end());
+  h2d(w_ablocks_, advance_host_.data(), n * sizeof(int), s_);
   launch_1d(s_, AdvanceCursors{w_ablocks_, d_last_index_, direction}, static_cast<int>(n), "walk_advance");
-  stream_sync(s_);  // the host vector may go away
 }
 
 void ImageContext::walk_add_max_err(float val_threshold, int direction) {
@@ -2416,15 +2466,291 @@ __global__ void __launch_bounds__(128) k_jpeg_emit(JpegEmit f) {
   visit_block_symbols(blk, qc, prev, f.zigzag, v);
   v.cur.finish();
 }
+
+// ---- one warp per unit --------------------------------------------------------------
+// The serial visitors above spend 64 dependent steps per thread on a third of a wave of
+// threads.  Here a warp owns a unit: lane l holds the zig-zag positions l and l + 32, the
+// nonzero pattern is a 64-bit mask from two ballots, the run before a coefficient is a bit
+// scan in that mask, and the bit position of a coefficient's code inside the unit is a warp
+// prefix sum.  A CTA (8 warps x 4 units) scans the lengths of its 32 consecutive units itself,
+// so the size pass is  unit_bits -> scan of the CTA totals -> emit  (three launches, was five).
+// Same symbols and bits as visit_block_symbols (EncodeDCTBlockSequential, g/jpeg_data_writer.cc:455).
+constexpr int kJpegWarpUnits = 32;  // units per CTA
+
+struct JpegWarpArgs {
+  const int16_t* cand;
+  const int* q;
+  const int* zigzag;
+  JpegCodes codes;
+  unsigned int* offset;  // [units] bit offset of a unit inside its CTA's group
+  unsigned int* sums;    // [ctas] bits of a CTA's group; after the scan: first bit of the group
+  unsigned int* words;
+  int nblocks, ncomp, units;
+};
+
+// What this lane contributes to the unit's bit string: up to two coefficients (DC for lane 0's
+// first one), each = nz x ZRL + code(sym) + nb extra bits; lane 31 also owns the end-of-block.
+struct JpegLanePieces {
+  int nz[2], sym[2], nb[2];
+  unsigned int extra[2];
+  bool on[2], eob;
+};
+
+__device__ __forceinline__ JpegLanePieces jpeg_lane_pieces(const JpegWarpArgs& f, int b, int c, int lane) {
+  JpegLanePieces p;
+  const int16_t* blk = f.cand + (static_cast<size_t>(c) * f.nblocks + b) * 64;
+  const int* qc = f.q + 64 * c;
+  const int nat0 = f.zigzag[lane], nat1 = f.zigzag[lane + 32];
+  const int v0 = blk[nat0], v1 = blk[nat1];
+  const unsigned int m_lo = __ballot_sync(0xffffffffu, v0 != 0) & ~1u;  // position 0 is the DC
+  const unsigned int m_hi = __ballot_sync(0xffffffffu, v1 != 0);
+  const unsigned long long mask = (static_cast<unsigned long long>(m_hi) << 32) | m_lo;
+  p.eob = (mask >> 63) == 0ull;  // the scan ends in a run of zeros
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int z = lane + 32 * h, v = h ? v1 : v0, nat = h ? nat1 : nat0;
+    p.nz[h] = 0;
+    p.sym[h] = 0;
+    p.nb[h] = 0;
+    p.extra[h] = 0u;
+    p.on[h] = false;
+    if (z == 0) {
+      const int prev = b > 0 ? div_exact_multiple((blk - 64)[0], qc[0]) : 0;
+      const int16_t dc = static_cast<int16_t>(div_exact_multiple(v, qc[0]));
+      int16_t diff = static_cast<int16_t>(dc - prev);
+      int16_t low = diff;
+      if (diff < 0) {
+        diff = static_cast<int16_t>(-diff);
+        --low;
+      }
+      const unsigned int mag = static_cast<unsigned int>(static_cast<int>(diff));
+      const int nb = mag == 0 ? 0 : hd_floor_log2_nz(mag) + 1;
+      p.sym[h] = nb;
+      p.nb[h] = nb;
+      p.extra[h] = static_cast<unsigned int>(low) & ((1u << nb) - 1u);
+      p.on[h] = true;
+    } else if (v != 0) {
+      const unsigned long long below = mask & ((1ull << z) - 1ull);
+      const int last = below ? 63 - __clzll(static_cast<long long>(below)) : 0;
+      const int run = z - 1 - last;
+      const int cq = div_exact_multiple(v, qc[nat]);
+      int m = cq, lo = cq;
+      if (cq < 0) {
+        m = -cq;
+        lo = ~m;
+      }
+      const int nbits = hd_floor_log2_nz(static_cast<unsigned int>(m)) + 1;
+      p.nz[h] = run >> 4;
+      p.sym[h] = ((run & 15) << 4) + nbits;
+      p.nb[h] = nbits;
+      p.extra[h] = static_cast<unsigned int>(lo) & ((1u << nbits) - 1u);
+      p.on[h] = true;
+    }
+  }
+  return p;
+}
+
+// code tables of the (up to) three components in shared memory: depth [6][256], code [6][256]
+struct JpegSmemCodes {
+  uint8_t depth[6 * 256];
+  uint16_t code[6 * 256];
+};
+__device__ __forceinline__ void jpeg_load_codes(JpegSmemCodes* s, const JpegCodes& g) {
+  for (int i = threadIdx.x; i < 6 * 256 / 4; i += blockDim.x)
+    reinterpret_cast<unsigned int*>(s->depth)[i] = reinterpret_cast<const unsigned int*>(g.depth)[i];
+  for (int i = threadIdx.x; i < 6 * 256 / 2; i += blockDim.x)
+    reinterpret_cast<unsigned int*>(s->code)[i] = reinterpret_cast<const unsigned int*>(g.code)[i];
+}
+
+// bits of this lane's half h (h = 1 of lane 31 includes the end-of-block)
+__device__ __forceinline__ unsigned int jpeg_lane_bits(const JpegLanePieces& p, int h, int lane, const uint8_t* dc_d,
+                                                       const uint8_t* ac_d) {
+  unsigned int n = 0;
+  if (p.on[h]) {
+    if (h == 0 && lane == 0) {
+      n = dc_d[p.sym[0]] + p.nb[0];
+    } else {
+      n = p.nz[h] * ac_d[0xf0] + ac_d[p.sym[h]] + p.nb[h];
+    }
+  }
+  if (h == 1 && lane == 31 && p.eob) n += ac_d[0];
+  return n;
+}
+
+__global__ void __launch_bounds__(256) k_jpeg_unit_bits_warp(JpegWarpArgs f) {
+  __shared__ JpegSmemCodes codes;
+  __shared__ unsigned int ubits[kJpegWarpUnits];
+  jpeg_load_codes(&codes, f.codes);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int t = 0; t < 4; ++t) {
+    const int slot = warp * 4 + t;
+    const int u = blockIdx.x * kJpegWarpUnits + slot;
+    unsigned int n = 0;
+    if (u < f.units) {
+      const int b = u / f.ncomp, c = u - b * f.ncomp;
+      const JpegLanePieces p = jpeg_lane_pieces(f, b, c, lane);
+      const uint8_t* dc_d = codes.depth + c * 256;
+      const uint8_t* ac_d = codes.depth + (3 + c) * 256;
+      n = jpeg_lane_bits(p, 0, lane, dc_d, ac_d) + jpeg_lane_bits(p, 1, lane, dc_d, ac_d);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+    }
+    if (lane == 0) ubits[slot] = n;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned int v = ubits[lane];
+    unsigned int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const int u = blockIdx.x * kJpegWarpUnits + lane;
+    if (u < f.units) f.offset[u] = incl - v;
+    if (lane == 31) f.sums[blockIdx.x] = incl;
+  }
+}
+
+// ORs `n` bits (n <= 27, MSB first) at bit position `pos` of a zeroed shared-memory bit string
+__device__ __forceinline__ void jpeg_stage_put(unsigned int* stage, unsigned int& pos, int n, unsigned int value) {
+  if (n == 0) return;
+  const unsigned int w = pos >> 5, sh = pos & 31u;
+  const unsigned long long v = static_cast<unsigned long long>(value) << (64 - static_cast<int>(sh) - n);
+  atomicOr(&stage[w], static_cast<unsigned int>(v >> 32));
+  const unsigned int lo = static_cast<unsigned int>(v);
+  if (lo) atomicOr(&stage[w + 1], lo);
+  pos += static_cast<unsigned int>(n);
+}
+
+constexpr int kJpegStageWords = 64;  // a unit is at most 63 x 27 + 27 + 16 bits, plus 31 bits of lead-in
+
+__global__ void __launch_bounds__(256) k_jpeg_emit_warp(JpegWarpArgs f) {
+  __shared__ JpegSmemCodes codes;
+  __shared__ unsigned int stage_all[8][kJpegStageWords];
+  jpeg_load_codes(&codes, f.codes);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned int* stage = stage_all[warp];
+  const unsigned int group_first = f.sums[blockIdx.x];
+#pragma unroll 1
+  for (int t = 0; t < 4; ++t) {
+    const int u = blockIdx.x * kJpegWarpUnits + warp * 4 + t;
+    if (u >= f.units) break;  // uniform over the warp
+    stage[lane] = 0u;
+    stage[lane + 32] = 0u;
+    __syncwarp();
+    const int b = u / f.ncomp, c = u - b * f.ncomp;
+    const JpegLanePieces p = jpeg_lane_pieces(f, b, c, lane);
+    const uint8_t* dc_d = codes.depth + c * 256;
+    const uint8_t* ac_d = codes.depth + (3 + c) * 256;
+    const uint16_t* dc_c = codes.code + c * 256;
+    const uint16_t* ac_c = codes.code + (3 + c) * 256;
+    const unsigned int len0 = jpeg_lane_bits(p, 0, lane, dc_d, ac_d), len1 = jpeg_lane_bits(p, 1, lane, dc_d, ac_d);
+    unsigned int inc0 = len0, inc1 = len1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned int a0 = __shfl_up_sync(0xffffffffu, inc0, d), a1 = __shfl_up_sync(0xffffffffu, inc1, d);
+      if (lane >= d) {
+        inc0 += a0;
+        inc1 += a1;
+      }
+    }
+    const unsigned int total0 = __shfl_sync(0xffffffffu, inc0, 31), total1 = __shfl_sync(0xffffffffu, inc1, 31);
+    const unsigned int first_bit = group_first + f.offset[u];
+    const unsigned int lead = first_bit & 31u;
+    unsigned int pos[2] = {lead + inc0 - len0, lead + total0 + inc1 - len1};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (p.on[h]) {
+        if (h == 0 && lane == 0) {
+          jpeg_stage_put(stage, pos[0], dc_d[p.sym[0]], dc_c[p.sym[0]]);
+        } else {
+          for (int k = 0; k < p.nz[h]; ++k) jpeg_stage_put(stage, pos[h], ac_d[0xf0], ac_c[0xf0]);
+          jpeg_stage_put(stage, pos[h], ac_d[p.sym[h]], ac_c[p.sym[h]]);
+        }
+        jpeg_stage_put(stage, pos[h], p.nb[h], p.extra[h]);
+      }
+    }
+    if (lane == 31 && p.eob) jpeg_stage_put(stage, pos[1], ac_d[0], ac_c[0]);
+    __syncwarp();
+    // whole words of the unit are its own; the first and the last one are shared with the neighbours
+    const unsigned int nbits = lead + total0 + total1;
+    const int nw = static_cast<int>((nbits + 31u) >> 5);
+    unsigned int* out = f.words + (first_bit >> 5);
+    for (int w = lane; w < nw; w += 32) {
+      const unsigned int v = stage[w];
+      if (w == 0 || w == nw - 1) {
+        if (v) atomicOr(&out[w], v);
+      } else {
+        out[w] = v;
+      }
+    }
+    __syncwarp();
+  }
+}
 }  // namespace
 #endif
 
-void ImageContext::jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint16_t* code, size_t* nbytes,
-                                    size_t* num_ff) {
+// GB200_JPEG=thread keeps the one-thread-per-unit kernels (five launches and a mid-pass round
+// trip for the scan total); default: one warp per unit, the scan size taken from the host's
+// symbol counts (expected_bits) and checked against the device's at the end.
+void ImageContext::jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint16_t* code,
+                                    unsigned long long expected_bits, size_t* nbytes, size_t* num_ff) {
   h2d(j_depth_, depth, 6 * 256, s_);
   h2d(j_code_, code, 6 * 256 * sizeof(uint16_t), s_);
   JpegCodes codes{j_depth_, j_code_};
   const int units = g_.nblocks * ncomp;
+  if (expected_bits >= (1ull << 32)) throw std::runtime_error("jpeg scan exceeds 2^32 bits");
+#if !defined(GB200_HOSTSIM)
+  static const bool kWarpPerUnit = [] {
+    const char* e = getenv("GB200_JPEG");
+    return !(e != nullptr && e[0] == 't');
+  }();
+  if (kWarpPerUnit) {
+    const int ctas = (units + kJpegWarpUnits - 1) / kJpegWarpUnits;
+    if (static_cast<size_t>(ctas) > j_wsums_cap_) {
+      stream_sync(s_);
+      if (j_wsums_) { dev_free(j_wsums_); j_wsums_ = nullptr; }
+      j_wsums_cap_ = static_cast<size_t>(ctas) + 64;
+      // [cap] group sums | u64 scan total | u32 0xFF count | pad
+      j_wsums_ = static_cast<unsigned int*>(dev_alloc((j_wsums_cap_ + 8) * sizeof(unsigned int)));
+    }
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(j_wsums_ + ((j_wsums_cap_ + 1) & ~static_cast<size_t>(1)));
+    unsigned int* counter = reinterpret_cast<unsigned int*>(d_total + 1);
+    const unsigned long long total_bits = expected_bits;
+    const size_t nwords = static_cast<size_t>((total_bits + 31) >> 5);
+    if (nwords + 1 > j_words_cap_) {
+      stream_sync(s_);
+      if (j_words_) { dev_free(j_words_); j_words_ = nullptr; }
+      j_words_cap_ = nwords + nwords / 4 + 1024;
+      j_words_ = static_cast<unsigned int*>(dev_alloc(j_words_cap_ * sizeof(unsigned int)));
+    }
+    dev_zero(j_words_, (nwords + 1) * sizeof(unsigned int), s_);
+    dev_zero(counter, sizeof(unsigned int), s_);
+    JpegWarpArgs wa{d_cand_, d_q_, t_.zigzag, codes, j_offset_, j_wsums_, j_words_, g_.nblocks, ncomp, units};
+    note_launch("jpeg_unit_bits", s_, units);
+    k_jpeg_unit_bits_warp<<<ctas, 256, 0, s_>>>(wa);
+    note_launch_end("jpeg_unit_bits", s_);
+    note_launch("scan_sums", s_, ctas);
+    k_scan_sums<<<1, 1024, 0, s_>>>(j_wsums_, ctas, d_total);
+    note_launch_end("scan_sums", s_);
+    note_launch("jpeg_emit", s_, units);
+    k_jpeg_emit_warp<<<ctas, 256, 0, s_>>>(wa);
+    note_launch_end("jpeg_emit", s_);
+    if (nwords) launch_1d(s_, JpegCountFF{j_words_, total_bits, counter}, static_cast<int>(nwords), "jpeg_count_ff");
+    unsigned long long back[2] = {0, 0};  // scan total, 0xFF count
+    d2h(back, d_total, sizeof(back), s_);
+    if (back[0] != expected_bits)
+      throw std::runtime_error("jpeg scan: the device's bit count differs from the host's symbol counts");
+    j_nbytes_ = static_cast<size_t>((total_bits + 7) >> 3);
+    *nbytes = j_nbytes_;
+    *num_ff = static_cast<size_t>(back[1] & 0xffffffffull);
+    return;
+  }
+#endif
 #if defined(GB200_HOSTSIM)
   launch_1d(s_, JpegUnitBits{d_cand_, d_q_, t_.zigzag, codes, j_bits_, g_.nblocks, ncomp}, units, "jpeg_unit_bits");
 #else
@@ -2436,6 +2762,8 @@ void ImageContext::jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint1
   unsigned long long total_bits = 0;
   exclusive_scan(j_bits_, j_offset_, units, &total_bits);
   if (total_bits >= (1ull << 32)) throw std::runtime_error("jpeg scan exceeds 2^32 bits");
+  if (total_bits != expected_bits)
+    throw std::runtime_error("jpeg scan: the device's bit count differs from the host's symbol counts");
   const size_t nwords = static_cast<size_t>((total_bits + 31) >> 5);
   if (nwords + 1 > j_words_cap_) {
     if (j_words_) { dev_free(j_words_); j_words_ = nullptr; }
@@ -2478,6 +2806,59 @@ void ImageContext::jpeg_fetch_kept_scan(std::vector<uint8_t>* scan) {
   std::swap(j_nbytes_, j_best_nbytes_);
   try {
     jpeg_fetch_scan(scan);
+  } catch (...) {
+    std::swap(j_words_, j_best_words_);
+    std::swap(j_nbytes_, j_best_nbytes_);
+    throw;
+  }
+  std::swap(j_words_, j_best_words_);
+  std::swap(j_nbytes_, j_best_nbytes_);
+}
+
+// f1: prefix | stuffed scan | trailer assembled on the device, one copy back.
+void ImageContext::jpeg_fetch_file(const std::string& prefix, const std::string& trailer, std::string* file) {
+  bind();
+  const size_t nwords = (j_nbytes_ + 3) / 4;
+  const size_t ctas = (nwords + 1023) / 1024;
+  // scratch: [nwords] counts | [nwords] shifts | CTA sums + 64-bit total
+  const size_t scratch_words = 2 * nwords + ctas + 16;
+  if (scratch_words > j_file_scratch_cap_) {
+    stream_sync(s_);
+    if (j_file_scratch_) { dev_free(j_file_scratch_); j_file_scratch_ = nullptr; }
+    j_file_scratch_cap_ = scratch_words + scratch_words / 4 + 1024;
+    j_file_scratch_ = static_cast<unsigned int*>(dev_alloc(j_file_scratch_cap_ * sizeof(unsigned int)));
+  }
+  unsigned int* count = j_file_scratch_;
+  unsigned int* shift = j_file_scratch_ + nwords;
+  unsigned int* sums = j_file_scratch_ + 2 * nwords;
+  unsigned long long num_ff = 0;
+  if (nwords) {
+    launch_1d(s_, JpegWordFF{j_words_, static_cast<unsigned long long>(j_nbytes_), count}, static_cast<int>(nwords),
+              "jpeg_word_ff");
+    exclusive_scan_with(count, shift, static_cast<int>(nwords), &num_ff, sums);
+  }
+  const size_t total = prefix.size() + j_nbytes_ + static_cast<size_t>(num_ff) + trailer.size();
+  if (total > j_file_cap_) {
+    stream_sync(s_);
+    if (j_file_) { dev_free(j_file_); j_file_ = nullptr; }
+    j_file_cap_ = total + total / 4 + 4096;
+    j_file_ = static_cast<uint8_t*>(dev_alloc(j_file_cap_));
+  }
+  if (!prefix.empty()) h2d(j_file_, prefix.data(), prefix.size(), s_);
+  if (nwords)
+    launch_1d(s_, JpegStuffBytes{j_words_, shift, static_cast<unsigned long long>(j_nbytes_), j_file_ + prefix.size()},
+              static_cast<int>(nwords), "jpeg_stuff_bytes");
+  if (!trailer.empty())
+    h2d(j_file_ + prefix.size() + j_nbytes_ + static_cast<size_t>(num_ff), trailer.data(), trailer.size(), s_);
+  file->resize(total);
+  if (total) d2h(&(*file)[0], j_file_, total, s_);
+}
+
+void ImageContext::jpeg_fetch_kept_file(const std::string& prefix, const std::string& trailer, std::string* file) {
+  std::swap(j_words_, j_best_words_);
+  std::swap(j_nbytes_, j_best_nbytes_);
+  try {
+    jpeg_fetch_file(prefix, trailer, file);
   } catch (...) {
     std::swap(j_words_, j_best_words_);
     std::swap(j_nbytes_, j_best_nbytes_);

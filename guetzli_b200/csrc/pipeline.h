@@ -77,6 +77,11 @@ class ImageContext {
   // a7+a9+a10: renders the candidate and scores it against the original.
   // Leaves the distmap and per-block maxima on the device; returns distance_.
   float compare();
+  // the same in two halves: compare_begin() queues the kernels, compare_end() waits for the
+  // distance; stream work queued in between runs behind the metric's kernels (where the
+  // launches need a host round trip -- strip mode, the staged chain -- compare_begin() does it all)
+  void compare_begin();
+  float compare_end();
   void download_distmap(float* out);      // [h][w] packed
   void download_block_max(float* out);    // [nblocks]
 
@@ -144,12 +149,20 @@ class ImageContext {
   // Entropy-codes the scan with the given canonical codes (depth/code [6][256]).
   // Returns the number of scan bytes before 0xFF stuffing and the number of 0xFF
   // bytes among them; the bytes stay on the device until jpeg_fetch_scan().
-  void jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint16_t* code, size_t* nbytes, size_t* num_ff);
+  // expected_bits: length of the scan as the caller's symbol counts give it (sum over the symbols of
+  // count x (code length + extra bits)); sizes the buffers without a round trip and is checked
+  // against the device's own total
+  void jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint16_t* code, unsigned long long expected_bits,
+                        size_t* nbytes, size_t* num_ff);
   void jpeg_fetch_scan(std::vector<uint8_t>* scan);  // nbytes raw (unstuffed, padded) bytes
   // keeps a device-side copy of the scan just encoded (the best output so far); the bytes
   // cross PCIe once, when the search is over
   void jpeg_keep_scan();
   void jpeg_fetch_kept_scan(std::vector<uint8_t>* scan);
+  // f1: the whole file = prefix | scan with a zero byte after every 0xFF | trailer, assembled on
+  // the device from the current / the kept scan (jpeg_dev.h), one copy back
+  void jpeg_fetch_file(const std::string& prefix, const std::string& trailer, std::string* file);
+  void jpeg_fetch_kept_file(const std::string& prefix, const std::string& trailer, std::string* file);
 
   // test hooks: run single stages on caller-provided planes (packed [n][h][w]).
   void debug_blur(const float* in, float* out, int id);
@@ -224,6 +237,8 @@ class ImageContext {
   void fused_separate(const float* xyb, float* ps, bool with_diffs);
   void fused_blur(const float* in, float* out, int nplanes, int id);
   float fused_compare_tail();
+  void fused_compare_submit();
+  float fused_compare_result();
   void fused_compare_launches();
   void fused_sup0();
   void guarded_init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int h, bool prepare_now);
@@ -271,6 +286,10 @@ class ImageContext {
   size_t device_partial_sort_resident(size_t n, size_t want, std::vector<std::pair<int, float> >* out);
   bool metric_only_ = false;  // no coefficients at all: butteraugli of two linear images
   float compare_tail();
+  void compare_render();
+  bool compare_pending_ = false;
+  std::vector<int> advance_host_;  // source of walk_advance's upload
+  float compare_stash_ = 0.0f;
   bool from_coeffs_ = false;  // original given as coefficients (JPEG input)
   void init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int h, bool prepare_now);
   float* ac_ = nullptr;      // [2]
@@ -308,6 +327,12 @@ class ImageContext {
   unsigned int* j_bits_ = nullptr;      // [3*nblocks] unit bit lengths (scan order)
   unsigned int* j_offset_ = nullptr;    // [3*nblocks] exclusive scan
   unsigned int* j_sums_ = nullptr;      // scan scratch
+  unsigned int* j_wsums_ = nullptr;     // warp-per-unit size pass: bits per group of 32 units | u64 total | 0xFF count
+  size_t j_wsums_cap_ = 0;
+  uint8_t* j_file_ = nullptr;           // the assembled file (jpeg_fetch_file)
+  size_t j_file_cap_ = 0;
+  unsigned int* j_file_scratch_ = nullptr;
+  size_t j_file_scratch_cap_ = 0;
   uint8_t* j_depth_ = nullptr;          // [6][256]
   uint16_t* j_code_ = nullptr;          // [6][256]
   unsigned int* j_words_ = nullptr;     // scan bits, big-endian 32-bit words
