@@ -550,7 +550,7 @@ void ImageContext::init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int
   sel_cap_ = 0;
   d_sel_val_ = nullptr;
   d_sel_block_ = nullptr;
-  j_hist_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * (static_cast<size_t>(kHistCopies + 1) * kHistStride + 2)));
+  j_hist_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * (static_cast<size_t>(kHistCopies + 1) * kHistStride + 8)));
   owned_.push_back(j_hist_);
   j_bits_ = static_cast<unsigned int*>(dev_alloc(sizeof(unsigned int) * 3 * g_.nblocks));
   owned_.push_back(j_bits_);
@@ -570,8 +570,6 @@ void ImageContext::init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int
   edit_cap_ = 0;
   j_words_ = nullptr;
   j_words_cap_ = 0;
-  j_wsums_ = nullptr;
-  j_wsums_cap_ = 0;
   j_file_ = nullptr;
   j_file_cap_ = 0;
   j_file_scratch_ = nullptr;
@@ -693,7 +691,6 @@ void ImageContext::release() {
   if (x_i32_) { dev_free(x_i32_); x_i32_ = nullptr; }
   if (x_small_) { dev_free(x_small_); x_small_ = nullptr; }
   if (j_words_) { dev_free(j_words_); j_words_ = nullptr; }
-  if (j_wsums_) { dev_free(j_wsums_); j_wsums_ = nullptr; }
   if (j_file_) { dev_free(j_file_); j_file_ = nullptr; }
   if (j_file_scratch_) { dev_free(j_file_scratch_); j_file_scratch_ = nullptr; }
   if (j_best_words_) { dev_free(j_best_words_); j_best_words_ = nullptr; }
@@ -1510,6 +1507,13 @@ void ImageContext::walk_download_state(std::vector<int>* last_index, std::vector
 
 void ImageContext::walk_weights(int direction, int radius, double target_distance, bool zero_distmap,
                                 unsigned long long* order_size, unsigned long long* blocks_to_change) {
+  walk_weights_launch(direction, radius, target_distance, zero_distmap);
+  walk_weights_fetch(order_size, blocks_to_change);
+}
+
+// the kernels / the copy back of the two sums.  A caller that knows the arguments of the next
+// iteration queues the kernels behind the metric's and picks the sums up later.
+void ImageContext::walk_weights_launch(int direction, int radius, double target_distance, bool zero_distmap) {
   BlockWeights bw;
   bw.block_max = zero_distmap ? zero_block_max_ : block_max_;
   bw.weight = weights_;
@@ -1522,6 +1526,17 @@ void ImageContext::walk_weights(int direction, int radius, double target_distanc
   const int lanes = 1024;
   launch_1d(s_, WalkStatsPartial{d_last_index_, z_cnt_, weights_, direction, g_.nblocks, lanes, w_stats_}, lanes,
             "walk_stats");
+#else
+  dev_zero(w_stats_, 2 * sizeof(unsigned long long), s_);
+  note_launch("walk_stats", s_, g_.nblocks);
+  k_walk_stats<<<(g_.nblocks + 255) / 256, 256, 0, s_>>>(d_last_index_, z_cnt_, weights_, direction, g_.nblocks, w_stats_);
+  note_launch_end("walk_stats", s_);
+#endif
+}
+
+void ImageContext::walk_weights_fetch(unsigned long long* order_size, unsigned long long* blocks_to_change) {
+#if defined(GB200_HOSTSIM)
+  const int lanes = 1024;
   unsigned long long part[2 * 1024];
   d2h(part, w_stats_, sizeof(part), s_);
   unsigned long long n = 0, c = 0;
@@ -1532,10 +1547,6 @@ void ImageContext::walk_weights(int direction, int radius, double target_distanc
   *order_size = n;
   *blocks_to_change = c;
 #else
-  dev_zero(w_stats_, 2 * sizeof(unsigned long long), s_);
-  note_launch("walk_stats", s_, g_.nblocks);
-  k_walk_stats<<<(g_.nblocks + 255) / 256, 256, 0, s_>>>(d_last_index_, z_cnt_, weights_, direction, g_.nblocks, w_stats_);
-  note_launch_end("walk_stats", s_);
   unsigned long long tot[2];
   d2h(tot, w_stats_, sizeof(tot), s_);
   *order_size = tot[0];
@@ -2295,6 +2306,9 @@ size_t ImageContext::exact_order_prefix_resident(int direction, size_t want, std
 void ImageContext::exclusive_scan(const unsigned int* in, unsigned int* out, int n, unsigned long long* total) {
   exclusive_scan_with(in, out, n, total, nullptr);
 }
+void ImageContext::exclusive_scan_to(const unsigned int* in, unsigned int* out, int n, unsigned long long* d_total) {
+  exclusive_scan_with(in, out, n, d_total, nullptr);
+}
 void ImageContext::exclusive_scan_with(const unsigned int* in, unsigned int* out, int n, unsigned long long* total,
                                        unsigned int*) {
   unsigned long long acc = 0;
@@ -2372,6 +2386,19 @@ __global__ void __launch_bounds__(256) k_scan_add(unsigned int* out, const unsig
 
 void ImageContext::exclusive_scan(const unsigned int* in, unsigned int* out, int n, unsigned long long* total) {
   exclusive_scan_with(in, out, n, total, j_sums_);
+}
+// the same without the round trip: the total goes to device memory (8-byte aligned)
+void ImageContext::exclusive_scan_to(const unsigned int* in, unsigned int* out, int n, unsigned long long* d_total) {
+  const int ctas = (n + 1023) / 1024;
+  note_launch("scan_local", s_, n);
+  k_scan_local<<<ctas, 256, 0, s_>>>(in, out, j_sums_, n);
+  note_launch_end("scan_local", s_);
+  note_launch("scan_sums", s_, ctas);
+  k_scan_sums<<<1, 1024, 0, s_>>>(j_sums_, ctas, d_total);
+  note_launch_end("scan_sums", s_);
+  note_launch("scan_add", s_, n);
+  k_scan_add<<<ctas, 256, 0, s_>>>(out, j_sums_, n);
+  note_launch_end("scan_add", s_);
 }
 void ImageContext::exclusive_scan_with(const unsigned int* in, unsigned int* out, int n, unsigned long long* total,
                                        unsigned int* j_sums_) {
@@ -2466,291 +2493,32 @@ __global__ void __launch_bounds__(128) k_jpeg_emit(JpegEmit f) {
   visit_block_symbols(blk, qc, prev, f.zigzag, v);
   v.cur.finish();
 }
-
-// ---- one warp per unit --------------------------------------------------------------
-// The serial visitors above spend 64 dependent steps per thread on a third of a wave of
-// threads.  Here a warp owns a unit: lane l holds the zig-zag positions l and l + 32, the
-// nonzero pattern is a 64-bit mask from two ballots, the run before a coefficient is a bit
-// scan in that mask, and the bit position of a coefficient's code inside the unit is a warp
-// prefix sum.  A CTA (8 warps x 4 units) scans the lengths of its 32 consecutive units itself,
-// so the size pass is  unit_bits -> scan of the CTA totals -> emit  (three launches, was five).
-// Same symbols and bits as visit_block_symbols (EncodeDCTBlockSequential, g/jpeg_data_writer.cc:455).
-constexpr int kJpegWarpUnits = 32;  // units per CTA
-
-struct JpegWarpArgs {
-  const int16_t* cand;
-  const int* q;
-  const int* zigzag;
-  JpegCodes codes;
-  unsigned int* offset;  // [units] bit offset of a unit inside its CTA's group
-  unsigned int* sums;    // [ctas] bits of a CTA's group; after the scan: first bit of the group
-  unsigned int* words;
-  int nblocks, ncomp, units;
-};
-
-// What this lane contributes to the unit's bit string: up to two coefficients (DC for lane 0's
-// first one), each = nz x ZRL + code(sym) + nb extra bits; lane 31 also owns the end-of-block.
-struct JpegLanePieces {
-  int nz[2], sym[2], nb[2];
-  unsigned int extra[2];
-  bool on[2], eob;
-};
-
-__device__ __forceinline__ JpegLanePieces jpeg_lane_pieces(const JpegWarpArgs& f, int b, int c, int lane) {
-  JpegLanePieces p;
-  const int16_t* blk = f.cand + (static_cast<size_t>(c) * f.nblocks + b) * 64;
-  const int* qc = f.q + 64 * c;
-  const int nat0 = f.zigzag[lane], nat1 = f.zigzag[lane + 32];
-  const int v0 = blk[nat0], v1 = blk[nat1];
-  const unsigned int m_lo = __ballot_sync(0xffffffffu, v0 != 0) & ~1u;  // position 0 is the DC
-  const unsigned int m_hi = __ballot_sync(0xffffffffu, v1 != 0);
-  const unsigned long long mask = (static_cast<unsigned long long>(m_hi) << 32) | m_lo;
-  p.eob = (mask >> 63) == 0ull;  // the scan ends in a run of zeros
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int z = lane + 32 * h, v = h ? v1 : v0, nat = h ? nat1 : nat0;
-    p.nz[h] = 0;
-    p.sym[h] = 0;
-    p.nb[h] = 0;
-    p.extra[h] = 0u;
-    p.on[h] = false;
-    if (z == 0) {
-      const int prev = b > 0 ? div_exact_multiple((blk - 64)[0], qc[0]) : 0;
-      const int16_t dc = static_cast<int16_t>(div_exact_multiple(v, qc[0]));
-      int16_t diff = static_cast<int16_t>(dc - prev);
-      int16_t low = diff;
-      if (diff < 0) {
-        diff = static_cast<int16_t>(-diff);
-        --low;
-      }
-      const unsigned int mag = static_cast<unsigned int>(static_cast<int>(diff));
-      const int nb = mag == 0 ? 0 : hd_floor_log2_nz(mag) + 1;
-      p.sym[h] = nb;
-      p.nb[h] = nb;
-      p.extra[h] = static_cast<unsigned int>(low) & ((1u << nb) - 1u);
-      p.on[h] = true;
-    } else if (v != 0) {
-      const unsigned long long below = mask & ((1ull << z) - 1ull);
-      const int last = below ? 63 - __clzll(static_cast<long long>(below)) : 0;
-      const int run = z - 1 - last;
-      const int cq = div_exact_multiple(v, qc[nat]);
-      int m = cq, lo = cq;
-      if (cq < 0) {
-        m = -cq;
-        lo = ~m;
-      }
-      const int nbits = hd_floor_log2_nz(static_cast<unsigned int>(m)) + 1;
-      p.nz[h] = run >> 4;
-      p.sym[h] = ((run & 15) << 4) + nbits;
-      p.nb[h] = nbits;
-      p.extra[h] = static_cast<unsigned int>(lo) & ((1u << nbits) - 1u);
-      p.on[h] = true;
-    }
-  }
-  return p;
-}
-
-// code tables of the (up to) three components in shared memory: depth [6][256], code [6][256]
-struct JpegSmemCodes {
-  uint8_t depth[6 * 256];
-  uint16_t code[6 * 256];
-};
-__device__ __forceinline__ void jpeg_load_codes(JpegSmemCodes* s, const JpegCodes& g) {
-  for (int i = threadIdx.x; i < 6 * 256 / 4; i += blockDim.x)
-    reinterpret_cast<unsigned int*>(s->depth)[i] = reinterpret_cast<const unsigned int*>(g.depth)[i];
-  for (int i = threadIdx.x; i < 6 * 256 / 2; i += blockDim.x)
-    reinterpret_cast<unsigned int*>(s->code)[i] = reinterpret_cast<const unsigned int*>(g.code)[i];
-}
-
-// bits of this lane's half h (h = 1 of lane 31 includes the end-of-block)
-__device__ __forceinline__ unsigned int jpeg_lane_bits(const JpegLanePieces& p, int h, int lane, const uint8_t* dc_d,
-                                                       const uint8_t* ac_d) {
-  unsigned int n = 0;
-  if (p.on[h]) {
-    if (h == 0 && lane == 0) {
-      n = dc_d[p.sym[0]] + p.nb[0];
-    } else {
-      n = p.nz[h] * ac_d[0xf0] + ac_d[p.sym[h]] + p.nb[h];
-    }
-  }
-  if (h == 1 && lane == 31 && p.eob) n += ac_d[0];
-  return n;
-}
-
-__global__ void __launch_bounds__(256) k_jpeg_unit_bits_warp(JpegWarpArgs f) {
-  __shared__ JpegSmemCodes codes;
-  __shared__ unsigned int ubits[kJpegWarpUnits];
-  jpeg_load_codes(&codes, f.codes);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll 1
-  for (int t = 0; t < 4; ++t) {
-    const int slot = warp * 4 + t;
-    const int u = blockIdx.x * kJpegWarpUnits + slot;
-    unsigned int n = 0;
-    if (u < f.units) {
-      const int b = u / f.ncomp, c = u - b * f.ncomp;
-      const JpegLanePieces p = jpeg_lane_pieces(f, b, c, lane);
-      const uint8_t* dc_d = codes.depth + c * 256;
-      const uint8_t* ac_d = codes.depth + (3 + c) * 256;
-      n = jpeg_lane_bits(p, 0, lane, dc_d, ac_d) + jpeg_lane_bits(p, 1, lane, dc_d, ac_d);
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
-    }
-    if (lane == 0) ubits[slot] = n;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    const unsigned int v = ubits[lane];
-    unsigned int incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
-    }
-    const int u = blockIdx.x * kJpegWarpUnits + lane;
-    if (u < f.units) f.offset[u] = incl - v;
-    if (lane == 31) f.sums[blockIdx.x] = incl;
-  }
-}
-
-// ORs `n` bits (n <= 27, MSB first) at bit position `pos` of a zeroed shared-memory bit string
-__device__ __forceinline__ void jpeg_stage_put(unsigned int* stage, unsigned int& pos, int n, unsigned int value) {
-  if (n == 0) return;
-  const unsigned int w = pos >> 5, sh = pos & 31u;
-  const unsigned long long v = static_cast<unsigned long long>(value) << (64 - static_cast<int>(sh) - n);
-  atomicOr(&stage[w], static_cast<unsigned int>(v >> 32));
-  const unsigned int lo = static_cast<unsigned int>(v);
-  if (lo) atomicOr(&stage[w + 1], lo);
-  pos += static_cast<unsigned int>(n);
-}
-
-constexpr int kJpegStageWords = 64;  // a unit is at most 63 x 27 + 27 + 16 bits, plus 31 bits of lead-in
-
-__global__ void __launch_bounds__(256) k_jpeg_emit_warp(JpegWarpArgs f) {
-  __shared__ JpegSmemCodes codes;
-  __shared__ unsigned int stage_all[8][kJpegStageWords];
-  jpeg_load_codes(&codes, f.codes);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned int* stage = stage_all[warp];
-  const unsigned int group_first = f.sums[blockIdx.x];
-#pragma unroll 1
-  for (int t = 0; t < 4; ++t) {
-    const int u = blockIdx.x * kJpegWarpUnits + warp * 4 + t;
-    if (u >= f.units) break;  // uniform over the warp
-    stage[lane] = 0u;
-    stage[lane + 32] = 0u;
-    __syncwarp();
-    const int b = u / f.ncomp, c = u - b * f.ncomp;
-    const JpegLanePieces p = jpeg_lane_pieces(f, b, c, lane);
-    const uint8_t* dc_d = codes.depth + c * 256;
-    const uint8_t* ac_d = codes.depth + (3 + c) * 256;
-    const uint16_t* dc_c = codes.code + c * 256;
-    const uint16_t* ac_c = codes.code + (3 + c) * 256;
-    const unsigned int len0 = jpeg_lane_bits(p, 0, lane, dc_d, ac_d), len1 = jpeg_lane_bits(p, 1, lane, dc_d, ac_d);
-    unsigned int inc0 = len0, inc1 = len1;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned int a0 = __shfl_up_sync(0xffffffffu, inc0, d), a1 = __shfl_up_sync(0xffffffffu, inc1, d);
-      if (lane >= d) {
-        inc0 += a0;
-        inc1 += a1;
-      }
-    }
-    const unsigned int total0 = __shfl_sync(0xffffffffu, inc0, 31), total1 = __shfl_sync(0xffffffffu, inc1, 31);
-    const unsigned int first_bit = group_first + f.offset[u];
-    const unsigned int lead = first_bit & 31u;
-    unsigned int pos[2] = {lead + inc0 - len0, lead + total0 + inc1 - len1};
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (p.on[h]) {
-        if (h == 0 && lane == 0) {
-          jpeg_stage_put(stage, pos[0], dc_d[p.sym[0]], dc_c[p.sym[0]]);
-        } else {
-          for (int k = 0; k < p.nz[h]; ++k) jpeg_stage_put(stage, pos[h], ac_d[0xf0], ac_c[0xf0]);
-          jpeg_stage_put(stage, pos[h], ac_d[p.sym[h]], ac_c[p.sym[h]]);
-        }
-        jpeg_stage_put(stage, pos[h], p.nb[h], p.extra[h]);
-      }
-    }
-    if (lane == 31 && p.eob) jpeg_stage_put(stage, pos[1], ac_d[0], ac_c[0]);
-    __syncwarp();
-    // whole words of the unit are its own; the first and the last one are shared with the neighbours
-    const unsigned int nbits = lead + total0 + total1;
-    const int nw = static_cast<int>((nbits + 31u) >> 5);
-    unsigned int* out = f.words + (first_bit >> 5);
-    for (int w = lane; w < nw; w += 32) {
-      const unsigned int v = stage[w];
-      if (w == 0 || w == nw - 1) {
-        if (v) atomicOr(&out[w], v);
-      } else {
-        out[w] = v;
-      }
-    }
-    __syncwarp();
-  }
-}
 }  // namespace
 #endif
 
-// GB200_JPEG=thread keeps the one-thread-per-unit kernels (five launches and a mid-pass round
-// trip for the scan total); default: one warp per unit, the scan size taken from the host's
-// symbol counts (expected_bits) and checked against the device's at the end.
+// The length of the scan is known beforehand from the caller's symbol counts (expected_bits), so
+// the pass runs without a host round trip in the middle: unit lengths -> exclusive scan -> emit ->
+// 0xFF count, then one copy back of the device's own total (checked against the expectation) and
+// the count.
 void ImageContext::jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint16_t* code,
                                     unsigned long long expected_bits, size_t* nbytes, size_t* num_ff) {
+  if (expected_bits >= (1ull << 32)) throw std::runtime_error("jpeg scan exceeds 2^32 bits");
   h2d(j_depth_, depth, 6 * 256, s_);
   h2d(j_code_, code, 6 * 256 * sizeof(uint16_t), s_);
   JpegCodes codes{j_depth_, j_code_};
   const int units = g_.nblocks * ncomp;
-  if (expected_bits >= (1ull << 32)) throw std::runtime_error("jpeg scan exceeds 2^32 bits");
-#if !defined(GB200_HOSTSIM)
-  static const bool kWarpPerUnit = [] {
-    const char* e = getenv("GB200_JPEG");
-    return !(e != nullptr && e[0] == 't');
-  }();
-  if (kWarpPerUnit) {
-    const int ctas = (units + kJpegWarpUnits - 1) / kJpegWarpUnits;
-    if (static_cast<size_t>(ctas) > j_wsums_cap_) {
-      stream_sync(s_);
-      if (j_wsums_) { dev_free(j_wsums_); j_wsums_ = nullptr; }
-      j_wsums_cap_ = static_cast<size_t>(ctas) + 64;
-      // [cap] group sums | u64 scan total | u32 0xFF count | pad
-      j_wsums_ = static_cast<unsigned int*>(dev_alloc((j_wsums_cap_ + 8) * sizeof(unsigned int)));
-    }
-    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(j_wsums_ + ((j_wsums_cap_ + 1) & ~static_cast<size_t>(1)));
-    unsigned int* counter = reinterpret_cast<unsigned int*>(d_total + 1);
-    const unsigned long long total_bits = expected_bits;
-    const size_t nwords = static_cast<size_t>((total_bits + 31) >> 5);
-    if (nwords + 1 > j_words_cap_) {
-      stream_sync(s_);
-      if (j_words_) { dev_free(j_words_); j_words_ = nullptr; }
-      j_words_cap_ = nwords + nwords / 4 + 1024;
-      j_words_ = static_cast<unsigned int*>(dev_alloc(j_words_cap_ * sizeof(unsigned int)));
-    }
-    dev_zero(j_words_, (nwords + 1) * sizeof(unsigned int), s_);
-    dev_zero(counter, sizeof(unsigned int), s_);
-    JpegWarpArgs wa{d_cand_, d_q_, t_.zigzag, codes, j_offset_, j_wsums_, j_words_, g_.nblocks, ncomp, units};
-    note_launch("jpeg_unit_bits", s_, units);
-    k_jpeg_unit_bits_warp<<<ctas, 256, 0, s_>>>(wa);
-    note_launch_end("jpeg_unit_bits", s_);
-    note_launch("scan_sums", s_, ctas);
-    k_scan_sums<<<1, 1024, 0, s_>>>(j_wsums_, ctas, d_total);
-    note_launch_end("scan_sums", s_);
-    note_launch("jpeg_emit", s_, units);
-    k_jpeg_emit_warp<<<ctas, 256, 0, s_>>>(wa);
-    note_launch_end("jpeg_emit", s_);
-    if (nwords) launch_1d(s_, JpegCountFF{j_words_, total_bits, counter}, static_cast<int>(nwords), "jpeg_count_ff");
-    unsigned long long back[2] = {0, 0};  // scan total, 0xFF count
-    d2h(back, d_total, sizeof(back), s_);
-    if (back[0] != expected_bits)
-      throw std::runtime_error("jpeg scan: the device's bit count differs from the host's symbol counts");
-    j_nbytes_ = static_cast<size_t>((total_bits + 7) >> 3);
-    *nbytes = j_nbytes_;
-    *num_ff = static_cast<size_t>(back[1] & 0xffffffffull);
-    return;
+  const unsigned long long total_bits = expected_bits;
+  const size_t nwords = static_cast<size_t>((total_bits + 31) >> 5);
+  if (nwords + 1 > j_words_cap_) {
+    stream_sync(s_);
+    if (j_words_) { dev_free(j_words_); j_words_ = nullptr; }
+    j_words_cap_ = nwords + nwords / 4 + 1024;
+    j_words_ = static_cast<unsigned int*>(dev_alloc(j_words_cap_ * sizeof(unsigned int)));
   }
-#endif
+  dev_zero(j_words_, (nwords + 1) * sizeof(unsigned int), s_);
+  // [0] 0xFF count, [2..3] the scan's 64-bit total (copied here by the scan)
+  unsigned int* result = j_hist_ + static_cast<size_t>(kHistCopies + 1) * kHistStride + 2;
+  dev_zero(result, 4 * sizeof(unsigned int), s_);
 #if defined(GB200_HOSTSIM)
   launch_1d(s_, JpegUnitBits{d_cand_, d_q_, t_.zigzag, codes, j_bits_, g_.nblocks, ncomp}, units, "jpeg_unit_bits");
 #else
@@ -2759,18 +2527,7 @@ void ImageContext::jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint1
   k_jpeg_unit_bits<<<jgrid, 128, 0, s_>>>(JpegUnitBits{d_cand_, d_q_, t_.zigzag, codes, j_bits_, g_.nblocks, ncomp});
   note_launch_end("jpeg_unit_bits", s_);
 #endif
-  unsigned long long total_bits = 0;
-  exclusive_scan(j_bits_, j_offset_, units, &total_bits);
-  if (total_bits >= (1ull << 32)) throw std::runtime_error("jpeg scan exceeds 2^32 bits");
-  if (total_bits != expected_bits)
-    throw std::runtime_error("jpeg scan: the device's bit count differs from the host's symbol counts");
-  const size_t nwords = static_cast<size_t>((total_bits + 31) >> 5);
-  if (nwords + 1 > j_words_cap_) {
-    if (j_words_) { dev_free(j_words_); j_words_ = nullptr; }
-    j_words_cap_ = nwords + nwords / 4 + 1024;
-    j_words_ = static_cast<unsigned int*>(dev_alloc(j_words_cap_ * sizeof(unsigned int)));
-  }
-  dev_zero(j_words_, (nwords + 1) * sizeof(unsigned int), s_);
+  exclusive_scan_to(j_bits_, j_offset_, units, reinterpret_cast<unsigned long long*>(result + 2));
 #if defined(GB200_HOSTSIM)
   launch_1d(s_, JpegEmit{d_cand_, d_q_, t_.zigzag, codes, j_offset_, j_words_, g_.nblocks, ncomp}, units,
             "jpeg_emit");
@@ -2779,14 +2536,15 @@ void ImageContext::jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint1
   k_jpeg_emit<<<jgrid, 128, 0, s_>>>(JpegEmit{d_cand_, d_q_, t_.zigzag, codes, j_offset_, j_words_, g_.nblocks, ncomp});
   note_launch_end("jpeg_emit", s_);
 #endif
-  unsigned int* counter = j_hist_ + static_cast<size_t>(kHistCopies + 1) * kHistStride + 1;
-  dev_zero(counter, sizeof(unsigned int), s_);
-  launch_1d(s_, JpegCountFF{j_words_, total_bits, counter}, static_cast<int>(nwords), "jpeg_count_ff");
-  unsigned int ff = 0;
-  d2h(&ff, counter, sizeof(unsigned int), s_);
+  if (nwords) launch_1d(s_, JpegCountFF{j_words_, total_bits, result}, static_cast<int>(nwords), "jpeg_count_ff");
+  unsigned int back[4] = {0, 0, 0, 0};
+  d2h(back, result, sizeof(back), s_);
+  const unsigned long long device_bits = (static_cast<unsigned long long>(back[3]) << 32) | back[2];
+  if (device_bits != expected_bits)
+    throw std::runtime_error("jpeg scan: the device's bit count differs from the host's symbol counts");
   j_nbytes_ = static_cast<size_t>((total_bits + 7) >> 3);
   *nbytes = j_nbytes_;
-  *num_ff = ff;
+  *num_ff = back[0];
 }
 
 void ImageContext::jpeg_keep_scan() {

@@ -112,6 +112,8 @@ class ImageContext {
   // a15 without the download, plus the size of the order the weights imply
   void walk_weights(int direction, int radius, double target_distance, bool zero_distmap,
                     unsigned long long* order_size, unsigned long long* blocks_to_change);
+  void walk_weights_launch(int direction, int radius, double target_distance, bool zero_distmap);
+  void walk_weights_fetch(unsigned long long* order_size, unsigned long long* blocks_to_change);
   void download_weights(float* out);
   // nonzero coefficients of the candidate's two chroma components
   size_t count_nonzero_chroma();
@@ -327,8 +329,6 @@ class ImageContext {
   unsigned int* j_bits_ = nullptr;      // [3*nblocks] unit bit lengths (scan order)
   unsigned int* j_offset_ = nullptr;    // [3*nblocks] exclusive scan
   unsigned int* j_sums_ = nullptr;      // scan scratch
-  unsigned int* j_wsums_ = nullptr;     // warp-per-unit size pass: bits per group of 32 units | u64 total | 0xFF count
-  size_t j_wsums_cap_ = 0;
   uint8_t* j_file_ = nullptr;           // the assembled file (jpeg_fetch_file)
   size_t j_file_cap_ = 0;
   unsigned int* j_file_scratch_ = nullptr;
@@ -342,6 +342,7 @@ class ImageContext {
   size_t j_best_cap_ = 0;
   size_t j_best_nbytes_ = 0;
   void exclusive_scan(const unsigned int* in, unsigned int* out, int n, unsigned long long* total);
+  void exclusive_scan_to(const unsigned int* in, unsigned int* out, int n, unsigned long long* d_total);
   // same with caller-provided scratch for the per-CTA sums (n / 1024 + 8 words)
   void exclusive_scan_with(const unsigned int* in, unsigned int* out, int n, unsigned long long* total,
                            unsigned int* scratch);

@@ -713,8 +713,6 @@ class Search {
         st_->ms_sort += ms_since(t0);
         return -1;
       }
-      order.resize(n_slice);
-      ctx_->walk_fetch_pairs(n_slice, order.data());
     }
     ImageContext::BulkResult bulk;
     {
@@ -724,6 +722,12 @@ class Search {
       } else {
         ctx_->walk_bulk_apply(direction, i0 - base, &bulk, nullptr, split_count);
       }
+    }
+    if (!exact) {
+      // the sorted middle comes back after the bulk's kernels were queued: one wait covers both
+      Tick tk(&dt_[1]);
+      order.resize(n_slice);
+      ctx_->walk_fetch_pairs(n_slice, order.data());
     }
     st_->ms_sort += ms_since(t0);
     Clock::time_point tw = Clock::now();
@@ -875,6 +879,7 @@ class Search {
     // The candidate cursors and max errors also live on the device (walk_dev.h); the host
     // copies above (and cand_) are a mirror that iterations on the device path leave stale.
     ctx_->walk_begin();
+    weights_queued_ = false;
     fetched_.assign(num_blocks, 0);
     fetched_list_.clear();
     // GB200_WALK=host keeps every iteration on the host path, =device forces the device path.
@@ -900,8 +905,14 @@ class Search {
         for (int rblock = 1; rblock <= 4; ++rblock) {
           unsigned long long n_entries = 0, n_blocks = 0;
           Tick tk(&dt_[6]);
-          ctx_->walk_weights(direction, rblock, params_.butteraugli_target * target_mul, first_up_iter, &n_entries,
-                             &n_blocks);
+          if (weights_queued_ && rblock == 1 && queued_direction_ == direction && !first_up_iter) {
+            // queued behind the previous iteration's Compare: only the two sums are fetched
+            ctx_->walk_weights_fetch(&n_entries, &n_blocks);
+          } else {
+            ctx_->walk_weights(direction, rblock, params_.butteraugli_target * target_mul, first_up_iter, &n_entries,
+                               &n_blocks);
+          }
+          weights_queued_ = false;
           order_size = static_cast<size_t>(n_entries);
           blocks_to_change = static_cast<int>(n_blocks);
           if (order_size != 0) break;
@@ -1140,6 +1151,11 @@ class Search {
           ctx_->scatter_coeffs(m.edit_index, m.edit_value);
         }
         compare_begin();
+        // a15 of the next iteration (same direction, radius 1) needs nothing from the host: its
+        // kernels go behind the metric's, the sums are picked up at the top of the loop
+        ctx_->walk_weights_launch(direction, 1, params_.butteraugli_target * target_mul, false);
+        weights_queued_ = true;
+        queued_direction_ = direction;
         const size_t encoded = encoded_size(m.ac_h);
         logf("Iter %2d: %s(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
              st_->iterations, "f111111", 7, direction > 0 ? "up" : "down", static_cast<int>(out.consumed),
@@ -1192,6 +1208,8 @@ class Search {
     ~Tick() { *acc += ms_since(t0); }
   };
   bool device_done_ = false;   // the current iteration took the device path
+  bool weights_queued_ = false;  // block weights + order statistics of the next iteration are on the device
+  int queued_direction_ = 0;
   std::vector<char> fetched_;  // blocks whose state the host holds for the current iteration
   std::vector<int> fetched_list_;
   bool mirror_valid_ = true;   // cand_ / last_indexes / max_block_error equal the device's
