@@ -519,6 +519,10 @@ void gb200_debug_std_sort(int* block, float* key, size_t n) {
   }
 }
 
+void gb200_debug_huffman_depths(const uint32_t* counts, int n, int limit, uint8_t* depth) {
+  gb200::huffman_code_lengths(counts, n, limit, depth);
+}
+
 void gb200_trim_memory(void) {
 #if !defined(GB200_HOSTSIM)
   guarded([&]() { gb200::dev_trim(); });

@@ -164,6 +164,9 @@ int gb200_write_jpeg(const int16_t* coeffs, int w, int h, const int* q, uint8_t*
 /* test hooks: prefix-exact replay of std::sort on (block, key) pairs vs std::sort itself */
 size_t gb200_debug_partial_sort(int* block, float* key, size_t n, size_t want);
 void gb200_debug_std_sort(int* block, float* key, size_t n);
+/* test hook: length-limited Huffman code lengths of a symbol histogram (host side of the size pass and of
+ * the walk; CreateHuffmanTree, guetzli/entropy_encode.cc:73).  depth[n] must be zeroed by the caller. */
+void gb200_debug_huffman_depths(const uint32_t* counts, int n, int limit, uint8_t* depth);
 /* experimental: the replay with the large partition passes on the device */
 size_t gb200_debug_device_partial_sort(gb200_image* img, int* block, float* key, size_t n, size_t want);
 

@@ -34,6 +34,7 @@
 #include "guetzli/processor.cc"
 #undef private
 
+#include "guetzli/entropy_encode.h"
 #include "guetzli/fdct.h"
 #include "guetzli/idct.h"
 #include "guetzli/jpeg_data_encoder.h"
@@ -469,5 +470,11 @@ double gref_mask_lut(int which, double delta) {
 }
 
 double gref_gamma(double v) { return butteraugli::Gamma(v); }
+
+// CreateHuffmanTree (guetzli/entropy_encode.cc:73): depth[n] zeroed by the caller
+void gref_huffman_depths(const uint32_t* counts, int n, int limit, uint8_t* depth) {
+  std::vector<guetzli::HuffmanTree> tree(2 * static_cast<size_t>(n) + 1);
+  guetzli::CreateHuffmanTree(counts, static_cast<size_t>(n), limit, tree.data(), depth);
+}
 
 }  // extern "C"

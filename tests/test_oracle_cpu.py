@@ -157,3 +157,48 @@ def test_repeated_blocks_tie_everywhere(port_lib, ref):
     rgb = np.ascontiguousarray(np.tile(synth.noise(112, 112, 11), (1, 2, 1)))
     st = parity.check_process_vs_ref(port_lib, ref, rgb, 94)
     assert st.device["order_exact"] > 100 and st.device["order_partial"] > 50
+
+
+def test_huffman_code_lengths_match_reference(port_lib, ref):
+    """The sort-once builder of the code lengths (jpeg_out.cc huffman_code_lengths) against the
+    reference's CreateHuffmanTree (guetzli/entropy_encode.cc:73) on histograms that need anywhere
+    from one to many count floors, incl. ties, single symbols and the phantom symbol 256."""
+    import ctypes as C
+    rl = ref.lib()
+    rl.gref_huffman_depths.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    rl.gref_huffman_depths.restype = None
+    port_lib.gb200_debug_huffman_depths.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    port_lib.gb200_debug_huffman_depths.restype = None
+    rng = np.random.default_rng(77)
+    n = 257
+    for t in range(3000):
+        mode = t % 7
+        present = rng.random(n) < rng.uniform(0.02, 1.0)
+        if mode == 0:
+            c = rng.integers(1, 5, n)
+        elif mode == 1:
+            c = 1 << rng.integers(0, 28, n)
+        elif mode == 2:
+            c = rng.integers(1, 1 << int(rng.integers(2, 25)), n)
+        elif mode == 3:
+            c = 2 * rng.integers(1, 1000, n)
+        elif mode == 4:
+            c = np.where(rng.random(n) < 0.3, 1, rng.integers(1, 5_000_000, n))
+        elif mode == 5:
+            c = (1 + 4_000_000 * rng.random(n) ** 8).astype(np.int64)
+        else:  # Fibonacci-like counts: the deepest possible trees
+            c = np.ones(n, dtype=np.int64)
+            f = [1, 1]
+            while len(f) < 40:
+                f.append(f[-1] + f[-2])
+            idx = rng.permutation(n)[:40]
+            c[idx] = np.array(f[:40], dtype=np.int64)
+            present[idx] = True
+        counts = np.where(present, c, 0).astype(np.uint32)
+        counts[256] = 1
+        limit = 12 if t % 11 == 0 else 16
+        a = np.zeros(n, dtype=np.uint8)
+        b = np.zeros(n, dtype=np.uint8)
+        rl.gref_huffman_depths(counts.ctypes.data, n, limit, a.ctypes.data)
+        port_lib.gb200_debug_huffman_depths(counts.ctypes.data, n, limit, b.ctypes.data)
+        assert np.array_equal(a, b), (t, mode)
