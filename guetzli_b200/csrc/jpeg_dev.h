@@ -151,34 +151,27 @@ struct JpegUnitBits {  // 1D over nblocks * ncomp
 };
 
 // Bit sink writing MSB-first into big-endian 32-bit words.  Bits are gathered in a
-// 64-bit register and leave as whole words: the first and the last word of a unit are
-// shared with its neighbours (atomic OR; the bits that belong to the neighbours are zero
-// in our word), the words in between are the unit's own (plain stores).
+// 64-bit register and leave as whole words with one atomic OR each (the first and
+// last word of a unit are shared with its neighbours; the bits that belong to the
+// neighbours are zero in our word, so OR-ing is safe).  Plain stores for the words in
+// between were measured slower on the B200 (48 vs 37 us per 1080p launch).
 struct BitCursor {
   unsigned int* words;
   unsigned long long word;  // index of the next word to write
   unsigned long long acc;   // pending bits, right-aligned
   int nacc;                 // number of pending bits (< 32 between calls)
-  bool shared;              // the next word to leave also holds bits of the preceding unit
   GB_HD void start(unsigned int* w, unsigned long long bit_pos) {
     words = w;
     word = bit_pos >> 5;
     acc = 0;
     nacc = static_cast<int>(bit_pos & 31);  // leading zero bits stand in for the neighbour's bits
-    shared = nacc != 0;
   }
   GB_HD void put(int n, unsigned int value) {  // n <= 27
     acc = (acc << n) | value;
     nacc += n;
     if (nacc >= 32) {
       nacc -= 32;
-      // a whole word that starts inside this unit belongs to it alone: plain store
-      if (shared) {
-        hd_atomic_or(&words[word], static_cast<unsigned int>(acc >> nacc));
-        shared = false;
-      } else {
-        words[word] = static_cast<unsigned int>(acc >> nacc);
-      }
+      hd_atomic_or(&words[word], static_cast<unsigned int>(acc >> nacc));
       ++word;
       acc &= (1ull << nacc) - 1ull;
     }

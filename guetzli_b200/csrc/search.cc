@@ -1150,18 +1150,25 @@ class Search {
           Tick tk(&dt_[7]);
           ctx_->scatter_coeffs(m.edit_index, m.edit_value);
         }
-        compare_begin();
-        // a15 of the next iteration (same direction, radius 1) needs nothing from the host: its
-        // kernels go behind the metric's, the sums are picked up at the top of the loop
-        ctx_->walk_weights_launch(direction, 1, params_.butteraugli_target * target_mul, false);
-        weights_queued_ = true;
-        queued_direction_ = direction;
+        // GB200_OVERLAP=0 (A/B aid): size pass first, then the whole Compare, nothing queued ahead
+        static const bool kOverlap = [] {
+          const char* e = getenv("GB200_OVERLAP");
+          return !(e != nullptr && e[0] == '0');
+        }();
+        if (kOverlap) {
+          compare_begin();
+          // a15 of the next iteration (same direction, radius 1) needs nothing from the host: its
+          // kernels go behind the metric's, the sums are picked up at the top of the loop
+          ctx_->walk_weights_launch(direction, 1, params_.butteraugli_target * target_mul, false);
+          weights_queued_ = true;
+          queued_direction_ = direction;
+        }
         const size_t encoded = encoded_size(m.ac_h);
         logf("Iter %2d: %s(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
              st_->iterations, "f111111", 7, direction > 0 ? "up" : "down", static_cast<int>(out.consumed),
              order_size, out.changed_blocks, blocks_to_change, num_blocks, out.val_threshold, encoded,
              100.0 - (100.0 * out.est_jpg_size) / encoded);
-        compare_end();
+        if (kOverlap) compare_end(); else compare();
         maybe_output(encoded);
         prev_size = out.est_jpg_size;
       }
