@@ -10,7 +10,9 @@ import parity
 
 
 @pytest.mark.parametrize("name,world", [("gradnoise_128x128_s11_q84", 2), ("odd_70x51_s3_q88", 3),
-                                        ("gray_64x64_s9_q90", 2), ("bees_444x258_q95", 3)])
+                                        ("gray_64x64_s9_q90", 2), ("bees_444x258_q95", 3),
+                                        # strips narrower than the 7-block-row halo: 8 ranks on 16 block rows
+                                        ("gradnoise_128x128_s11_q84", 8), ("odd_70x51_s3_q88", 4)])
 def test_strip_mode_matches_golden(port_lib, name, world):
     g = parity.GOLDEN[name]
     rgb = parity.golden_input(name)
