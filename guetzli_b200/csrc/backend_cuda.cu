@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <map>
+#include <string.h>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -168,8 +169,40 @@ static void wait_stream(Stream s) {
   GB_CUDA(cudaEventSynchronize(ev));
 }
 
+// Small results (sums, counters, the window's block states: ≈7 per iteration of the search) come
+// back through a pinned per-thread mailbox: a copy into pageable memory is staged by the driver
+// and waits on its own; the pinned copy is a plain DMA followed by the stream wait.
+namespace {
+constexpr size_t kMailboxBytes = 64 << 10;
+struct Mailbox {
+  void* p = nullptr;
+  bool tried = false;
+  ~Mailbox() {
+    if (p) cudaFreeHost(p);
+  }
+};
+void* mailbox() {
+  thread_local Mailbox m;
+  if (!m.tried) {
+    m.tried = true;
+    if (cudaHostAlloc(&m.p, kMailboxBytes, cudaHostAllocPortable) != cudaSuccess) {
+      m.p = nullptr;
+      cudaGetLastError();  // pageable copies then
+    }
+  }
+  return m.p;
+}
+}  // namespace
+
 void d2h(void* dst, const void* src, size_t n, Stream s) {
   g_d2h_bytes += static_cast<long long>(n);
+  void* pin = n <= kMailboxBytes ? mailbox() : nullptr;
+  if (pin != nullptr) {
+    GB_CUDA(cudaMemcpyAsync(pin, src, n, cudaMemcpyDeviceToHost, s));
+    wait_stream(s);
+    memcpy(dst, pin, n);
+    return;
+  }
   GB_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, s));
   wait_stream(s);
 }

@@ -2000,7 +2000,8 @@ void ImageContext::walk_fetch_sorted(size_t first, size_t n, float* val, int* bl
   d2h(block, d_sel_block_ + first, n * sizeof(int), s_);
 }
 
-void ImageContext::walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, const int* host_blocks, bool after_split) {
+void ImageContext::walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, const int* host_blocks, bool after_split,
+                                   size_t gather_first, size_t gather_n) {
   const int* entry_blocks = d_sel_block_;
   if (host_blocks != nullptr) {
     if (nbulk > w_acap_) {
@@ -2080,6 +2081,15 @@ void ImageContext::walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, c
       note_launch_end("walk_bulk_apply", s_);
     }
 #endif
+    if (gather_n > 0) {
+      if (gather_first + gather_n > sel_sorted_) throw std::runtime_error("walk_bulk_apply: gather outside the selection");
+      gather_reserve(gather_n);
+      const size_t n = gather_n;
+      int* d_cursor = reinterpret_cast<int*>(w_gcoeffs_ + n * 192);
+      launch_1d(s_, GatherBlockState{d_sel_block_ + gather_first, d_cand_, d_last_index_, w_stamp_, w_iter_, g_.nblocks,
+                                     w_gcoeffs_, d_cursor, d_cursor + n},
+                static_cast<int>(24 * n), "walk_gather");
+    }
     d2h(host_counters, w_counters_, sizeof(host_counters), s_);
   }
   r->touched = static_cast<int>(host_counters[0]);
@@ -2102,13 +2112,7 @@ void ImageContext::walk_bulk_undo(int direction) {
   pending_touched_ = 0;
 }
 
-void ImageContext::walk_gather(const std::vector<int>& blocks, std::vector<int16_t>* coeffs, std::vector<int>* cursor,
-                               std::vector<int>* in_bulk) {
-  const size_t n = blocks.size();
-  coeffs->resize(n * 192);
-  cursor->resize(n);
-  in_bulk->resize(n);
-  if (n == 0) return;
+void ImageContext::gather_reserve(size_t n) {
   if (n > w_gcap_) {
     stream_sync(s_);
     if (w_gblocks_) { dev_free(w_gblocks_); w_gblocks_ = nullptr; }
@@ -2118,18 +2122,41 @@ void ImageContext::walk_gather(const std::vector<int>& blocks, std::vector<int16
     // one buffer, one copy back: [cap][192] int16 | [cap] cursors | [cap] flags
     w_gcoeffs_ = static_cast<int16_t*>(dev_alloc(w_gcap_ * (192 * sizeof(int16_t) + 2 * sizeof(int))));
   }
-  int* d_cursor = reinterpret_cast<int*>(w_gcoeffs_ + n * 192);
-  int* d_inbulk = d_cursor + n;
-  h2d(w_gblocks_, blocks.data(), n * sizeof(int), s_);
-  launch_1d(s_, GatherBlockState{w_gblocks_, d_cand_, d_last_index_, w_stamp_, w_iter_, g_.nblocks, w_gcoeffs_, d_cursor,
-                                 d_inbulk},
-            static_cast<int>(24 * n), "walk_gather");
+}
+
+void ImageContext::gather_fetch(size_t n, std::vector<int16_t>* coeffs, std::vector<int>* cursor, std::vector<int>* in_bulk) {
   const size_t bytes = n * (192 * sizeof(int16_t) + 2 * sizeof(int));
   gather_host_.resize(bytes);
   d2h(gather_host_.data(), w_gcoeffs_, bytes, s_);
   memcpy(coeffs->data(), gather_host_.data(), n * 192 * sizeof(int16_t));
   memcpy(cursor->data(), gather_host_.data() + n * 192 * sizeof(int16_t), n * sizeof(int));
   memcpy(in_bulk->data(), gather_host_.data() + n * 192 * sizeof(int16_t) + n * sizeof(int), n * sizeof(int));
+}
+
+void ImageContext::walk_gather_selection_fetch(size_t n, std::vector<int16_t>* coeffs, std::vector<int>* cursor,
+                                               std::vector<int>* in_bulk) {
+  coeffs->resize(n * 192);
+  cursor->resize(n);
+  in_bulk->resize(n);
+  if (n == 0) return;
+  gather_fetch(n, coeffs, cursor, in_bulk);
+}
+
+void ImageContext::walk_gather(const std::vector<int>& blocks, std::vector<int16_t>* coeffs, std::vector<int>* cursor,
+                               std::vector<int>* in_bulk) {
+  const size_t n = blocks.size();
+  coeffs->resize(n * 192);
+  cursor->resize(n);
+  in_bulk->resize(n);
+  if (n == 0) return;
+  gather_reserve(n);
+  int* d_cursor = reinterpret_cast<int*>(w_gcoeffs_ + n * 192);
+  int* d_inbulk = d_cursor + n;
+  h2d(w_gblocks_, blocks.data(), n * sizeof(int), s_);
+  launch_1d(s_, GatherBlockState{w_gblocks_, d_cand_, d_last_index_, w_stamp_, w_iter_, g_.nblocks, w_gcoeffs_, d_cursor,
+                                 d_inbulk},
+            static_cast<int>(24 * n), "walk_gather");
+  gather_fetch(n, coeffs, cursor, in_bulk);
 }
 
 void ImageContext::walk_advance(const std::vector<int>& blocks, int direction) {

@@ -136,8 +136,13 @@ class ImageContext {
   // consumes entries [0, nbulk) of the sorted selection on the device; host_blocks != nullptr:
   // the entries' blocks come from the host instead (prefix of the reference-ordered sort)
   // after_split: the counts of walk_select_split are pending and are consumed as well
+  // gather_n > 0: the state of the blocks of selection entries [gather_first, gather_first + gather_n)
+  // is gathered right behind the bulk's kernels (walk_gather_selection_fetch picks it up)
   void walk_bulk_apply(int direction, size_t nbulk, BulkResult* r, const int* host_blocks = nullptr,
-                       bool after_split = false);
+                       bool after_split = false, size_t gather_first = 0, size_t gather_n = 0);
+  // per entry of that range (a block may repeat): [n][3][64] coefficients, cursor, "touched by the bulk"
+  void walk_gather_selection_fetch(size_t n, std::vector<int16_t>* coeffs, std::vector<int>* cursor,
+                                   std::vector<int>* in_bulk);
   void walk_bulk_undo(int direction);
   void walk_gather(const std::vector<int>& blocks, std::vector<int16_t>* coeffs, std::vector<int>* cursor,
                    std::vector<int>* in_bulk);
@@ -291,6 +296,8 @@ class ImageContext {
   void compare_render();
   bool compare_pending_ = false;
   std::vector<int> advance_host_;  // source of walk_advance's upload
+  void gather_reserve(size_t n);
+  void gather_fetch(size_t n, std::vector<int16_t>* coeffs, std::vector<int>* cursor, std::vector<int>* in_bulk);
   float compare_stash_ = 0.0f;
   bool from_coeffs_ = false;  // original given as coefficients (JPEG input)
   void init(const uint8_t* rgb, const int16_t* dq_coeffs, int w, int h, bool prepare_now);

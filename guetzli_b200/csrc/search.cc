@@ -715,12 +715,16 @@ class Search {
       }
     }
     ImageContext::BulkResult bulk;
+    size_t pre_first = 0, pre_n = 0;
     {
       Tick tk(&dt_[2]);
       if (exact) {
         ctx_->walk_bulk_apply(direction, i0, &bulk, bulk_blocks.data());
       } else {
-        ctx_->walk_bulk_apply(direction, i0 - base, &bulk, nullptr, split_count);
+        // the window's first chunk: its block states are gathered right behind the bulk
+        pre_first = i0 - base;
+        pre_n = std::min<size_t>(64, usable_end > pre_first ? usable_end - pre_first : 0);
+        ctx_->walk_bulk_apply(direction, i0 - base, &bulk, nullptr, split_count, pre_first, pre_n);
       }
     }
     if (!exact) {
@@ -753,23 +757,31 @@ class Search {
       const size_t end = std::min(usable_end, pos + chunk);
       // state of the blocks of this chunk that the host does not hold yet
       std::vector<int> need;
+      std::vector<size_t> slot;  // where a needed block's state sits in the gathered arrays
+      const bool pre = pre_n > 0 && pos == pre_first && end - pos == pre_n;
       for (size_t i = pos; i < end; ++i) {
         const int b = order[i].first;
         if (!fetched_[b]) {
           fetched_[b] = 1;
           fetched_list_.push_back(b);
           need.push_back(b);
+          slot.push_back(pre ? i - pos : need.size() - 1);
         }
       }
       std::vector<int16_t> gc;
       std::vector<int> gcur, gin;
       {
         Tick tk(&dt_[3]);
-        ctx_->walk_gather(need, &gc, &gcur, &gin);
+        if (pre) {
+          ctx_->walk_gather_selection_fetch(pre_n, &gc, &gcur, &gin);  // one slot per entry, queued with the bulk
+        } else {
+          ctx_->walk_gather(need, &gc, &gcur, &gin);
+        }
       }
       Tick tk4(&dt_[4]);
-      for (size_t e = 0; e < need.size(); ++e) {
-        const int b = need[e];
+      for (size_t k = 0; k < need.size(); ++k) {
+        const int b = need[k];
+        const size_t e = slot[k];
         for (int c = 0; c < 3; ++c)
           memcpy(&cand_[c * per + static_cast<size_t>(b) * 64], &gc[(e * 3 + c) * 64], 64 * sizeof(int16_t));
         m.last_indexes[b] = gcur[e];
