@@ -14,37 +14,6 @@ namespace {
 inline int floor_log2_nz(uint32_t n) { return 31 ^ __builtin_clz(n); }
 inline int floor_log2(uint32_t n) { return n == 0 ? -1 : floor_log2_nz(n); }
 
-struct TreeNode {
-  uint32_t count;
-  int16_t left;            // -1 for leaves
-  int16_t right_or_value;  // symbol for leaves
-};
-
-// Depth of every leaf below root; false if any leaf is deeper than limit.
-bool assign_depths(const TreeNode* pool, int root, int limit, uint8_t* depth) {
-  int stack_node[64], stack_level[64];
-  int sp = 0;
-  stack_node[sp] = root;
-  stack_level[sp] = 0;
-  ++sp;
-  while (sp > 0) {
-    --sp;
-    const int p = stack_node[sp], level = stack_level[sp];
-    if (pool[p].left >= 0) {
-      if (level + 1 > limit) return false;
-      stack_node[sp] = pool[p].right_or_value;
-      stack_level[sp] = level + 1;
-      ++sp;
-      stack_node[sp] = pool[p].left;
-      stack_level[sp] = level + 1;
-      ++sp;
-    } else {
-      depth[pool[p].right_or_value] = static_cast<uint8_t>(level);
-    }
-  }
-  return true;
-}
-
 }  // namespace
 
 // Length-limited code lengths as g/entropy_encode.cc:73 builds them: Huffman tree over the
@@ -602,19 +571,6 @@ std::string write_jpeg(const CoeffImage& img) {
       }
     }
     bw.finish();
-  }
-  out.append(plan.trailer);
-  return out;
-}
-
-// Turns the raw (unstuffed, padded) scan bytes into the final file.
-std::string assemble_jpeg(const JpegPlan& plan, const uint8_t* scan, size_t nbytes) {
-  std::string out;
-  out.reserve(plan.prefix.size() + nbytes + nbytes / 64 + 16);
-  out = plan.prefix;
-  for (size_t i = 0; i < nbytes; ++i) {
-    out.push_back(static_cast<char>(scan[i]));
-    if (scan[i] == 0xff) out.push_back(0);
   }
   out.append(plan.trailer);
   return out;

@@ -106,7 +106,6 @@ struct JpegPlan {
 };
 JpegPlan plan_jpeg(const CoeffImage& img, int ncomp, SymbolHistogram* dc_h, SymbolHistogram* ac_h);
 void host_symbol_histograms(const CoeffImage& img, int ncomp, SymbolHistogram* dc_h, SymbolHistogram* ac_h);
-std::string assemble_jpeg(const JpegPlan& plan, const uint8_t* scan, size_t nbytes);
 // EOI plus whatever follows it (the input's tail bytes unless metadata is stripped).
 std::string jpeg_trailer(const CoeffImage& img);
 

@@ -2586,20 +2586,6 @@ void ImageContext::jpeg_keep_scan() {
   j_best_nbytes_ = j_nbytes_;
 }
 
-void ImageContext::jpeg_fetch_kept_scan(std::vector<uint8_t>* scan) {
-  std::swap(j_words_, j_best_words_);
-  std::swap(j_nbytes_, j_best_nbytes_);
-  try {
-    jpeg_fetch_scan(scan);
-  } catch (...) {
-    std::swap(j_words_, j_best_words_);
-    std::swap(j_nbytes_, j_best_nbytes_);
-    throw;
-  }
-  std::swap(j_words_, j_best_words_);
-  std::swap(j_nbytes_, j_best_nbytes_);
-}
-
 // f1: prefix | stuffed scan | trailer assembled on the device, one copy back.
 void ImageContext::jpeg_fetch_file(const std::string& prefix, const std::string& trailer, std::string* file) {
   bind();
@@ -2651,21 +2637,6 @@ void ImageContext::jpeg_fetch_kept_file(const std::string& prefix, const std::st
   }
   std::swap(j_words_, j_best_words_);
   std::swap(j_nbytes_, j_best_nbytes_);
-}
-
-void ImageContext::jpeg_fetch_scan(std::vector<uint8_t>* scan) {
-  const size_t nwords = (j_nbytes_ + 3) / 4;
-  std::vector<unsigned int> words(nwords);
-  if (nwords) d2h(words.data(), j_words_, nwords * sizeof(unsigned int), s_);
-  scan->resize(nwords * 4);
-  for (size_t i = 0; i < nwords; ++i) {
-    const unsigned int v = words[i];
-    (*scan)[4 * i + 0] = static_cast<uint8_t>(v >> 24);
-    (*scan)[4 * i + 1] = static_cast<uint8_t>(v >> 16);
-    (*scan)[4 * i + 2] = static_cast<uint8_t>(v >> 8);
-    (*scan)[4 * i + 3] = static_cast<uint8_t>(v);
-  }
-  scan->resize(j_nbytes_);
 }
 
 void ImageContext::debug_blur(const float* in, float* out, int id) {

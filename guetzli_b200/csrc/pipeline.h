@@ -155,17 +155,15 @@ class ImageContext {
   void jpeg_histograms(unsigned int* hist, bool* chroma_nonzero);
   // Entropy-codes the scan with the given canonical codes (depth/code [6][256]).
   // Returns the number of scan bytes before 0xFF stuffing and the number of 0xFF
-  // bytes among them; the bytes stay on the device until jpeg_fetch_scan().
+  // bytes among them; the bytes stay on the device until jpeg_fetch_file().
   // expected_bits: length of the scan as the caller's symbol counts give it (sum over the symbols of
   // count x (code length + extra bits)); sizes the buffers without a round trip and is checked
   // against the device's own total
   void jpeg_encode_scan(int ncomp, const uint8_t* depth, const uint16_t* code, unsigned long long expected_bits,
                         size_t* nbytes, size_t* num_ff);
-  void jpeg_fetch_scan(std::vector<uint8_t>* scan);  // nbytes raw (unstuffed, padded) bytes
   // keeps a device-side copy of the scan just encoded (the best output so far); the bytes
   // cross PCIe once, when the search is over
   void jpeg_keep_scan();
-  void jpeg_fetch_kept_scan(std::vector<uint8_t>* scan);
   // f1: the whole file = prefix | scan with a zero byte after every 0xFF | trailer, assembled on
   // the device from the current / the kept scan (jpeg_dev.h), one copy back
   void jpeg_fetch_file(const std::string& prefix, const std::string& trailer, std::string* file);
