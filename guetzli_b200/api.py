@@ -80,6 +80,7 @@ def load_library(path=None):
         getattr(lib, "gb200_image_" + name).argtypes = [C.c_void_p] + (
             [] if name == "num_blocks" else [C.c_void_p])
     lib.gb200_image_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.gb200_image_save_jpeg.argtypes = [C.c_void_p, C.c_void_p, P(P(C.c_uint8)), P(C.c_size_t)]
     lib.gb200_image_block_weights.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p]
     lib.gb200_image_zeroing_orders.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gb200_image_debug_blur.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -399,6 +400,16 @@ class DeviceImage:
         i = np.ascontiguousarray(index, dtype=np.int32)
         v = np.ascontiguousarray(value, dtype=np.int16)
         self._ck(self.lib.gb200_image_scatter(self._h, i.ctypes.data, v.ctypes.data, len(i)))
+
+    def save_jpeg(self, q):
+        """SaveToJpegData + WriteJpeg of the current candidate, entropy-coded and assembled on the device."""
+        q = np.ascontiguousarray(q, dtype=np.int32)
+        out = C.POINTER(C.c_uint8)()
+        out_len = C.c_size_t()
+        self._ck(self.lib.gb200_image_save_jpeg(self._h, q.ctypes.data, C.byref(out), C.byref(out_len)))
+        data = C.string_at(out, out_len.value)
+        self.lib.gb200_free(out)
+        return data
 
     def compare(self):
         d = C.c_float()

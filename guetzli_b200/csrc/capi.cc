@@ -482,6 +482,17 @@ int gb200_write_jpeg(const int16_t* coeffs, int w, int h, const int* q, uint8_t*
   });
 }
 
+int gb200_image_save_jpeg(gb200_image* img, const int* q, uint8_t** out, size_t* out_len) {
+  return guarded([&]() {
+    img->ctx->bind();
+    std::string s;
+    gb200::device_save_jpeg(img->ctx, q, &s);
+    *out = static_cast<uint8_t*>(malloc(s.size() + 1));
+    memcpy(*out, s.data(), s.size());
+    *out_len = s.size();
+  });
+}
+
 // test hooks for the prefix-exact std::sort replay (exact_sort.h)
 size_t gb200_debug_partial_sort(int* block, float* key, size_t n, size_t want) {
   std::vector<gb200::exact_sort::Item> v(n);

@@ -756,6 +756,9 @@ void ImageContext::apply_global_quant(const int q[192]) {
             "quantize_coeffs");
 }
 
+// the quant tables the candidate's coefficients are multiples of, without re-quantising it
+void ImageContext::set_quant(const int q[192]) { h2d(d_q_, q, 192 * sizeof(int), s_); }
+
 void ImageContext::scatter_coeffs(const std::vector<int>& index, const std::vector<int16_t>& value) {
   const int n = static_cast<int>(index.size());
   if (n == 0) return;

@@ -68,6 +68,7 @@ class ImageContext {
 
   // a8: candidate := Quantize(original, q) for all coefficients. q: [3][64].
   void apply_global_quant(const int q[192]);
+  void set_quant(const int q[192]);  // tables only (the candidate is given, upload_candidate)
   // Sparse edits of the candidate: flat indices into [3][nblocks][64].
   void scatter_coeffs(const std::vector<int>& index, const std::vector<int16_t>& value);
   // Whole candidate from the host (tests).

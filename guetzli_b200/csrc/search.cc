@@ -1246,6 +1246,45 @@ class Search {
 
 }  // namespace
 
+void device_save_jpeg(ImageContext* ctx, const int q[192], std::string* out) {
+  const Geom& g = ctx->geom();
+  CoeffImage img;
+  img.w = g.w;
+  img.h = g.h;
+  img.bw = g.bw;
+  img.bh = g.bh;
+  img.nblocks = g.nblocks;
+  img.coeffs = nullptr;  // the coefficients stay on the device
+  memcpy(img.q, q, sizeof(img.q));
+  ctx->set_quant(q);
+  unsigned int hist[6][257];
+  bool chroma = false;
+  ctx->jpeg_histograms(&hist[0][0], &chroma);
+  const int ncomp = chroma ? 3 : 1;  // num_output_components (g/output_image.cc:357)
+  SymbolHistogram dc_h[3], ac_h[3];
+  uint32_t raw[6][256];
+  memset(raw, 0, sizeof(raw));
+  for (int c = 0; c < ncomp; ++c)
+    for (int i = 0; i < 256; ++i) {
+      raw[c][i] = hist[c][i];
+      raw[3 + c][i] = hist[3 + c][i];
+      dc_h[c].counts[i] = 2 * hist[c][i];
+      ac_h[c].counts[i] = 2 * hist[3 + c][i];
+    }
+  const JpegPlan plan = plan_jpeg(img, ncomp, dc_h, ac_h);
+  unsigned long long expected_bits = 0;
+  for (int c = 0; c < ncomp; ++c)
+    for (int i = 0; i < 256; ++i) {
+      expected_bits += static_cast<unsigned long long>(raw[c][i]) * (plan.depth[c][i] + (i & 15));
+      expected_bits += static_cast<unsigned long long>(raw[3 + c][i]) * (plan.depth[3 + c][i] + (i & 15));
+    }
+  size_t nbytes = 0, num_ff = 0;
+  ctx->jpeg_encode_scan(ncomp, &plan.depth[0][0], &plan.code[0][0], expected_bits, &nbytes, &num_ff);
+  ctx->jpeg_fetch_file(plan.prefix, plan.trailer, out);
+  if (out->size() != plan.prefix.size() + nbytes + num_ff + plan.trailer.size())
+    throw std::runtime_error("device JPEG size mismatch");
+}
+
 static bool check_params(const SearchParams& params, std::string* err) {
   if (params.butteraugli_target > 2.0f) {
     *err =

@@ -58,6 +58,11 @@ bool process_jpeg(const SearchParams& params, const uint8_t* data, size_t len, i
 bool process_rgb(const SearchParams& params, const uint8_t* rgb, int w, int h, int device, LogSink log,
                  void* log_user, std::string* jpeg_out, SearchStats* stats, std::string* err);
 
+// a11 as a call of its own (SaveToJpegData + WriteJpeg, g/output_image.cc:348, g/jpeg_data_writer.cc:540):
+// the JPEG file of the context's current candidate, whose coefficients are multiples of q[3][64];
+// symbol counts, entropy coding, byte stuffing and file assembly on the device.  Throws on error.
+void device_save_jpeg(ImageContext* ctx, const int q[192], std::string* out);
+
 // false + message when the image needs more than the 32-bit indices of the device lists
 bool image_size_supported(int w, int h, std::string* err);
 

@@ -139,6 +139,10 @@ int gb200_image_upload_candidate(gb200_image* img, const int16_t* coeffs);
 int gb200_image_download_candidate(gb200_image* img, int16_t* coeffs);
 /* sparse SetCoeffBlock edits: flat indices into [3][num_blocks][64] */
 int gb200_image_scatter(gb200_image* img, const int* index, const int16_t* value, int n);
+/* OutputImage::SaveToJpegData + WriteJpeg of the current candidate (guetzli/output_image.cc:348,
+ * guetzli/jpeg_data_writer.cc:540): symbol counts, entropy coding, 0xFF stuffing and file assembly on the
+ * device.  q[3][64]: the quant tables the candidate's coefficients are multiples of.  *out: gb200_free. */
+int gb200_image_save_jpeg(gb200_image* img, const int* q, uint8_t** out, size_t* out_len);
 /* ButteraugliComparator::Compare (guetzli/butteraugli_comparator.cc:63) */
 int gb200_image_compare(gb200_image* img, float* distance);
 int gb200_image_distmap(gb200_image* img, float* out /* [h][w] */);

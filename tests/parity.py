@@ -150,3 +150,63 @@ def check_process_vs_ref(lib, ref, rgb, quality, lookahead=3, new_zeroing_model=
             assert x == y, f"trace line {i}:\n  mine: {x}\n  ref : {y}"
     assert jpeg == rjpeg, "JPEG bytes differ"
     return st
+
+
+def adversarial_candidates(nblocks, q, seed):
+    """Candidate coefficient sets (multiples of q) that stress the entropy coder: zero runs of 16 and
+    more (ZRL), a lone last coefficient, all-zero blocks, the largest magnitudes the device quotient
+    supports, DC swings, zero chroma (one-component output), dense random blocks."""
+    rng = np.random.default_rng(seed)
+    zz = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,
+                   7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38,
+                   31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63])
+    q = np.asarray(q, dtype=np.int64).reshape(3, 64)
+    out = {}
+    # sparse: few nonzero coefficients far apart in zig-zag order -> ZRL symbols, end-of-block after a run
+    lv = np.zeros((3, nblocks, 64), dtype=np.int64)
+    for c in range(3):
+        for b in range(nblocks):
+            for z in rng.choice(np.arange(1, 64), size=int(rng.integers(0, 4)), replace=False):
+                lv[c, b, zz[z]] = int(rng.integers(-3, 4))
+            lv[c, b, 0] = int(rng.integers(-40, 41))
+    lv[0, : max(1, nblocks // 7), 1:] = 0          # DC-only blocks
+    lv[:, nblocks // 2, :] = 0                      # an all-zero MCU
+    lv[0, nblocks - 1, 1:] = 0
+    lv[0, nblocks - 1, 63] = 1                      # a lone coefficient at the very end: three ZRLs, no EOB
+    out["sparse"] = lv
+    # dense random levels incl. large magnitudes (|level * q| stays below 2^15)
+    lim = np.minimum(1023, 32767 // q)[:, None, :]
+    dense = rng.integers(-1023, 1024, (3, nblocks, 64))
+    dense = np.clip(dense, -lim, lim)
+    dense[:, :, 1:] = np.where(rng.random((3, nblocks, 63)) < 0.35, 0, dense[:, :, 1:])
+    out["dense"] = dense
+    # luma only: both chroma components zero -> a one-component file
+    gray = dense.copy()
+    gray[1:] = 0
+    out["gray"] = gray
+    # extreme DC differences
+    swing = np.zeros((3, nblocks, 64), dtype=np.int64)
+    swing[:, ::2, 0] = lim[:, 0, 0][:, None]
+    swing[:, 1::2, 0] = -lim[:, 0, 0][:, None]
+    out["dc_swing"] = swing
+    return {k: (v * q[:, None, :]).astype(np.int16) for k, v in out.items()}
+
+
+def check_device_save_jpeg(lib, ref, rgb, seed=0):
+    """a11 + f1 as one call (gb200_image_save_jpeg): the device's file equals the reference's
+    SaveToJpegData + WriteJpeg (and the host serialiser) on coefficient patterns that natural images rarely have."""
+    h, w, _ = rgb.shape
+    q = test_quant(seed)
+    img = gb.DeviceImage(rgb, lib=lib)
+    try:
+        img.apply_global_quant(q)
+        cases = {"quantised_original": img.download_candidate()}
+        cases.update(adversarial_candidates(img.nblocks, q, seed))
+        for name, coeffs in cases.items():
+            img.upload_candidate(coeffs)
+            got = img.save_jpeg(q)
+            want = ref.write_jpeg(coeffs, w, h, q)
+            assert got == want, (name, len(got), len(want))
+            assert got == gb.write_jpeg(coeffs, w, h, q, lib=lib), name
+    finally:
+        img.close()

@@ -28,6 +28,11 @@ def test_compare_and_block_kernels(cuda_lib, ref, h, w, seed):
     parity.check_compare_and_blocks(cuda_lib, ref, synth.noise(h, w, seed))
 
 
+@pytest.mark.parametrize("h,w,seed", [(64, 96, 7), (40, 33, 2), (264, 520, 5)])
+def test_device_save_jpeg(cuda_lib, ref, h, w, seed):
+    parity.check_device_save_jpeg(cuda_lib, ref, synth.gradnoise(h, w, seed), seed)
+
+
 @pytest.mark.parametrize("name", sorted(parity.GOLDEN))
 def test_process_matches_golden(cuda_lib, name):
     st = parity.check_golden(cuda_lib, name)

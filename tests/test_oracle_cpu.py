@@ -202,3 +202,8 @@ def test_huffman_code_lengths_match_reference(port_lib, ref):
         rl.gref_huffman_depths(counts.ctypes.data, n, limit, a.ctypes.data)
         port_lib.gb200_debug_huffman_depths(counts.ctypes.data, n, limit, b.ctypes.data)
         assert np.array_equal(a, b), (t, mode)
+
+
+@pytest.mark.parametrize("h,w,seed", [(64, 96, 7), (40, 33, 2), (72, 136, 5)])
+def test_port_device_save_jpeg(port_lib, ref, h, w, seed):
+    parity.check_device_save_jpeg(port_lib, ref, synth.gradnoise(h, w, seed), seed)
