@@ -1285,17 +1285,21 @@ void device_save_jpeg(ImageContext* ctx, const int q[192], std::string* out) {
     throw std::runtime_error("device JPEG size mismatch");
 }
 
+// IsGrayscale (g/processor.cc:782): both chroma components of the input are all zero
+static bool is_grayscale(ImageContext* ctx) {
+  const std::vector<int16_t>& c = ctx->orig_coeffs();
+  const size_t per = static_cast<size_t>(ctx->geom().nblocks) * 64;
+  for (size_t i = per; i < 3 * per; ++i)
+    if (c[i] != 0) return false;
+  return true;
+}
+
 static bool check_params(const SearchParams& params, std::string* err) {
   if (params.butteraugli_target > 2.0f) {
     *err =
         "Guetzli should be called with quality >= 84, otherwise the\n"
         "output will have noticeable artifacts. If you want to\n"
         "proceed anyway, please edit the source code.\n";
-    fputs(err->c_str(), stderr);
-    return false;
-  }
-  if (params.try_420 || params.force_420) {
-    *err = "guetzli_b200: YUV420 is outside the B200 hot path (DESIGN.md)\n";
     fputs(err->c_str(), stderr);
     return false;
   }
@@ -1349,6 +1353,14 @@ bool process_resident_impl(const SearchParams& params, ImageContext* ctx, const 
   const long long h2d0 = h2d_bytes_total(), d2h0 = d2h_bytes_total();
   ctx->prepare();
   const int w = ctx->width(), h = ctx->height();
+  // YUV420 (g/processor.cc:847-877) is not built.  The reference only goes there when the image is
+  // large enough for Butteraugli (:832-838) and force_420 is set, or try_420 is set and the image
+  // is not grayscale (IsGrayscale :782); everything else takes the 4:4:4 path below unchanged.
+  if (w >= 32 && h >= 32 && (params.force_420 || (params.try_420 && !is_grayscale(ctx)))) {
+    *err = "guetzli_b200: YUV420 is outside the B200 hot path (DESIGN.md)\n";
+    fputs(err->c_str(), stderr);
+    return false;
+  }
   // RGB input: EncodeRGBToJpeg gives the JPEGData the same JFIF APP0 that stripping writes
   // (g/jpeg_data_encoder.cc:53-64,73), so Params::clear_metadata makes no difference there
   const JpegMeta* meta = src ? &src->meta : nullptr;

@@ -87,6 +87,13 @@ void gref_free(void* p) { free(p); }
 static int g_clear_metadata = 1;
 void gref_set_clear_metadata(int on) { g_clear_metadata = on; }
 
+// Params::try_420 / force_420 for the gref_process_rgb* hooks (processor.h:32-33; default false).
+static int g_try_420 = 0, g_force_420 = 0;
+void gref_set_420(int try_420, int force_420) {
+  g_try_420 = try_420;
+  g_force_420 = force_420;
+}
+
 // _ex: also sets Params::zeroing_greedy_lookahead / new_zeroing_model (processor.h:35-36).
 int gref_process_rgb_ex(const uint8_t* rgb, int w, int h, float butteraugli_target, int lookahead, int new_model,
                         uint8_t** out, size_t* out_len, char** trace, size_t* trace_len, int* counters,
@@ -96,6 +103,8 @@ int gref_process_rgb_ex(const uint8_t* rgb, int w, int h, float butteraugli_targ
   params.zeroing_greedy_lookahead = lookahead;
   params.new_zeroing_model = new_model != 0;
   params.clear_metadata = g_clear_metadata != 0;
+  params.try_420 = g_try_420 != 0;
+  params.force_420 = g_force_420 != 0;
   guetzli::ProcessStats stats;
   std::string dbg;
   if (trace) stats.debug_output = &dbg;

@@ -207,3 +207,21 @@ def test_huffman_code_lengths_match_reference(port_lib, ref):
 @pytest.mark.parametrize("h,w,seed", [(64, 96, 7), (40, 33, 2), (72, 136, 5)])
 def test_port_device_save_jpeg(port_lib, ref, h, w, seed):
     parity.check_device_save_jpeg(port_lib, ref, synth.gradnoise(h, w, seed), seed)
+
+
+def test_420_flags_where_the_reference_stays_on_444(port_lib, ref):
+    """Params::try_420 on a grayscale image (IsGrayscale, processor.cc:782,846) and try_420 / force_420 on an
+    image too small for Butteraugli (:832-838) never reach the YUV420 code of the reference: same bytes and
+    trace as the reference run with the same flags."""
+    rl = ref.lib()
+    cases = [(parity.gray(64, 64, 9), 90, dict(try_420=True)),
+             (synth.gradnoise(20, 40, 5), 95, dict(force_420=True)),
+             (synth.gradnoise(20, 40, 5), 95, dict(try_420=True))]
+    try:
+        for rgb, quality, flags in cases:
+            rl.gref_set_420(int(flags.get("try_420", False)), int(flags.get("force_420", False)))
+            rok, rjpeg, rtrace, _, _ = ref.process_rgb(rgb, quality)
+            ok, jpeg, trace, _ = parity.run_process(port_lib, rgb, quality, **flags)
+            assert ok and rok and jpeg == rjpeg and trace == rtrace, flags
+    finally:
+        rl.gref_set_420(0, 0)
