@@ -377,14 +377,14 @@ size_t jpeg_header_bytes(const CoeffImage& img, int ncomp) {
   return n;
 }
 
-size_t compute_entropy_codes(const SymbolHistogram* h3, uint8_t* depths) {
+size_t compute_entropy_codes(const SymbolHistogram* h3, uint8_t* depths, int ncomp) {
   const int K = SymbolHistogram::kSize;
   SymbolHistogram clustered[3] = {h3[0], h3[1], h3[2]};
-  size_t num = 3;
+  size_t num = static_cast<size_t>(ncomp);
   int index[4];
   uint8_t cdepth[3 * SymbolHistogram::kSize];
   cluster_histograms(clustered, &num, index, cdepth);
-  for (int i = 0; i < 3; ++i) memcpy(&depths[i * K], &cdepth[index[i] * K], K);
+  for (int i = 0; i < ncomp; ++i) memcpy(&depths[i * K], &cdepth[index[i] * K], K);
   size_t bytes = 0;
   for (size_t i = 0; i < num; ++i) bytes += histogram_header_bits(clustered[i]) / 8;
   return bytes;

@@ -91,7 +91,9 @@ size_t jpeg_header_bytes(const CoeffImage& img);                        // g/jpe
 size_t jpeg_header_bytes(const CoeffImage& img, int ncomp);
 size_t estimate_dc_bytes_of(SymbolHistogram* dc_h, int ncomp);
 // g/processor.cc:497: per-component depths [3][257] + header bytes of the clustered codes.
-size_t compute_entropy_codes(const SymbolHistogram* h3, uint8_t* depths);
+// ncomp = number of histograms the reference holds there (jpg.components.size(), :583): 3, or 1 for the
+// one-component JPEGData of the YUV420 pass over a grayscale image
+size_t compute_entropy_codes(const SymbolHistogram* h3, uint8_t* depths, int ncomp = 3);
 size_t entropy_coded_bytes(const SymbolHistogram* h3, const uint8_t* depths);  // g/processor.cc:518
 
 // Everything of the file that precedes the entropy-coded scan (SOI, APP0, DQT,

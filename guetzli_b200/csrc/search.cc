@@ -78,7 +78,8 @@ double quant_heuristic_score(const int q[3][64]) {
 // of quant matrices (g/processor.cc:194-296).
 class QuantBisection {
  public:
-  QuantBisection() : lo_(-1.0), hi_(-1.0), total_csf_(0.0) {
+  // downsample: the generator of the YUV420 pass starts from score 0 (g/processor.cc:204)
+  explicit QuantBisection(bool downsample) : downsample_(downsample), lo_(-1.0), hi_(-1.0), total_csf_(0.0) {
     for (int k = 0; k < 64; ++k) total_csf_ += 3.0 * contrast_sensitivity(k);
   }
 
@@ -87,7 +88,7 @@ class QuantBisection {
       double hscore;
       if (hi_ == -1.0) {
         if (lo_ == -1.0) {
-          hscore = total_csf_;
+          hscore = downsample_ ? 0.0 : total_csf_;
         } else if (lo_ < 5.0 * total_csf_) {
           hscore = lo_ + total_csf_;
         } else {
@@ -140,6 +141,7 @@ class QuantBisection {
       score -= 3.0 * contrast_sensitivity(zz[k]);
     }
   }
+  bool downsample_;
   double lo_, hi_, total_csf_;
   std::vector<QuantTrial> tried_;
 };
@@ -161,6 +163,15 @@ class Search {
   }
 
   void set_meta(const JpegMeta* meta) { img_.meta = meta; }
+  // Params::force_420 on a grayscale image: the reference's YUV420 pass finds nothing to downsample
+  // (OutputImage::Downsample returns at once, g/output_image.cc:305) and runs, instead of the 4:4:4
+  // pass, on the one-component JPEGData that SaveToJpegData leaves (g/processor.cc:855-877): quant
+  // search from score 0, frequency masking of component 0 only with one AC histogram, and the
+  // second masking call (comp_mask 6) returns at once (:577).
+  void set_yuv420_gray() {
+    yuv420_gray_ = true;
+    sfm_ncomp_ = 1;
+  }
 
   // JPEG input: the original's own quant tables (q_in of g/processor.cc:825), file
   // structure and metadata.  All pointers must outlive run().
@@ -392,7 +403,7 @@ class Search {
   }
 
   bool select_quant_matrix(int best_q[3][64]) {
-    QuantBisection gen;
+    QuantBisection gen(yuv420_gray_);
     const float target_mul_high = 0.97f, target_mul_low = 0.95f;
     QuantTrial best = try_quant_matrix(target_mul_high, best_q);
     for (;;) {
@@ -406,7 +417,7 @@ class Search {
       }
     }
     memcpy(&best_q[0][0], &best.q[0][0], sizeof(best.q));
-    logf("\n%s selected quantization matrix:\n", "YUV444");
+    logf("\n%s selected quantization matrix:\n", yuv420_gray_ ? "YUV420" : "YUV444");
     log_quant(best_q);
     return best.dist_ok;
   }
@@ -612,7 +623,8 @@ class Search {
       }
       out.val_threshold = order[i].second;
       out.consumed = gi + 1;
-      if (refresh_here) m.ac_histogram_size = static_cast<int>(compute_entropy_codes(m.ac_h, m.ac_depths.data()));
+      if (refresh_here)
+        m.ac_histogram_size = static_cast<int>(compute_entropy_codes(m.ac_h, m.ac_depths.data(), sfm_ncomp_));
       if (eval_here) {
         out.est_jpg_size = m.header_size + m.dc_size + m.ac_histogram_size +
                            static_cast<int>(entropy_coded_bytes(m.ac_h, m.ac_depths.data()));
@@ -878,7 +890,7 @@ class Search {
       chroma_nz_ = static_cast<long long>(ctx_->count_nonzero_chroma());
     }
     m.ac_depths.resize(3 * SymbolHistogram::kSize);
-    m.ac_histogram_size = static_cast<int>(compute_entropy_codes(m.ac_h, m.ac_depths.data()));
+    m.ac_histogram_size = static_cast<int>(compute_entropy_codes(m.ac_h, m.ac_depths.data(), sfm_ncomp_));
     const int base_size = m.header_size + m.dc_size + m.ac_histogram_size +
                           static_cast<int>(entropy_coded_bytes(m.ac_h, m.ac_depths.data()));
     int prev_size = base_size;
@@ -1177,7 +1189,7 @@ class Search {
         }
         const size_t encoded = encoded_size(m.ac_h);
         logf("Iter %2d: %s(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
-             st_->iterations, "f111111", 7, direction > 0 ? "up" : "down", static_cast<int>(out.consumed),
+             st_->iterations, "f111111", yuv420_gray_ ? 1 : 7, direction > 0 ? "up" : "down", static_cast<int>(out.consumed),
              order_size, out.changed_blocks, blocks_to_change, num_blocks, out.val_threshold, encoded,
              100.0 - (100.0 * out.est_jpg_size) / encoded);
         if (kOverlap) compare_end(); else compare();
@@ -1226,6 +1238,8 @@ class Search {
     explicit Tick(double* a) : acc(a), t0(Clock::now()) {}
     ~Tick() { *acc += ms_since(t0); }
   };
+  bool yuv420_gray_ = false;   // see set_yuv420_gray()
+  int sfm_ncomp_ = 3;          // jpg.components.size() in SelectFrequencyMasking (g/processor.cc:583)
   bool device_done_ = false;   // the current iteration took the device path
   bool weights_queued_ = false;  // block weights + order statistics of the next iteration are on the device
   int queued_direction_ = 0;
@@ -1353,10 +1367,12 @@ bool process_resident_impl(const SearchParams& params, ImageContext* ctx, const 
   const long long h2d0 = h2d_bytes_total(), d2h0 = d2h_bytes_total();
   ctx->prepare();
   const int w = ctx->width(), h = ctx->height();
-  // YUV420 (g/processor.cc:847-877) is not built.  The reference only goes there when the image is
-  // large enough for Butteraugli (:832-838) and force_420 is set, or try_420 is set and the image
-  // is not grayscale (IsGrayscale :782); everything else takes the 4:4:4 path below unchanged.
-  if (w >= 32 && h >= 32 && (params.force_420 || (params.try_420 && !is_grayscale(ctx)))) {
+  // YUV420 (g/processor.cc:847-877) is not built.  The reference only downsamples when the image is
+  // large enough for Butteraugli (:832-838), not grayscale (IsGrayscale :782, OutputImage::Downsample
+  // g/output_image.cc:305), and force_420 or try_420 is set.  A tiny image ignores the flags, a
+  // grayscale image ignores try_420 and runs force_420 as a one-component pass (set_yuv420_gray).
+  const bool gray = (params.force_420 || params.try_420) ? is_grayscale(ctx) : false;
+  if (w >= 32 && h >= 32 && (params.force_420 || params.try_420) && !gray) {
     *err = "guetzli_b200: YUV420 is outside the B200 hot path (DESIGN.md)\n";
     fputs(err->c_str(), stderr);
     return false;
@@ -1386,6 +1402,7 @@ bool process_resident_impl(const SearchParams& params, ImageContext* ctx, const 
     }
   } else {
     Search search(params, ctx, log, log_user, st);
+    if (params.force_420 && gray) search.set_yuv420_gray();
     if (src) {
       search.set_jpeg_source(src->q_in, &src->layout, meta);
     } else {

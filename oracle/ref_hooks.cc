@@ -166,6 +166,8 @@ int gref_process_jpeg(const uint8_t* jpeg, size_t len, float butteraugli_target,
   guetzli::Params params;
   params.butteraugli_target = butteraugli_target;
   params.clear_metadata = clear_metadata != 0;
+  params.try_420 = g_try_420 != 0;
+  params.force_420 = g_force_420 != 0;
   guetzli::ProcessStats stats;
   std::string dbg;
   if (trace) stats.debug_output = &dbg;

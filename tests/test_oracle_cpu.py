@@ -209,14 +209,20 @@ def test_port_device_save_jpeg(port_lib, ref, h, w, seed):
     parity.check_device_save_jpeg(port_lib, ref, synth.gradnoise(h, w, seed), seed)
 
 
-def test_420_flags_where_the_reference_stays_on_444(port_lib, ref):
-    """Params::try_420 on a grayscale image (IsGrayscale, processor.cc:782,846) and try_420 / force_420 on an
-    image too small for Butteraugli (:832-838) never reach the YUV420 code of the reference: same bytes and
-    trace as the reference run with the same flags."""
+def test_420_flags_where_the_reference_does_not_downsample(port_lib, ref):
+    """Params::try_420 on a grayscale image (IsGrayscale, processor.cc:782,846), try_420 / force_420 on an
+    image too small for Butteraugli (:832-838) and force_420 on a grayscale image (nothing to downsample,
+    output_image.cc:305) never subsample anything in the reference: same bytes and trace as the reference
+    run with the same flags."""
     rl = ref.lib()
     cases = [(parity.gray(64, 64, 9), 90, dict(try_420=True)),
              (synth.gradnoise(20, 40, 5), 95, dict(force_420=True)),
-             (synth.gradnoise(20, 40, 5), 95, dict(try_420=True))]
+             (synth.gradnoise(20, 40, 5), 95, dict(try_420=True)),
+             # force_420 on a grayscale image: the YUV420 pass with nothing to downsample (one-component
+             # JPEGData, quant search from score 0, masking of component 0 with a single AC histogram)
+             (parity.gray(64, 64, 9), 90, dict(force_420=True)),
+             (parity.gray(48, 72, 3), 95, dict(force_420=True, try_420=True)),
+             (np.full((40, 40, 3), 77, dtype=np.uint8), 95, dict(force_420=True))]
     try:
         for rgb, quality, flags in cases:
             rl.gref_set_420(int(flags.get("try_420", False)), int(flags.get("force_420", False)))
