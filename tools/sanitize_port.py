@@ -52,3 +52,26 @@ for world in (2, 3):
     ok, j = gb.process_tiled_threads(p, img, 80, 96, world, lib=lib)
     assert ok and j == j1, world
 print("strip mode ok", flush=True)
+# the size pass / file assembly as a call of its own on adversarial coefficient patterns, the
+# Huffman builder on skewed histograms, force_420 on a grayscale image
+import reflib  # noqa: E402
+
+if reflib.available():
+    parity.check_device_save_jpeg(lib, reflib, synth.gradnoise(40, 33, 2), 2)
+    print("device save_jpeg ok", flush=True)
+import ctypes as C  # noqa: E402
+
+lib.gb200_debug_huffman_depths.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+lib.gb200_debug_huffman_depths.restype = None
+for t in range(300):
+    counts = (1 + 4_000_000 * rng.random(257) ** 8).astype(np.uint32)
+    counts[rng.random(257) < 0.3] = 0
+    counts[256] = 1
+    depth = np.zeros(257, dtype=np.uint8)
+    lib.gb200_debug_huffman_depths(counts.ctypes.data, 257, 16, depth.ctypes.data)
+    assert depth.max() <= 16
+print("huffman ok", flush=True)
+ok, _ = gb.process(gb.Params(butteraugli_target=gb.butteraugli_score_for_quality(90, lib=lib), force_420=True), None,
+                   parity.gray(48, 40, 3), 40, 48, lib=lib)
+assert ok
+print("force_420 on a grayscale image ok", flush=True)
