@@ -66,6 +66,8 @@ def main():
         if not same:
             bad += 1
             print("MISMATCH", info, flush=True)
+        if (seed - first + 1) % 25 == 0:
+            print(f"... {seed - first + 1} cases, {bad} mismatches", flush=True)
     print(f"{count} cases from seed {first}: {bad} mismatches")
     return 1 if bad else 0
 
