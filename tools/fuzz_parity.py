@@ -16,7 +16,8 @@ import reflib  # noqa: E402
 
 
 def random_image(rng):
-    h, w = int(rng.integers(32, 97)), int(rng.integers(32, 97))
+    top = int(os.environ.get("FUZZ_MAX_DIM", "96")) + 1  # larger images reach the device half of the walk more often
+    h, w = int(rng.integers(32, top)), int(rng.integers(32, top))
     kind = int(rng.integers(0, 7))
     yy, xx = np.mgrid[0:h, 0:w]
     if kind == 0:
