@@ -2,7 +2,9 @@
 """Differential run of guetzli::Process(RGB) -- CPU port of the product's code against the unmodified
 reference -- on random small images, qualities and zeroing parameters: JPEG bytes and --verbose trace must
 be identical.  Test infrastructure (needs oracle/_ref and oracle/_build).
-usage: tools/fuzz_parity.py [first_seed] [count]"""
+usage: tools/fuzz_parity.py [first_seed] [count]
+environment: FUZZ_MAX_DIM (largest side, default 96), FUZZ_TILED=1 (also the strip mode over 2-6 thread ranks),
+GB200_WALK=device / GB200_DEVICE_ORDER=1 (force the device half of the walk / the device replay of std::sort)"""
 import os
 import sys
 
@@ -53,6 +55,10 @@ def one(seed, port):
                   zeroing_greedy_lookahead=lookahead, new_zeroing_model=new_model)
     ok, jpeg = gb.process(p, st, rgb, w, h, lib=port)
     same = ok == rok and jpeg == rjpeg and "".join(st.debug_output) == rtrace
+    if os.environ.get("FUZZ_TILED"):  # the row-strip mode (thread ranks) must give the same bytes
+        world = int(rng.integers(2, 7))
+        tok, tjpeg = gb.process_tiled_threads(p, rgb, w, h, world, lib=port)
+        same = same and tok == ok and tjpeg == jpeg
     return same, dict(seed=seed, kind=kind, h=h, w=w, quality=quality, lookahead=lookahead, new_model=new_model,
                       iterations=st.counters.get("number of iterations"))
 
